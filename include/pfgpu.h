@@ -1,0 +1,191 @@
+/*
+ * pfgpu.h -- C ABI of libpfgpu: the B200 (sm_100a) implementation of PhageFilter's `query`
+ * hot path.  This is the drop-in boundary: plain pointers and sizes, no C++ / torch types.
+ *
+ * The reference (Dreycey/PhageFilter, one Rust binary crate) has no FFI of its own; the seam
+ * is the one `src/main.rs` already uses around the query loop.  Each entry point below cites
+ * the reference interface it replaces (file:line relative to the reference root).  The Rust
+ * binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns PF_OK (0) or a non-zero pf_status; pf_last_error() gives a
+ *     thread-local message.  Nothing unwinds across the boundary.
+ *   - one pf_db per GPU; calls on one handle are serialised by the caller (the reference
+ *     calls query_batch serially from the main thread, main.rs:337-342).
+ *   - the caller owns its input buffers; the library owns device memory and every array it
+ *     returns (valid until the next call on the same handle).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PFGPU_H
+#define PFGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pf_status {
+    PF_OK = 0,
+    PF_ERR_ARG = 1,     /* bad argument */
+    PF_ERR_IO = 2,      /* file missing / unreadable (reference: panic in BloomTree::load, bloom_tree.rs:366-375) */
+    PF_ERR_FORMAT = 3,  /* tree.bin / .bf does not decode (reference: panic, bloom_filter.rs:163-168) */
+    PF_ERR_CUDA = 4,    /* CUDA runtime error or no device */
+    PF_ERR_NOMEM = 5,   /* host or device allocation failed (frontier too large: split the block) */
+    PF_ERR_NCCL = 6,
+    PF_ERR_STATE = 7
+} pf_status;
+
+const char *pf_last_error(void);
+/* library version string, e.g. "pfgpu 0.1 sm_100a" */
+const char *pf_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Database handle: flattened, level-ordered, device-resident gSBT.
+ * Replaces BloomTree::load (bloom_tree.rs:364-386), BloomTree::prune_tree (:302-330) and the
+ * lazily loading BFLruCache (cache.rs:38-77): every distinct `.bf` is decoded once and kept
+ * in HBM; nodes that name the same file share one filter.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pf_db pf_db;
+
+typedef struct pf_db_info_t {
+    uint64_t kmer_size;        /* BloomTree.kmer_size */
+    uint64_t num_bits;         /* m = bits.len() of every filter */
+    uint64_t words_per_filter; /* u64 words per filter in HBM (padded to 128 B) */
+    uint64_t n_nodes;          /* after pruning */
+    uint64_t n_leaves;         /* after pruning */
+    uint64_t n_filters;        /* distinct .bf files resident */
+    uint64_t n_levels;         /* tree depth + 1 */
+    uint64_t filter_bytes;     /* HBM bytes held by filters */
+    uint64_t seed1, seed2;     /* hash_states (bloom_tree.rs:46-47) */
+    uint32_t num_hashes;       /* K */
+    uint32_t largest_genome;
+    float false_pos_rate;
+    int32_t device;
+    int32_t hash_rot;          /* FxHasher::finish rotate in use (26 = rustc-hash 2.1.1) */
+    int32_t fast_path;         /* 1 if the 2-bit register path covers this k (17..32) */
+} pf_db_info_t;
+
+/* search_depth < 0: no pruning (main.rs:293-299 passes Some(depth)). */
+int pf_db_open(const char *db_path, int device, int64_t search_depth, pf_db **out);
+int pf_db_info(const pf_db *db, pf_db_info_t *out);
+/* tax_id of the leaf with left-first DFS index `dfs_leaf` (query.rs:197-218 order). */
+const char *pf_db_leaf_id(const pf_db *db, uint64_t dfs_leaf);
+/* rustc-hash's finish() rotate differs between crate versions; default 26. */
+int pf_db_set_hash_rot(pf_db *db, int rot);
+/* Self-certifying known-answer test: rebuild leaf `dfs_leaf` from its genome with rot in {26,20}
+ * and compare with the stored bits.  *rot_out = matching rotate, or -1 if neither matches. */
+int pf_db_detect_hash_rot(pf_db *db, uint64_t dfs_leaf, const uint8_t *genome, uint64_t len, int *rot_out);
+void pf_db_close(pf_db *db);
+
+/* ------------------------------------------------------------------------------------------
+ * Read batches.  Replaces DNASequence.kmers (file_parser.rs:135-155): k-mers are never
+ * materialised; reads travel as 2-bit codes (A=0,C=1,G=2,T=3; base j of a read sits at bits
+ * [2j,2j+2) of its little-endian bit stream, 16 bases per uint32 word) and the canonical
+ * k-mer bytes the reference hashes are re-created in registers.  A read holding any byte other
+ * than upper-case A/C/G/T is an *exception read*: its raw bytes travel verbatim and take the
+ * byte-exact slow path (the reference hashes raw bytes, file_parser.rs:135-148).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pf_read_batch {
+    uint32_t n_reads;
+    uint32_t n_exc;            /* number of exception reads */
+    const uint32_t *lengths;   /* [n_reads] bases per read */
+    const uint64_t *word_off;  /* [n_reads] first word of each read in `packed`; always even */
+    const uint32_t *packed;    /* [n_words] 2-bit codes; must be followed by >= 4 readable pad words */
+    uint64_t n_words;          /* including the trailing pad */
+    const uint32_t *exc_index; /* [n_reads] index into exc_off for exception reads, 0xFFFFFFFF otherwise; NULL if n_exc==0 */
+    const uint64_t *exc_off;   /* [n_exc+1] byte offsets into exc_bytes */
+    const uint8_t *exc_bytes;  /* raw bytes of the exception reads */
+} pf_read_batch;
+
+/* Host-side packer from raw ASCII reads (seqs concatenated, offs[n_reads+1]) into pinned memory. */
+typedef struct pf_packed pf_packed;
+int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, pf_packed **out);
+const pf_read_batch *pf_packed_batch(const pf_packed *p);
+void pf_packed_free(pf_packed *p);
+void *pf_alloc_pinned(size_t bytes);
+void pf_free_pinned(void *p);
+
+/* Per-read matched leaves of one block: CSR over the block's reads; leaves are DFS leaf
+ * indices, ascending within a read.  Replaces ResultMap (result_map.rs:9-46). */
+typedef struct pf_hits {
+    uint64_t n_hits;
+    const uint64_t *read_off; /* [n_reads+1] */
+    const uint32_t *leaf;     /* [n_hits] */
+} pf_hits;
+
+/* query::query_batch (query.rs:66-82) for one block: H2D copy of the batch, level-synchronous
+ * descent on the GPU, leaf counters accumulated in the handle (mapped_reads, query.rs:143),
+ * and -- if want_hits -- the (read -> leaves) map copied back.  threshold is f32 and the pass
+ * bound is ceilf(threshold * (float)n_kmers) exactly as query.rs:48. */
+int pf_query_block(pf_db *db, const pf_read_batch *in, float threshold, int want_hits, pf_hits *out);
+
+/* Same query on a batch already resident in HBM (used to time the device path alone). */
+typedef struct pf_dev_batch pf_dev_batch;
+int pf_batch_upload(pf_db *db, const pf_read_batch *in, pf_dev_batch **out);
+int pf_query_device(pf_db *db, pf_dev_batch *batch, float threshold, int want_hits, pf_hits *out);
+void pf_batch_free(pf_db *db, pf_dev_batch *batch);
+
+/* Leaf counters: BloomNode.mapped_reads in DFS leaf order (query.rs:197-218). */
+int pf_leaf_counts(pf_db *db, uint64_t *counts /* [n_leaves] */);
+int pf_reset_counts(pf_db *db);
+/* query::save_leaf_counts (query.rs:173-183): "{id},{count}\n" for count > 0. */
+int pf_save_leaf_counts(pf_db *db, const char *csv_path);
+
+/* Work / timing counters since the last pf_reset_stats. */
+typedef struct pf_stats_t {
+    uint64_t blocks;          /* pf_query_* calls */
+    uint64_t reads;
+    uint64_t pairs;           /* (read,node) pairs evaluated */
+    uint64_t probes_issued;   /* bloom bit probes issued by the kernel */
+    uint64_t levels;          /* tree levels traversed */
+    uint64_t probe_launches;  /* launches of the probe kernel */
+    uint64_t other_launches;  /* init / scan / scatter / pack kernels */
+    uint64_t h2d_bytes, d2h_bytes;
+    double probe_kernel_ms;   /* CUDA-event time summed over probe launches */
+    double device_ms;         /* CUDA-event time of the query calls, first launch to last */
+} pf_stats_t;
+int pf_get_stats(pf_db *db, pf_stats_t *out);
+int pf_reset_stats(pf_db *db);
+/* 0 (default): read-level early exit on.  1: reference-faithful probing -- every k-mer of every
+ * pair is probed until its first clear bit (probes_issued then equals the reference's count). */
+int pf_db_set_exhaustive(pf_db *db, int on);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: reads are sharded by rank, every rank holds a replica of the tree, and the
+ * per-leaf counters are combined with ONE ncclAllReduce(sum, u64[n_leaves]).
+ * The 128-byte id is created on rank 0 and handed to the other ranks by the host.
+ * ---------------------------------------------------------------------------------------- */
+int pf_nccl_unique_id(void *id128);
+int pf_comm_init(pf_db *db, int nranks, int rank, const void *id128);
+int pf_allreduce_counts(pf_db *db);
+
+/* ------------------------------------------------------------------------------------------
+ * Database builder on the GPU (the `build`/`add` side the query consumes):
+ * BloomTree::new (bloom_tree.rs:100-119), ::insert (:128-145), ::save (:339-355).
+ * Writes the reference's on-disk format (tree.bin + one .bf per node).
+ * name_mode 0: "Internal_Node_<counter>"; 1: "Internal_Node_<u16>" from splitmix64(name_seed),
+ * redrawn until unused (bloom_tree.rs:232-234 draws a random u16).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pf_builder pf_builder;
+int pf_builder_create(uint64_t kmer_size, float false_pos_rate, uint32_t largest_genome, uint64_t seed1,
+                      uint64_t seed2, int device, int name_mode, uint64_t name_seed, pf_builder **out);
+int pf_builder_set_hash_rot(pf_builder *b, int rot);
+int pf_builder_insert(pf_builder *b, const char *id, const uint8_t *seq, uint64_t len);
+int pf_builder_save(pf_builder *b, const char *db_path);
+void pf_builder_free(pf_builder *b);
+/* filter geometry in f32 (bloom_filter.rs:342-357) */
+uint64_t pf_needed_bits(float false_pos_rate, uint32_t num_items);
+uint32_t pf_optimal_num_hashes(uint64_t num_bits, uint32_t num_items);
+
+/* ------------------------------------------------------------------------------------------
+ * Roofline micro-benchmark: all SMs issue independent random 32-byte-sector loads over a
+ * working set of `bytes` (1.8 MB -> L2-resident filter; >= L2 size -> HBM).  Reports sectors/s.
+ * ---------------------------------------------------------------------------------------- */
+int pf_microbench_sectors(int device, uint64_t bytes, int iters, double *sectors_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFGPU_H */

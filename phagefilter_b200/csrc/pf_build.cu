@@ -1,0 +1,424 @@
+// pf_build.cu -- GPU database builder producing the reference's on-disk format.
+//
+//   BloomTree::new            bloom_tree.rs:100-119     pf_builder_create
+//   BloomTree::insert         bloom_tree.rs:128-145     pf_builder_insert
+//     init_leaf_node          bloom_tree.rs:154-170     insert_kernel (canonical k-mers -> atomicOr)
+//     add_to_tree             bloom_tree.rs:187-214     greedy descent: union + two Hamming distances
+//     init_internal_node      bloom_tree.rs:226-246
+//   BloomFilter::union        bloom_filter.rs:275-278   union_kernel
+//   BloomFilter::distance     bloom_filter.rs:142-150   distance2_kernel (popcount of xor)
+//   BloomTree::save           bloom_tree.rs:339-355     pf_builder_save (tree.bin + one .bf per node)
+#include <sys/stat.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pf_common.h"
+#include "pf_format.h"
+#include "pf_hash.cuh"
+
+namespace pf {
+
+// One thread per k-mer start; byte-exact canonicalisation and hashing on the raw genome bytes.
+__global__ void insert_kernel(const uint8_t *__restrict__ seq, uint64_t n_k, HashParams hp, uint32_t *filt) {
+    for (uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < n_k;
+         pos += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t *p = seq + pos;
+        const uint64_t hb = canonical_hash_bytes([&](uint32_t j) { return p[j]; }, hp.k);
+        const uint64_t h1 = fx_finish(hp.c1, hb, hp.rot), h2 = fx_finish(hp.c2, hb, hp.rot);
+        uint64_t g = h1;
+        for (uint32_t i = 0; i < hp.K; ++i) {
+            const uint64_t idx = mod_any(g, hp.m, hp.M);
+            atomicOr(filt + (idx >> 5), 1u << (idx & 31u));
+            g = i == 0 ? h2 : (i == 1 ? (h1 + 2ULL) * h2 : g + h2);
+        }
+    }
+}
+
+__global__ void union_kernel(uint64_t *__restrict__ dst, const uint64_t *__restrict__ src, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] |= src[i];
+}
+
+// out[0] += hamming(a, x), out[1] += hamming(b, x)
+__global__ void distance2_kernel(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b,
+                                 const uint64_t *__restrict__ x, uint64_t n, unsigned long long *out) {
+    unsigned long long da = 0, db = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = x[i];
+        da += __popcll(a[i] ^ v);
+        db += __popcll(b[i] ^ v);
+    }
+    for (int o = 16; o; o >>= 1) {
+        da += __shfl_xor_sync(0xFFFFFFFFu, da, o);
+        db += __shfl_xor_sync(0xFFFFFFFFu, db, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (da) atomicAdd(out, da);
+        if (db) atomicAdd(out + 1, db);
+    }
+}
+
+__global__ void diff_kernel(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, uint64_t n,
+                            unsigned long long *out) {
+    unsigned long long d = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        d += a[i] != b[i];
+    if (d) atomicAdd(out, d);
+}
+
+// Zero d_filter[0..wpf) and insert every canonical k-mer of the genome (init_leaf_node).
+int build_leaf_filter(const uint8_t *h_seq, uint64_t len, const HashParams &hp, uint64_t *d_filter, uint64_t wpf,
+                      cudaStream_t s) {
+    PF_CUDA_OK(cudaMemsetAsync(d_filter, 0, wpf * 8, s));
+    const uint64_t k = hp.k;
+    const uint64_t n_k = (k == 0 || k > len) ? 0 : len - k + 1;  // file_parser.rs:136-139
+    if (n_k == 0) return PF_OK;
+    uint8_t *d_seq = nullptr;
+    PF_CUDA_OK(cudaMalloc(&d_seq, len));
+    cudaError_t e = cudaMemcpyAsync(d_seq, h_seq, len, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        const int grid = (int)std::min<uint64_t>((n_k + 255) / 256, 148 * 16);
+        insert_kernel<<<grid, 256, 0, s>>>(d_seq, n_k, hp, reinterpret_cast<uint32_t *>(d_filter));
+        e = cudaGetLastError();
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(d_seq);
+    PF_CUDA_OK(e);
+    return PF_OK;
+}
+
+int filters_equal(const uint64_t *a, const uint64_t *b, uint64_t n_words, cudaStream_t s, bool *equal) {
+    unsigned long long *d = nullptr, h = 0;
+    PF_CUDA_OK(cudaMalloc(&d, 8));
+    cudaMemsetAsync(d, 0, 8, s);
+    diff_kernel<<<148 * 4, 256, 0, s>>>(a, b, n_words, d);
+    cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    PF_CUDA_OK(e);
+    *equal = h == 0;
+    return PF_OK;
+}
+
+// filter geometry in f32, exactly as bloom_filter.rs:342-357 (f32::ln -> logf, f32::round -> roundf,
+// `as usize` / `as u32` saturating).  volatile keeps every intermediate in f32.
+static uint64_t needed_bits(float fpr, uint32_t n) {
+    volatile float ln22 = 0.693147180559945309417232121458176568f * 0.693147180559945309417232121458176568f;
+    volatile float inv = 1.0f / fpr;
+    volatile float l = logf(inv);
+    volatile float q = l / ln22;
+    volatile float v = (float)n * q;
+    float r = roundf(v);
+    if (!(r > 0.0f)) return 0;
+    if (r >= 18446744073709551616.0f) return ~0ULL;
+    return (uint64_t)r;
+}
+static uint32_t optimal_num_hashes(uint64_t bits, uint32_t n) {
+    volatile float a = (float)bits / (float)n;
+    volatile float b = a * 0.693147180559945309417232121458176568f;
+    float r = roundf(b);
+    uint32_t k = !(r > 0.0f) ? 0u : (r >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)r);
+    return k < 2 ? 2 : (k > 200 ? 200 : k);
+}
+
+static uint64_t splitmix64(uint64_t &s) {
+    uint64_t z = (s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+struct pf_builder {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    HostTree tree;                    // nodes in creation order; root tracked in tree.root
+    std::vector<uint64_t *> filters;  // device filter per node (index = node index)
+    uint64_t m = 0, n_words = 0, wpf = 0;
+    uint32_t K = 0;
+    HashParams hp{};
+    int name_mode = 0;
+    uint64_t name_state = 0, name_counter = 0;
+    std::vector<uint8_t> name_used;
+    unsigned long long *d_dist = nullptr, *h_dist = nullptr;
+};
+
+static int new_node(pf_builder *b, const std::string &id, int32_t *out) {
+    uint64_t *f = nullptr;
+    cudaError_t e = cudaMalloc(&f, b->wpf * 8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cannot allocate filter %zu (%.1f MB each)", b->filters.size(), b->wpf * 8 / 1e6);
+        return PF_ERR_NOMEM;
+    }
+    PF_CUDA_OK(cudaMemsetAsync(f, 0, b->wpf * 8, b->stream));
+    HostNode n;
+    n.bf_path = id + ".bf";  // make_bloom_node, bloom_tree.rs:281
+    n.has_tax = true;
+    n.tax_id = id;
+    b->tree.nodes.push_back(n);
+    b->filters.push_back(f);
+    *out = (int32_t)b->tree.nodes.size() - 1;
+    return PF_OK;
+}
+
+extern "C" {
+
+uint64_t pf_needed_bits(float fpr, uint32_t n) { return needed_bits(fpr, n); }
+uint32_t pf_optimal_num_hashes(uint64_t bits, uint32_t n) { return optimal_num_hashes(bits, n); }
+
+int pf_builder_create(uint64_t kmer_size, float fpr, uint32_t largest_genome, uint64_t seed1, uint64_t seed2, int device,
+                      int name_mode, uint64_t name_seed, pf_builder **out) {
+    if (!out) return PF_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libpfgpu has no CPU fallback");
+        return PF_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("device %d out of range", device);
+        return PF_ERR_ARG;
+    }
+    pf_builder *b = new pf_builder();
+    b->device = device;
+    b->m = needed_bits(fpr, largest_genome);  // with_rate, bloom_filter.rs:229-240
+    b->K = optimal_num_hashes(b->m, largest_genome);
+    if (b->m == 0) {
+        delete b;
+        set_error("filter with zero bits");
+        return PF_ERR_ARG;
+    }
+    b->n_words = (b->m + 63) / 64;
+    b->wpf = (b->n_words + 15) / 16 * 16;
+    b->tree.false_pos_rate = fpr;
+    b->tree.largest_genome = largest_genome;
+    b->tree.kmer_size = kmer_size;
+    b->tree.seed1 = seed1;
+    b->tree.seed2 = seed2;
+    b->hp = make_hash_params(seed1, seed2, kmer_size, b->m, b->K, 26);
+    b->name_mode = name_mode;
+    b->name_state = name_seed;
+    if (name_mode == 1) b->name_used.assign(65536, 0);
+    cudaSetDevice(device);
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&b->d_dist, 16) != cudaSuccess || cudaMallocHost(&b->h_dist, 16) != cudaSuccess) {
+        set_error("CUDA error creating builder: %s", cudaGetErrorString(cudaGetLastError()));
+        delete b;
+        return PF_ERR_CUDA;
+    }
+    *out = b;
+    return PF_OK;
+}
+
+int pf_builder_set_hash_rot(pf_builder *b, int rot) {
+    if (!b || rot < 0 || rot > 63) return PF_ERR_ARG;
+    b->hp.rot = (uint32_t)rot;
+    return PF_OK;
+}
+
+int pf_builder_insert(pf_builder *b, const char *id, const uint8_t *seq, uint64_t len) {
+    if (!b || !id || (!seq && len)) {
+        set_error("pf_builder_insert: null argument");
+        return PF_ERR_ARG;
+    }
+    PF_CUDA_OK(cudaSetDevice(b->device));
+    cudaStream_t s = b->stream;
+    int32_t leaf;
+    int rc = new_node(b, id, &leaf);
+    if (rc != PF_OK) return rc;
+    if ((rc = build_leaf_filter(seq, len, b->hp, b->filters[leaf], b->wpf, s))) return rc;
+    if (b->tree.root < 0) {
+        b->tree.root = leaf;
+        return PF_OK;
+    }
+    const int grid = 148 * 4;
+    // add_to_tree (bloom_tree.rs:187-214), iteratively: `link` is where the current subtree hangs
+    int32_t cur = b->tree.root, parent = -1;
+    bool parent_left = false;
+    for (;;) {
+        HostNode &cn = b->tree.nodes[cur];
+        if (cn.left >= 0 && cn.right >= 0) {
+            union_kernel<<<grid, 256, 0, s>>>(b->filters[cur], b->filters[leaf], b->wpf);  // :194
+            PF_CUDA_OK(cudaMemsetAsync(b->d_dist, 0, 16, s));
+            distance2_kernel<<<grid, 256, 0, s>>>(b->filters[cn.right], b->filters[cn.left], b->filters[leaf], b->wpf,
+                                                  b->d_dist);
+            PF_CUDA_OK(cudaMemcpyAsync(b->h_dist, b->d_dist, 16, cudaMemcpyDeviceToHost, s));
+            PF_CUDA_OK(cudaStreamSynchronize(s));
+            const unsigned long long right_d = b->h_dist[0], left_d = b->h_dist[1];
+            parent = cur;
+            if (right_d < left_d) {  // :200-202
+                parent_left = false;
+                cur = cn.right;
+            } else {  // :203-206 (ties go left)
+                parent_left = true;
+                cur = cn.left;
+            }
+        } else if (cn.left < 0 && cn.right < 0) {
+            // init_internal_node (bloom_tree.rs:226-246)
+            char name[64];
+            if (b->name_mode == 1) {
+                uint16_t n2;
+                do {
+                    n2 = (uint16_t)splitmix64(b->name_state);
+                } while (b->name_used[n2] && b->name_counter < 65536);
+                b->name_used[n2] = 1;
+                snprintf(name, sizeof name, "Internal_Node_%u", (unsigned)n2);
+            } else {
+                snprintf(name, sizeof name, "Internal_Node_%llu", (unsigned long long)b->name_counter);
+            }
+            b->name_counter++;
+            int32_t in;
+            if ((rc = new_node(b, name, &in))) return rc;
+            union_kernel<<<grid, 256, 0, s>>>(b->filters[in], b->filters[leaf], b->wpf);  // :237
+            union_kernel<<<grid, 256, 0, s>>>(b->filters[in], b->filters[cur], b->wpf);   // :238
+            b->tree.nodes[in].left = cur;    // :242 existing node on the left
+            b->tree.nodes[in].right = leaf;  // :243 new node on the right
+            if (parent < 0) b->tree.root = in;
+            else if (parent_left) b->tree.nodes[parent].left = in;
+            else b->tree.nodes[parent].right = in;
+            break;
+        } else {
+            set_error("Node with only one child encountered - should not happen.");
+            return PF_ERR_STATE;
+        }
+    }
+    PF_CUDA_OK(cudaStreamSynchronize(s));
+    PF_CUDA_OK(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_builder_save(pf_builder *b, const char *db_path) {
+    if (!b || !db_path) return PF_ERR_ARG;
+    PF_CUDA_OK(cudaSetDevice(b->device));
+    mkdir(db_path, 0777);
+    std::string dir(db_path), err;
+    // tree.bin wants pre-order with inline children: re-index from creation order
+    HostTree out = b->tree;
+    out.nodes.clear();
+    out.root = -1;
+    if (b->tree.root >= 0) {
+        std::vector<int32_t> map(b->tree.nodes.size(), -1), st{b->tree.root};
+        std::vector<int32_t> order;
+        while (!st.empty()) {
+            int32_t u = st.back();
+            st.pop_back();
+            map[u] = (int32_t)order.size();
+            order.push_back(u);
+            if (b->tree.nodes[u].right >= 0) st.push_back(b->tree.nodes[u].right);
+            if (b->tree.nodes[u].left >= 0) st.push_back(b->tree.nodes[u].left);
+        }
+        for (int32_t u : order) {
+            HostNode n = b->tree.nodes[u];
+            n.left = n.left >= 0 ? map[n.left] : -1;
+            n.right = n.right >= 0 ? map[n.right] : -1;
+            out.nodes.push_back(n);
+        }
+        out.root = 0;
+    }
+    if (!write_tree_bin(join_path(dir, "tree.bin"), out, err)) {
+        set_error("%s", err.c_str());
+        return PF_ERR_IO;
+    }
+    uint64_t *stage = nullptr;
+    PF_CUDA_OK(cudaMallocHost(&stage, b->wpf * 8));
+    BfHeader h;
+    h.num_bits = b->m;
+    h.n_words = b->n_words;
+    h.num_hashes = b->K;
+    h.seed1 = b->tree.seed1;
+    h.seed2 = b->tree.seed2;
+    int rc = PF_OK;
+    for (size_t i = 0; i < b->tree.nodes.size() && rc == PF_OK; ++i) {
+        if (cudaMemcpyAsync(stage, b->filters[i], b->wpf * 8, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess ||
+            cudaStreamSynchronize(b->stream) != cudaSuccess) {
+            set_error("CUDA error copying filter: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = PF_ERR_CUDA;
+            break;
+        }
+        const std::string p = join_path(dir, b->tree.nodes[i].bf_path);
+        // Drop writes each filter with file_path = directory.join(name) (bloom_filter.rs:105-117, bloom_tree.rs:282)
+        if (!write_bf(p, h, stage, p, err)) {
+            set_error("%s", err.c_str());
+            rc = PF_ERR_IO;
+        }
+    }
+    cudaFreeHost(stage);
+    return rc;
+}
+
+void pf_builder_free(pf_builder *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    for (auto f : b->filters) cudaFree(f);
+    cudaFree(b->d_dist);
+    if (b->h_dist) cudaFreeHost(b->h_dist);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+// ---- roofline micro-benchmark: independent random 32-byte-sector loads --------------------------
+__global__ void sector_gather_kernel(const uint32_t *__restrict__ buf, uint64_t n_sectors, int iters, uint32_t *sink) {
+    uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9e3779b97f4a7c15ULL + 12345;
+    uint32_t acc = 0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 8 independent loads in flight per thread
+            x ^= x << 13;
+            x ^= x >> 7;
+            x ^= x << 17;
+            const uint64_t sec = (uint64_t)(((unsigned __int128)x * n_sectors) >> 64);
+            acc += __ldg(buf + sec * 8 + (x & 7));
+        }
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
+int pf_microbench_sectors(int device, uint64_t bytes, int iters, double *sectors_per_s) {
+    if (!sectors_per_s || bytes < 32 || iters < 1) return PF_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device");
+        return PF_ERR_CUDA;
+    }
+    PF_CUDA_OK(cudaSetDevice(device));
+    uint32_t *buf = nullptr, *sink = nullptr;
+    const uint64_t n_sectors = bytes / 32;
+    PF_CUDA_OK(cudaMalloc(&buf, n_sectors * 32));
+    PF_CUDA_OK(cudaMalloc(&sink, 4));
+    PF_CUDA_OK(cudaMemset(buf, 0x5a, n_sectors * 32));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = 148 * 8, block = 256;
+    sector_gather_kernel<<<grid, block>>>(buf, n_sectors, 4, sink);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        sector_gather_kernel<<<grid, block>>>(buf, n_sectors, iters, sink);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double rate = (double)grid * block * iters * 8 / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(sink);
+    PF_CUDA_OK(e);
+    *sectors_per_s = best;
+    return PF_OK;
+}
+
+}  // extern "C"

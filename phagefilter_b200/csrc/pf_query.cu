@@ -1,0 +1,860 @@
+// pf_query.cu -- pf_db: flattened device-resident gSBT and the level-synchronous query.
+//
+// Replaces, behind the C ABI of include/pfgpu.h:
+//   BloomTree::load / prune_tree        bloom_tree.rs:364-386, 302-330
+//   BFLruCache::get_filter              cache.rs:56-77      (all filters resident in HBM instead)
+//   query::query_batch / _query_batch   query.rs:66-158
+//   query::save_leaf_counts             query.rs:173-218
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "pf_common.h"
+#include "pf_format.h"
+#include "pf_kernels.cuh"
+
+namespace pf {
+
+static thread_local std::string g_error;
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+template <class T>
+struct DevBuf {  // grow-only device array
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return PF_OK;
+        size_t want = std::max(n, cap + cap / 2);
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            // retry with the exact size before giving up
+            want = n;
+            e = cudaMalloc(&q, want * sizeof(T));
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                set_error("device allocation of %zu bytes failed (frontier too large: use smaller read blocks)",
+                          want * sizeof(T));
+                return PF_ERR_NOMEM;
+            }
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = want;
+        return PF_OK;
+    }
+    // grow while preserving the first `keep` elements (hit lists accumulate across levels)
+    int grow_keep(size_t n, size_t keep, cudaStream_t s) {
+        if (n <= cap) return PF_OK;
+        T *old = p;
+        p = nullptr;
+        size_t old_cap = cap;
+        cap = 0;
+        int rc = ensure(std::max(n, old_cap + old_cap / 2));
+        if (rc != PF_OK) {
+            p = old;
+            cap = old_cap;
+            return rc;
+        }
+        if (old && keep) cudaMemcpyAsync(p, old, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        if (old) {
+            cudaStreamSynchronize(s);
+            cudaFree(old);
+        }
+        return PF_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// pf_build.cu
+int build_leaf_filter(const uint8_t *h_seq, uint64_t len, const HashParams &hp, uint64_t *d_filter, uint64_t wpf,
+                      cudaStream_t s);
+int filters_equal(const uint64_t *a, const uint64_t *b, uint64_t n_words, cudaStream_t s, bool *equal);
+
+}  // namespace pf
+
+using namespace pf;
+
+struct pf_dev_batch {
+    uint32_t n_reads = 0, n_exc = 0;
+    uint64_t n_words = 0, exc_nbytes = 0;
+    DevBuf<uint32_t> lengths, packed, exc_index;
+    DevBuf<uint64_t> word_off, exc_off;
+    DevBuf<uint8_t> exc_bytes;
+    uint64_t bytes = 0;
+    void release() {
+        lengths.release();
+        packed.release();
+        exc_index.release();
+        word_off.release();
+        exc_off.release();
+        exc_bytes.release();
+    }
+};
+
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.h) return PF_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error("NCCL not found: %s", dlerror());
+        return PF_ERR_NCCL;
+    }
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        set_error("NCCL symbols missing");
+        return PF_ERR_NCCL;
+    }
+    g_nccl.h = h;
+    return PF_OK;
+}
+
+struct pf_db {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // host copy of the flattened tree (level order)
+    HostTree tree;
+    std::vector<uint32_t> h_left, h_right, h_slot;
+    std::vector<int32_t> h_leaf;
+    std::vector<int32_t> h_pre;         // level-order id -> index into tree.nodes
+    std::vector<uint32_t> level_start;  // n_levels + 1
+    std::vector<std::string> leaf_ids;  // DFS leaf order
+    uint64_t n_nodes = 0, n_leaves = 0, n_slots = 0, wpf = 0;
+    BfHeader geom;
+    HashParams hp{};
+    int exhaustive = 0;
+    // device tree
+    uint32_t *d_left = nullptr, *d_right = nullptr, *d_slot = nullptr;
+    int32_t *d_leaf = nullptr;
+    uint64_t *d_filters = nullptr;
+    // accumulators and per-block scratch
+    unsigned long long *d_counts = nullptr, *d_blk_counts = nullptr;
+    uint32_t *d_node_pass = nullptr, *d_cursor = nullptr;  // contiguous [2 * n_nodes]
+    unsigned long long *d_next_base = nullptr, *d_hit_base = nullptr;
+    unsigned int *d_work = nullptr;  // one counter per level
+    unsigned long long *d_probes = nullptr;
+    LevelTotals *d_totals = nullptr, *h_totals = nullptr;
+    DevBuf<uint32_t> fr_read[2], fr_node[2], hit_read, hit_leaf;
+    DevBuf<uint8_t> pass;
+    pf_dev_batch own_batch;  // device copy used by pf_query_block
+    // outputs
+    std::vector<uint64_t> out_off;
+    std::vector<uint32_t> out_leaf, tmp_read, tmp_leaf;
+    // timing
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_probe;  // 2 per level
+    pf_stats_t stats{};
+    ncclComm_t comm = nullptr;
+};
+
+static void db_free(pf_db *db) {
+    if (!db) return;
+    cudaSetDevice(db->device);
+    if (db->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(db->comm);
+    cudaFree(db->d_left);
+    cudaFree(db->d_right);
+    cudaFree(db->d_slot);
+    cudaFree(db->d_leaf);
+    cudaFree(db->d_filters);
+    cudaFree(db->d_counts);
+    cudaFree(db->d_blk_counts);
+    cudaFree(db->d_node_pass);
+    cudaFree(db->d_next_base);
+    cudaFree(db->d_hit_base);
+    cudaFree(db->d_work);
+    cudaFree(db->d_probes);
+    cudaFree(db->d_totals);
+    if (db->h_totals) cudaFreeHost(db->h_totals);
+    for (int i = 0; i < 2; i++) {
+        db->fr_read[i].release();
+        db->fr_node[i].release();
+    }
+    db->hit_read.release();
+    db->hit_leaf.release();
+    db->pass.release();
+    db->own_batch.release();
+    if (db->ev_begin) cudaEventDestroy(db->ev_begin);
+    if (db->ev_end) cudaEventDestroy(db->ev_end);
+    for (auto e : db->ev_probe) cudaEventDestroy(e);
+    if (db->stream) cudaStreamDestroy(db->stream);
+    delete db;
+}
+
+// prune_tree (bloom_tree.rs:302-330) + level-order flattening + DFS leaf numbering.
+static void flatten(pf_db *db, int64_t search_depth) {
+    const HostTree &t = db->tree;
+    db->h_left.clear();
+    db->h_right.clear();
+    db->h_slot.clear();
+    db->h_leaf.clear();
+    db->level_start.clear();
+    db->leaf_ids.clear();
+    if (t.root < 0) {
+        db->n_nodes = db->n_leaves = 0;
+        db->level_start.push_back(0);
+        return;
+    }
+    // level-order ids; `keep_children[pre]` is false for nodes cut by the search depth
+    std::vector<int32_t> order;               // level-order -> pre-order index
+    std::vector<uint32_t> depth_of;           // by level-order id
+    std::vector<int32_t> bfs_of(t.nodes.size(), -1);
+    order.push_back(t.root);
+    depth_of.push_back(0);
+    bfs_of[t.root] = 0;
+    db->level_start.push_back(0);
+    for (size_t q = 0; q < order.size(); ++q) {
+        const HostNode &n = t.nodes[order[q]];
+        uint32_t d = depth_of[q];
+        if (q > 0 && d != depth_of[q - 1]) db->level_start.push_back((uint32_t)q);
+        bool cut = search_depth >= 0 && (int64_t)d >= search_depth;
+        if (cut) continue;
+        for (int32_t c : {n.left, n.right}) {
+            if (c < 0) continue;
+            bfs_of[c] = (int32_t)order.size();
+            order.push_back(c);
+            depth_of.push_back(d + 1);
+        }
+    }
+    db->level_start.push_back((uint32_t)order.size());
+    db->n_nodes = order.size();
+    db->h_left.assign(db->n_nodes, NONE32);
+    db->h_right.assign(db->n_nodes, NONE32);
+    db->h_leaf.assign(db->n_nodes, -1);
+    for (size_t q = 0; q < order.size(); ++q) {
+        const HostNode &n = t.nodes[order[q]];
+        bool cut = search_depth >= 0 && (int64_t)depth_of[q] >= search_depth;
+        if (!cut) {
+            if (n.left >= 0) db->h_left[q] = (uint32_t)bfs_of[n.left];
+            if (n.right >= 0) db->h_right[q] = (uint32_t)bfs_of[n.right];
+        }
+    }
+    // left-first DFS leaf order (query.rs:197-218)
+    std::vector<uint32_t> st{0};
+    while (!st.empty()) {
+        uint32_t u = st.back();
+        st.pop_back();
+        if (db->h_left[u] == NONE32 && db->h_right[u] == NONE32) {  // is_leafnode, bloom_tree.rs:416-418
+            db->h_leaf[u] = (int32_t)db->leaf_ids.size();
+            db->leaf_ids.push_back(t.nodes[order[u]].tax_id);
+            continue;
+        }
+        if (db->h_right[u] != NONE32) st.push_back(db->h_right[u]);
+        if (db->h_left[u] != NONE32) st.push_back(db->h_left[u]);
+    }
+    db->n_leaves = db->leaf_ids.size();
+    db->h_pre = order;
+    // filter slots: one per distinct path string (cache.rs keys filters by path)
+    std::map<std::string, uint32_t> slot_of;
+    db->h_slot.resize(db->n_nodes);
+    for (size_t q = 0; q < order.size(); ++q) {
+        const std::string &p = t.nodes[order[q]].bf_path;
+        auto it = slot_of.find(p);
+        if (it == slot_of.end()) it = slot_of.emplace(p, (uint32_t)slot_of.size()).first;
+        db->h_slot[q] = it->second;
+    }
+    db->n_slots = slot_of.size();
+}
+
+template <class T>
+static int upload(T **dst, const std::vector<T> &v, cudaStream_t s) {
+    PF_CUDA_OK(cudaMalloc(dst, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) PF_CUDA_OK(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return PF_OK;
+}
+
+static int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libpfgpu has no CPU fallback");
+        return PF_ERR_CUDA;
+    }
+    if (db->device < 0 || db->device >= ndev) {
+        set_error("device %d out of range (%d devices)", db->device, ndev);
+        return PF_ERR_ARG;
+    }
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    PF_CUDA_OK(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+    PF_CUDA_OK(cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, db->device));
+    std::string err;
+    std::string dir(db_path);
+    if (!read_tree_bin(join_path(dir, "tree.bin"), db->tree, err)) {
+        set_error("%s", err.c_str());
+        return err.rfind("cannot open", 0) == 0 ? PF_ERR_IO : PF_ERR_FORMAT;
+    }
+    flatten(db, search_depth);
+    if (db->n_nodes == 0) {
+        set_error("database has no root node (reference panics in save_leaf_counts, main.rs:374)");
+        return PF_ERR_FORMAT;
+    }
+    // decode every distinct filter once; geometry must be uniform
+    std::vector<std::string> slot_path(db->n_slots);
+    for (size_t q = 0; q < db->n_nodes; ++q) slot_path[db->h_slot[q]] = db->tree.nodes[db->h_pre[q]].bf_path;
+    uint64_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t staged[2] = {nullptr, nullptr};
+    BfHeader first{};
+    if (!read_bf_header(join_path(dir, slot_path[0]), first, err)) {
+        set_error("%s", err.c_str());
+        return err.rfind("Failed to open", 0) == 0 ? PF_ERR_IO : PF_ERR_FORMAT;
+    }
+    if (first.num_bits == 0) {
+        set_error("filter with zero bits (the reference would divide by zero in contains)");
+        return PF_ERR_FORMAT;
+    }
+    db->geom = first;
+    db->wpf = (first.n_words + 15) / 16 * 16;  // 128-byte aligned slots
+    size_t total_words = (size_t)db->n_slots * db->wpf;
+    cudaError_t ce = cudaMalloc(&db->d_filters, total_words * 8);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cannot hold %zu filters (%.1f GB) in device memory", (size_t)db->n_slots, total_words * 8 / 1e9);
+        return PF_ERR_NOMEM;
+    }
+    for (int i = 0; i < 2; i++) {
+        PF_CUDA_OK(cudaMallocHost(&stage[i], db->wpf * 8));
+        PF_CUDA_OK(cudaEventCreateWithFlags(&staged[i], cudaEventDisableTiming));
+    }
+    int rc = PF_OK;
+    for (uint64_t s = 0; s < db->n_slots && rc == PF_OK; ++s) {
+        int b = (int)(s & 1);
+        cudaEventSynchronize(staged[b]);
+        memset(stage[b], 0, db->wpf * 8);
+        BfHeader h;
+        if (!read_bf(join_path(dir, slot_path[s]), h, stage[b], db->wpf, err)) {
+            set_error("%s", err.c_str());
+            rc = err.rfind("Failed to open", 0) == 0 ? PF_ERR_IO : PF_ERR_FORMAT;
+            break;
+        }
+        if (h.num_bits != first.num_bits || h.num_hashes != first.num_hashes || h.seed1 != first.seed1 ||
+            h.seed2 != first.seed2) {
+            set_error("filter %s differs in geometry/seeds from the rest of the database", slot_path[s].c_str());
+            rc = PF_ERR_FORMAT;
+            break;
+        }
+        cudaMemcpyAsync(db->d_filters + s * db->wpf, stage[b], db->wpf * 8, cudaMemcpyHostToDevice, db->stream);
+        cudaEventRecord(staged[b], db->stream);
+    }
+    cudaStreamSynchronize(db->stream);
+    for (int i = 0; i < 2; i++) {
+        cudaFreeHost(stage[i]);
+        cudaEventDestroy(staged[i]);
+    }
+    if (rc != PF_OK) return rc;
+    PF_CUDA_OK(cudaGetLastError());
+
+    db->hp = make_hash_params(first.seed1, first.seed2, db->tree.kmer_size, first.num_bits, first.num_hashes, 26);
+    if ((rc = upload(&db->d_left, db->h_left, db->stream))) return rc;
+    if ((rc = upload(&db->d_right, db->h_right, db->stream))) return rc;
+    if ((rc = upload(&db->d_slot, db->h_slot, db->stream))) return rc;
+    if ((rc = upload(&db->d_leaf, db->h_leaf, db->stream))) return rc;
+    size_t nn = db->n_nodes, nl = std::max<uint64_t>(db->n_leaves, 1), nlev = db->level_start.size();
+    PF_CUDA_OK(cudaMalloc(&db->d_counts, nl * 8));
+    PF_CUDA_OK(cudaMalloc(&db->d_blk_counts, nl * 8));
+    PF_CUDA_OK(cudaMalloc(&db->d_node_pass, 2 * nn * 4));
+    db->d_cursor = db->d_node_pass + nn;
+    PF_CUDA_OK(cudaMalloc(&db->d_next_base, nn * 8));
+    PF_CUDA_OK(cudaMalloc(&db->d_hit_base, nn * 8));
+    PF_CUDA_OK(cudaMalloc(&db->d_work, nlev * 4));
+    PF_CUDA_OK(cudaMalloc(&db->d_probes, 8));
+    PF_CUDA_OK(cudaMalloc(&db->d_totals, sizeof(LevelTotals)));
+    PF_CUDA_OK(cudaMallocHost(&db->h_totals, sizeof(LevelTotals)));
+    PF_CUDA_OK(cudaMemsetAsync(db->d_counts, 0, nl * 8, db->stream));
+    PF_CUDA_OK(cudaEventCreate(&db->ev_begin));
+    PF_CUDA_OK(cudaEventCreate(&db->ev_end));
+    PF_CUDA_OK(cudaStreamSynchronize(db->stream));
+    return PF_OK;
+}
+
+// ---- probe kernel dispatch on k ----------------------------------------------------------------
+template <int KM>
+static void launch_probe_k(const ProbeArgs &a, int grid, cudaStream_t s) {
+    probe_kernel<KM><<<grid, PROBE_THREADS, 0, s>>>(a);
+}
+static bool fast_path_ok(const HashParams &hp) { return hp.k >= 17 && hp.k <= 32 && hp.small_m; }
+static void launch_probe(const ProbeArgs &a, int grid, cudaStream_t s) {
+    if (!fast_path_ok(a.hp)) {
+        launch_probe_k<0>(a, grid, s);
+        return;
+    }
+    switch (a.hp.k) {
+#define PF_CASE(K) \
+    case K:        \
+        launch_probe_k<K>(a, grid, s); \
+        break;
+        PF_CASE(17) PF_CASE(18) PF_CASE(19) PF_CASE(20) PF_CASE(21) PF_CASE(22) PF_CASE(23) PF_CASE(24)
+        PF_CASE(25) PF_CASE(26) PF_CASE(27) PF_CASE(28) PF_CASE(29) PF_CASE(30) PF_CASE(31) PF_CASE(32)
+#undef PF_CASE
+        default:
+            launch_probe_k<0>(a, grid, s);
+    }
+}
+
+static int ensure_events(pf_db *db, size_t n) {
+    while (db->ev_probe.size() < n) {
+        cudaEvent_t e;
+        PF_CUDA_OK(cudaEventCreate(&e));
+        db->ev_probe.push_back(e);
+    }
+    return PF_OK;
+}
+
+// The level-synchronous descent for one resident batch.
+static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, pf_hits *out) {
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    cudaStream_t s = db->stream;
+    const uint32_t n_reads = bt->n_reads;
+    const size_t n_levels = db->level_start.size() - 1;
+    int rc;
+    if (out) *out = pf_hits{};
+    db->out_off.assign((size_t)n_reads + 1, 0);
+    db->out_leaf.clear();
+    if (n_reads == 0) {
+        if (out) out->read_off = db->out_off.data();
+        return PF_OK;
+    }
+    if ((rc = ensure_events(db, 2 * n_levels))) return rc;
+    PF_CUDA_OK(cudaEventRecord(db->ev_begin, s));
+    PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, 2 * db->n_nodes * 4, s));
+    PF_CUDA_OK(cudaMemsetAsync(db->d_work, 0, db->level_start.size() * 4, s));
+    PF_CUDA_OK(cudaMemsetAsync(db->d_blk_counts, 0, std::max<uint64_t>(db->n_leaves, 1) * 8, s));
+    PF_CUDA_OK(cudaMemsetAsync(db->d_probes, 0, 8, s));
+    PF_CUDA_OK(cudaMemsetAsync(db->d_totals, 0, sizeof(LevelTotals), s));
+    if ((rc = db->fr_read[0].ensure(n_reads)) || (rc = db->fr_node[0].ensure(n_reads))) return rc;
+    init_frontier_kernel<<<std::min<uint32_t>((n_reads + 255) / 256, 4096), 256, 0, s>>>(db->fr_read[0].p,
+                                                                                        db->fr_node[0].p, n_reads);
+    uint64_t other_launches = 1, probe_launches = 0, pairs = 0, levels = 0, hits_total = 0, probes = 0;
+    uint64_t n = n_reads, hits_before = 0;
+    int cur = 0;
+    const int grid = db->sm_count * 4;
+    for (size_t l = 0; l < n_levels && n > 0; ++l) {
+        if ((rc = db->pass.ensure(n))) return rc;
+        ProbeArgs a{};
+        a.fr_read = db->fr_read[cur].p;
+        a.fr_node = db->fr_node[cur].p;
+        a.n_pairs = (uint32_t)n;
+        a.lengths = bt->lengths.p;
+        a.word_off = bt->word_off.p;
+        a.packed = bt->packed.p;
+        a.exc_index = bt->n_exc ? bt->exc_index.p : nullptr;
+        a.exc_off = bt->exc_off.p;
+        a.exc_bytes = bt->exc_bytes.p;
+        a.node_slot = db->d_slot;
+        a.filters = db->d_filters;
+        a.words_per_filter = db->wpf;
+        a.pass = db->pass.p;
+        a.node_pass = db->d_node_pass;
+        a.work_ctr = db->d_work + l;
+        a.probes = db->d_probes;
+        a.hp = db->hp;
+        a.threshold = threshold;
+        a.exhaustive = db->exhaustive;
+        PF_CUDA_OK(cudaEventRecord(db->ev_probe[2 * l], s));
+        launch_probe(a, grid, s);
+        PF_CUDA_OK(cudaEventRecord(db->ev_probe[2 * l + 1], s));
+        probe_launches++;
+        pairs += n;
+        levels++;
+        level_scan_kernel<<<1, 1024, 0, s>>>(db->level_start[l], db->level_start[l + 1], db->d_node_pass, db->d_left,
+                                             db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base, db->d_blk_counts,
+                                             db->d_totals, db->d_probes);
+        other_launches++;
+        PF_CUDA_OK(cudaMemcpyAsync(db->h_totals, db->d_totals, sizeof(LevelTotals), cudaMemcpyDeviceToHost, s));
+        PF_CUDA_OK(cudaStreamSynchronize(s));
+        const uint64_t next_n = db->h_totals->next_pairs;
+        hits_total = db->h_totals->hits_total;
+        probes = db->h_totals->probes;
+        if (next_n > 0xFFFFFFF0ULL) {
+            set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
+                      (unsigned long long)next_n);
+            return PF_ERR_NOMEM;
+        }
+        const int nxt = cur ^ 1;
+        if (next_n && ((rc = db->fr_read[nxt].ensure(next_n)) || (rc = db->fr_node[nxt].ensure(next_n)))) return rc;
+        // hits of earlier levels live in the same arrays: grow with copy
+        if (want_hits && hits_total &&
+            ((rc = db->hit_read.grow_keep(hits_total, hits_before, s)) || (rc = db->hit_leaf.grow_keep(hits_total, hits_before, s))))
+            return rc;
+        hits_before = hits_total;
+        scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(
+            db->fr_read[cur].p, db->fr_node[cur].p, db->pass.p, (uint32_t)n, db->d_node_pass, db->d_cursor, db->d_left,
+            db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base, db->fr_read[nxt].p, db->fr_node[nxt].p,
+            db->hit_read.p, db->hit_leaf.p, want_hits);
+        other_launches++;
+        n = next_n;
+        cur = nxt;
+    }
+    add_counts_kernel<<<(uint32_t)((db->n_leaves + 255) / 256), 256, 0, s>>>(db->d_counts, db->d_blk_counts,
+                                                                            (uint32_t)db->n_leaves);
+    other_launches++;
+    PF_CUDA_OK(cudaEventRecord(db->ev_end, s));
+    uint64_t d2h = levels * sizeof(LevelTotals);
+    if (want_hits && hits_total) {
+        db->tmp_read.resize(hits_total);
+        db->tmp_leaf.resize(hits_total);
+        PF_CUDA_OK(cudaMemcpyAsync(db->tmp_read.data(), db->hit_read.p, hits_total * 4, cudaMemcpyDeviceToHost, s));
+        PF_CUDA_OK(cudaMemcpyAsync(db->tmp_leaf.data(), db->hit_leaf.p, hits_total * 4, cudaMemcpyDeviceToHost, s));
+        d2h += hits_total * 8;
+    }
+    PF_CUDA_OK(cudaStreamSynchronize(s));
+    PF_CUDA_OK(cudaGetLastError());
+    if (want_hits) {
+        // CSR by read, leaves ascending within a read (ResultMap holds a set per read id)
+        for (uint64_t i = 0; i < hits_total; ++i) db->out_off[(size_t)db->tmp_read[i] + 1]++;
+        for (uint32_t r = 0; r < n_reads; ++r) db->out_off[r + 1] += db->out_off[r];
+        db->out_leaf.resize(hits_total);
+        std::vector<uint64_t> fill(db->out_off.begin(), db->out_off.end() - 1);
+        for (uint64_t i = 0; i < hits_total; ++i) db->out_leaf[fill[db->tmp_read[i]]++] = db->tmp_leaf[i];
+        for (uint32_t r = 0; r < n_reads; ++r)
+            std::sort(db->out_leaf.begin() + db->out_off[r], db->out_leaf.begin() + db->out_off[r + 1]);
+        if (out) {
+            out->n_hits = hits_total;
+            out->read_off = db->out_off.data();
+            out->leaf = db->out_leaf.data();
+        }
+    } else if (out) {
+        out->read_off = db->out_off.data();
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, db->ev_begin, db->ev_end);
+    db->stats.device_ms += ms;
+    for (size_t l = 0; l < levels; ++l) {
+        float pm = 0.f;
+        cudaEventElapsedTime(&pm, db->ev_probe[2 * l], db->ev_probe[2 * l + 1]);
+        db->stats.probe_kernel_ms += pm;
+    }
+    db->stats.blocks++;
+    db->stats.reads += n_reads;
+    db->stats.pairs += pairs;
+    db->stats.probes_issued += probes;
+    db->stats.levels += levels;
+    db->stats.probe_launches += probe_launches;
+    db->stats.other_launches += other_launches;
+    db->stats.d2h_bytes += d2h;
+    return PF_OK;
+}
+
+static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b) {
+    if (!in || (in->n_reads && (!in->lengths || !in->word_off || !in->packed))) {
+        set_error("pf_read_batch: null array");
+        return PF_ERR_ARG;
+    }
+    if (in->n_exc && (!in->exc_index || !in->exc_off || !in->exc_bytes)) {
+        set_error("pf_read_batch: exception arrays missing");
+        return PF_ERR_ARG;
+    }
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    cudaStream_t s = db->stream;
+    int rc;
+    b->n_reads = in->n_reads;
+    b->n_exc = in->n_exc;
+    b->n_words = in->n_words;
+    b->bytes = 0;
+    if (in->n_reads == 0) return PF_OK;
+    if ((rc = b->lengths.ensure(in->n_reads)) || (rc = b->word_off.ensure(in->n_reads)) ||
+        (rc = b->packed.ensure(in->n_words + 4)))
+        return rc;
+    PF_CUDA_OK(cudaMemcpyAsync(b->lengths.p, in->lengths, (size_t)in->n_reads * 4, cudaMemcpyHostToDevice, s));
+    PF_CUDA_OK(cudaMemcpyAsync(b->word_off.p, in->word_off, (size_t)in->n_reads * 8, cudaMemcpyHostToDevice, s));
+    PF_CUDA_OK(cudaMemcpyAsync(b->packed.p, in->packed, (size_t)in->n_words * 4, cudaMemcpyHostToDevice, s));
+    PF_CUDA_OK(cudaMemsetAsync(b->packed.p + in->n_words, 0, 16, s));
+    b->bytes = (uint64_t)in->n_reads * 12 + in->n_words * 4;
+    if (in->n_exc) {
+        b->exc_nbytes = in->exc_off[in->n_exc];
+        if ((rc = b->exc_index.ensure(in->n_reads)) || (rc = b->exc_off.ensure((size_t)in->n_exc + 1)) ||
+            (rc = b->exc_bytes.ensure(std::max<uint64_t>(b->exc_nbytes, 1))))
+            return rc;
+        PF_CUDA_OK(cudaMemcpyAsync(b->exc_index.p, in->exc_index, (size_t)in->n_reads * 4, cudaMemcpyHostToDevice, s));
+        PF_CUDA_OK(cudaMemcpyAsync(b->exc_off.p, in->exc_off, ((size_t)in->n_exc + 1) * 8, cudaMemcpyHostToDevice, s));
+        if (b->exc_nbytes)
+            PF_CUDA_OK(cudaMemcpyAsync(b->exc_bytes.p, in->exc_bytes, b->exc_nbytes, cudaMemcpyHostToDevice, s));
+        b->bytes += (uint64_t)in->n_reads * 4 + ((uint64_t)in->n_exc + 1) * 8 + b->exc_nbytes;
+    }
+    db->stats.h2d_bytes += b->bytes;
+    return PF_OK;
+}
+
+// =================================== C ABI ======================================================
+extern "C" {
+
+const char *pf_last_error(void) { return g_error.c_str(); }
+const char *pf_version(void) { return "pfgpu 0.1 sm_100a"; }
+
+int pf_db_open(const char *db_path, int device, int64_t search_depth, pf_db **out) {
+    if (!db_path || !out) {
+        set_error("pf_db_open: null argument");
+        return PF_ERR_ARG;
+    }
+    *out = nullptr;
+    pf_db *db = new pf_db();
+    db->device = device;
+    int rc = db_open_impl(db, db_path, search_depth);
+    if (rc != PF_OK) {
+        std::string keep = g_error;
+        db_free(db);
+        g_error = keep;
+        return rc;
+    }
+    *out = db;
+    return PF_OK;
+}
+
+int pf_db_info(const pf_db *db, pf_db_info_t *o) {
+    if (!db || !o) {
+        set_error("pf_db_info: null argument");
+        return PF_ERR_ARG;
+    }
+    memset(o, 0, sizeof *o);
+    o->kmer_size = db->tree.kmer_size;
+    o->num_bits = db->geom.num_bits;
+    o->words_per_filter = db->wpf;
+    o->n_nodes = db->n_nodes;
+    o->n_leaves = db->n_leaves;
+    o->n_filters = db->n_slots;
+    o->n_levels = db->level_start.size() - 1;
+    o->filter_bytes = db->n_slots * db->wpf * 8;
+    o->seed1 = db->geom.seed1;
+    o->seed2 = db->geom.seed2;
+    o->num_hashes = db->geom.num_hashes;
+    o->largest_genome = db->tree.largest_genome;
+    o->false_pos_rate = db->tree.false_pos_rate;
+    o->device = db->device;
+    o->hash_rot = (int32_t)db->hp.rot;
+    o->fast_path = fast_path_ok(db->hp) ? 1 : 0;
+    return PF_OK;
+}
+
+const char *pf_db_leaf_id(const pf_db *db, uint64_t i) {
+    if (!db || i >= db->n_leaves) return nullptr;
+    return db->leaf_ids[i].c_str();
+}
+
+int pf_db_set_hash_rot(pf_db *db, int rot) {
+    if (!db || rot < 0 || rot > 63) {
+        set_error("pf_db_set_hash_rot: bad argument");
+        return PF_ERR_ARG;
+    }
+    db->hp.rot = (uint32_t)rot;
+    return PF_OK;
+}
+
+int pf_db_set_exhaustive(pf_db *db, int on) {
+    if (!db) return PF_ERR_ARG;
+    db->exhaustive = on ? 1 : 0;
+    return PF_OK;
+}
+
+int pf_db_detect_hash_rot(pf_db *db, uint64_t dfs_leaf, const uint8_t *genome, uint64_t len, int *rot_out) {
+    if (!db || !genome || !rot_out || dfs_leaf >= db->n_leaves) {
+        set_error("pf_db_detect_hash_rot: bad argument");
+        return PF_ERR_ARG;
+    }
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    *rot_out = -1;
+    uint32_t node = NONE32;
+    for (uint32_t u = 0; u < db->n_nodes; ++u)
+        if (db->h_leaf[u] == (int32_t)dfs_leaf) node = u;
+    if (node == NONE32) return PF_ERR_STATE;
+    uint64_t *scratch = nullptr;
+    PF_CUDA_OK(cudaMalloc(&scratch, db->wpf * 8));
+    int rc = PF_OK;
+    for (int rot : {26, 20}) {
+        HashParams hp = db->hp;
+        hp.rot = (uint32_t)rot;
+        bool eq = false;
+        if ((rc = build_leaf_filter(genome, len, hp, scratch, db->wpf, db->stream))) break;
+        if ((rc = filters_equal(scratch, db->d_filters + (uint64_t)db->h_slot[node] * db->wpf, db->wpf, db->stream, &eq)))
+            break;
+        if (eq) {
+            *rot_out = rot;
+            break;
+        }
+    }
+    cudaFree(scratch);
+    return rc;
+}
+
+void pf_db_close(pf_db *db) { db_free(db); }
+
+int pf_batch_upload(pf_db *db, const pf_read_batch *in, pf_dev_batch **out) {
+    if (!db || !in || !out) {
+        set_error("pf_batch_upload: null argument");
+        return PF_ERR_ARG;
+    }
+    pf_dev_batch *b = new pf_dev_batch();
+    int rc = batch_upload_impl(db, in, b);
+    if (rc == PF_OK && cudaStreamSynchronize(db->stream) != cudaSuccess) {
+        set_error("CUDA error in pf_batch_upload: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = PF_ERR_CUDA;
+    }
+    if (rc != PF_OK) {
+        b->release();
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return PF_OK;
+}
+
+void pf_batch_free(pf_db *db, pf_dev_batch *b) {
+    if (!b) return;
+    if (db) cudaSetDevice(db->device);
+    b->release();
+    delete b;
+}
+
+int pf_query_device(pf_db *db, pf_dev_batch *batch, float threshold, int want_hits, pf_hits *out) {
+    if (!db || !batch) {
+        set_error("pf_query_device: null argument");
+        return PF_ERR_ARG;
+    }
+    return query_impl(db, batch, threshold, want_hits, out);
+}
+
+int pf_query_block(pf_db *db, const pf_read_batch *in, float threshold, int want_hits, pf_hits *out) {
+    if (!db || !in) {
+        set_error("pf_query_block: null argument");
+        return PF_ERR_ARG;
+    }
+    int rc = batch_upload_impl(db, in, &db->own_batch);
+    if (rc != PF_OK) return rc;
+    return query_impl(db, &db->own_batch, threshold, want_hits, out);
+}
+
+int pf_leaf_counts(pf_db *db, uint64_t *counts) {
+    if (!db || !counts) {
+        set_error("pf_leaf_counts: null argument");
+        return PF_ERR_ARG;
+    }
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    PF_CUDA_OK(cudaMemcpyAsync(counts, db->d_counts, db->n_leaves * 8, cudaMemcpyDeviceToHost, db->stream));
+    PF_CUDA_OK(cudaStreamSynchronize(db->stream));
+    return PF_OK;
+}
+
+int pf_reset_counts(pf_db *db) {
+    if (!db) return PF_ERR_ARG;
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    PF_CUDA_OK(cudaMemsetAsync(db->d_counts, 0, std::max<uint64_t>(db->n_leaves, 1) * 8, db->stream));
+    PF_CUDA_OK(cudaStreamSynchronize(db->stream));
+    return PF_OK;
+}
+
+int pf_save_leaf_counts(pf_db *db, const char *csv_path) {
+    if (!db || !csv_path) {
+        set_error("pf_save_leaf_counts: null argument");
+        return PF_ERR_ARG;
+    }
+    std::vector<uint64_t> c(std::max<uint64_t>(db->n_leaves, 1));
+    int rc = pf_leaf_counts(db, c.data());
+    if (rc != PF_OK) return rc;
+    FILE *fp = fopen(csv_path, "wb");
+    if (!fp) {
+        set_error("cannot create %s", csv_path);
+        return PF_ERR_IO;
+    }
+    for (uint64_t i = 0; i < db->n_leaves; ++i)
+        if (c[i] > 0) fprintf(fp, "%s,%llu\n", db->leaf_ids[i].c_str(), (unsigned long long)c[i]);
+    if (fclose(fp) != 0) {
+        set_error("problem writing to output file %s", csv_path);
+        return PF_ERR_IO;
+    }
+    return PF_OK;
+}
+
+int pf_get_stats(pf_db *db, pf_stats_t *o) {
+    if (!db || !o) return PF_ERR_ARG;
+    *o = db->stats;
+    return PF_OK;
+}
+int pf_reset_stats(pf_db *db) {
+    if (!db) return PF_ERR_ARG;
+    db->stats = pf_stats_t{};
+    return PF_OK;
+}
+
+int pf_nccl_unique_id(void *id128) {
+    if (!id128) return PF_ERR_ARG;
+    int rc = load_nccl();
+    if (rc != PF_OK) return rc;
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) {
+        set_error("ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        return PF_ERR_NCCL;
+    }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return PF_OK;
+}
+
+int pf_comm_init(pf_db *db, int nranks, int rank, const void *id128) {
+    if (!db || !id128 || nranks < 1 || rank < 0 || rank >= nranks) {
+        set_error("pf_comm_init: bad argument");
+        return PF_ERR_ARG;
+    }
+    int rc = load_nccl();
+    if (rc != PF_OK) return rc;
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&db->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        set_error("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        db->comm = nullptr;
+        return PF_ERR_NCCL;
+    }
+    return PF_OK;
+}
+
+int pf_allreduce_counts(pf_db *db) {
+    if (!db) return PF_ERR_ARG;
+    if (!db->comm) {
+        set_error("pf_allreduce_counts: call pf_comm_init first");
+        return PF_ERR_STATE;
+    }
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    ncclResult_t r = g_nccl.AllReduce(db->d_counts, db->d_counts, db->n_leaves, ncclUint64, ncclSum, db->comm, db->stream);
+    if (r != ncclSuccess) {
+        set_error("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        return PF_ERR_NCCL;
+    }
+    PF_CUDA_OK(cudaStreamSynchronize(db->stream));
+    return PF_OK;
+}
+
+}  // extern "C"
