@@ -147,6 +147,9 @@ typedef struct pf_stats_t {
     double device_ms;         /* CUDA-event time of the query calls, first launch to last */
 } pf_stats_t;
 int pf_get_stats(pf_db *db, pf_stats_t *out);
+/* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can
+ * bracket calls with its own events on the launching stream. */
+void *pf_db_stream(pf_db *db);
 int pf_reset_stats(pf_db *db);
 /* 0 (default): read-level early exit on.  1: reference-faithful probing -- every k-mer of every
  * pair is probed until its first clear bit (probes_issued then equals the reference's count). */

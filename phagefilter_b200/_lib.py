@@ -81,6 +81,7 @@ SYMBOLS = {
     "pf_save_leaf_counts": (C.c_int, [_VP, C.c_char_p]),
     "pf_get_stats": (C.c_int, [_VP, C.POINTER(Stats)]),
     "pf_reset_stats": (C.c_int, [_VP]),
+    "pf_db_stream": (_VP, [_VP]),
     "pf_db_set_exhaustive": (C.c_int, [_VP, C.c_int]),
     "pf_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "pf_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, C.c_char_p]),

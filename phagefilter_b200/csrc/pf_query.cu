@@ -801,6 +801,7 @@ int pf_get_stats(pf_db *db, pf_stats_t *o) {
     *o = db->stats;
     return PF_OK;
 }
+void *pf_db_stream(pf_db *db) { return db ? (void *)db->stream : nullptr; }
 int pf_reset_stats(pf_db *db) {
     if (!db) return PF_ERR_ARG;
     db->stats = pf_stats_t{};
