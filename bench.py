@@ -106,7 +106,6 @@ def measured_peak_gbs():
 def cpu_reference_run(genomes, blob, offs, n_sample, steps, warmup, db_dir=None):
     """The reference's algorithm on host cores: oracle port, all threads, counting only its own work."""
     from oracle import pf_oracle
-    pf_oracle.set_sched_counting(False)
     if db_dir and os.path.exists(os.path.join(db_dir, "tree.bin")):
         tree = pf_oracle.Tree.load(db_dir)
     else:
@@ -123,7 +122,6 @@ def cpu_reference_run(genomes, blob, offs, n_sample, steps, warmup, db_dir=None)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    pf_oracle.set_sched_counting(True)
     return n_sample, times
 
 

@@ -65,6 +65,8 @@ typedef struct pf_db_info_t {
     int32_t device;
     int32_t hash_rot;          /* FxHasher::finish rotate in use (26 = rustc-hash 2.1.1) */
     int32_t fast_path;         /* 1 if the 2-bit register path covers this k (17..32) */
+    uint64_t n_internal;       /* interior nodes */
+    uint64_t n_monotone;       /* interior nodes whose filter was verified to contain both children's */
 } pf_db_info_t;
 
 /* search_depth < 0: no pruning (main.rs:293-299 passes Some(depth)). */
@@ -145,6 +147,7 @@ typedef struct pf_stats_t {
     uint64_t h2d_bytes, d2h_bytes;
     double probe_kernel_ms;   /* CUDA-event time summed over probe launches */
     double device_ms;         /* CUDA-event time of the query calls, first launch to last */
+    uint64_t group_rounds;    /* rounds of 32 k-mers each lane owned at once in the last call (1..8) */
 } pf_stats_t;
 int pf_get_stats(pf_db *db, pf_stats_t *out);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can
@@ -154,6 +157,16 @@ int pf_reset_stats(pf_db *db);
 /* 0 (default): read-level early exit on.  1: reference-faithful probing -- every k-mer of every
  * pair is probed until its first clear bit (probes_issued then equals the reference's count). */
 int pf_db_set_exhaustive(pf_db *db, int on);
+/* 1 (default): interior nodes whose filter was verified at load to be a bitwise superset of their
+ * children's filters ("child passes => parent passes") get a step-limited, sound cannot-pass test
+ * instead of the exact one; leaves and unverified nodes stay exact, so results are identical.
+ * 0: every node is evaluated exactly (the frontier then equals the reference's, query.rs:113-141). */
+int pf_db_set_lazy(pf_db *db, int on);
+/* hash_bytes of every k-mer is computed once per batch and cached in HBM (8 B per k-mer); a batch whose
+ * cache would exceed `bytes` (default 16 GiB) is processed in several chunks of reads. */
+int pf_db_set_hash_cache_bytes(pf_db *db, uint64_t bytes);
+/* Probe steps per node (level order, n_nodes entries) the next query with `threshold` will use. */
+int pf_db_node_steps(pf_db *db, float threshold, uint32_t *steps);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU: reads are sharded by rank, every rank holds a replica of the tree, and the

@@ -352,6 +352,9 @@ typedef struct pfo_node {
     char *tax_id;   /* Option<String>; NULL = None */
     uint64_t mapped_reads;
     int filter;     /* index into tree->filters */
+    /* cache for the kernel-schedule restatement (invalidated whenever the tree changes) */
+    int analysed, mono;
+    uint64_t pop;
 } pfo_node;
 
 struct pfo_tree {
@@ -704,6 +707,7 @@ static void refresh(pfo_tree *t) {
     t->pre = (pfo_node **)malloc((n ? n : 1) * sizeof *t->pre);
     t->n_leaves = t->n_pre = 0;
     collect(t, t->root);
+    for (uint64_t i = 0; i < t->n_pre; i++) t->pre[i]->analysed = 0;
     t->dirty = 0;
 }
 uint64_t pfo_tree_num_nodes(const pfo_tree *t) {
@@ -771,13 +775,15 @@ typedef struct {
     uint64_t need;
 } oread;
 
-/* Probe count of one (read,node) pair under the GPU kernel's deterministic schedule:
- *   need == 0            -> pass, no probes;   need > n_k -> fail, no probes;
- *   k-mers are taken in rounds of 32 consecutive positions; inside a round, step i makes every
- *   still-alive k-mer of the round probe bit i; after each step the pair fails as soon as
- *   total misses > n_k - need; after each round the pair passes as soon as hits >= need.
- * The pass/fail outcome is identical to query_passes; only the amount of work differs. */
-static uint64_t pair_sched(const pfo_filter *f, const oread *r, size_t k, int rot, int *pass_out) {
+/* Probe count of one (read,node) pair under the GPU kernel's deterministic schedule (pf_kernels.cuh,
+ * probe_group): need == 0 -> pass, no probes; need > n_k -> fail, no probes.  k-mers are taken in groups of
+ * 32*G consecutive positions.  Inside a group the phases are: step 0 of the first 32 k-mers; step 0 of the
+ * rest; then step i = 1..n_steps-1 of every k-mer still alive (none alive -> group done).  After every phase
+ * the pair fails as soon as total misses > n_k - need; after every group it passes as soon as hits >= need.
+ * With n_steps < K a surviving k-mer counts as a hit (sound pre-test of interior nodes).  The outcome at
+ * exact nodes (n_steps == K) is identical to query_passes; only the amount of work differs. */
+static uint64_t pair_sched(const pfo_filter *f, uint32_t n_steps, uint32_t G, const oread *r, size_t k, int rot,
+                           int *pass_out) {
     uint64_t probes = 0;
     if (r->need == 0) {
         *pass_out = 1;
@@ -788,10 +794,12 @@ static uint64_t pair_sched(const pfo_filter *f, const oread *r, size_t k, int ro
         return 0;
     }
     uint64_t allowed = r->n_k - r->need, misses = 0, hits = 0;
-    for (uint64_t base = 0; base < r->n_k; base += 32) {
-        uint64_t cnt = r->n_k - base < 32 ? r->n_k - base : 32;
-        uint64_t h1[32], h2[32];
-        int alive[32];
+    const uint64_t gsz = 32ull * G;
+    uint64_t *h1 = (uint64_t *)malloc(gsz * 8), *h2 = (uint64_t *)malloc(gsz * 8);
+    uint8_t *alive = (uint8_t *)malloc(gsz);
+    int decided = 0, result = 0;
+    for (uint64_t base = 0; base < r->n_k && !decided; base += gsz) {
+        uint64_t cnt = r->n_k - base < gsz ? r->n_k - base : gsz;
         for (uint64_t j = 0; j < cnt; j++) {
             const uint8_t *km = r->kmers + (base + j) * k;
             h1[j] = pfo_fx_hash(f->seed1, km, k, rot);
@@ -799,12 +807,24 @@ static uint64_t pair_sched(const pfo_filter *f, const oread *r, size_t k, int ro
             alive[j] = 1;
         }
         uint64_t dead = 0;
-        for (uint32_t i = 0; i < f->K; i++) {
-            uint64_t n_alive = 0;
-            for (uint64_t j = 0; j < cnt; j++) {
+        /* phase list: (step, lo, hi) */
+        for (uint32_t ph = 0; !decided; ph++) {
+            uint32_t step;
+            uint64_t lo, hi;
+            if (ph == 0) {
+                step = 0, lo = 0, hi = cnt < 32 ? cnt : 32;
+            } else if (ph == 1) {
+                if (cnt <= 32) continue;
+                step = 0, lo = 32, hi = cnt;
+            } else {
+                step = ph - 1;
+                if (step >= n_steps) break;
+                if (cnt - dead == 0) break;
+                lo = 0, hi = cnt;
+            }
+            for (uint64_t j = lo; j < hi; j++) {
                 if (!alive[j]) continue;
-                n_alive++;
-                uint64_t g = i == 0 ? h1[j] : i == 1 ? h2[j] : (h1[j] + (uint64_t)i) * h2[j];
+                uint64_t g = step == 0 ? h1[j] : step == 1 ? h2[j] : (h1[j] + (uint64_t)step) * h2[j];
                 uint64_t idx = g % f->m;
                 probes++;
                 if (!((f->words[idx >> 6] >> (idx & 63)) & 1)) {
@@ -812,20 +832,24 @@ static uint64_t pair_sched(const pfo_filter *f, const oread *r, size_t k, int ro
                     dead++;
                 }
             }
-            if (n_alive == 0) break;
             if (misses + dead > allowed) {
-                *pass_out = 0;
-                return probes;
+                decided = 1;
+                result = 0;
             }
         }
+        if (decided) break;
         misses += dead;
         hits += cnt - dead;
         if (hits >= r->need) {
-            *pass_out = 1;
-            return probes;
+            decided = 1;
+            result = 1;
         }
     }
-    *pass_out = hits >= r->need;
+    if (!decided) result = hits >= r->need;
+    free(h1);
+    free(h2);
+    free(alive);
+    *pass_out = result;
     return probes;
 }
 
@@ -837,9 +861,6 @@ static int query_passes(const pfo_filter *f, const oread *r, size_t k, int rot, 
     return matches >= r->need;
 }
 
-/* When off (CPU-baseline timing) only the reference's own work (query_passes) is done. */
-static int g_count_sched = 1;
-void pfo_set_sched_counting(int on) { g_count_sched = on; }
 
 typedef struct {
     pfo_tree *t;
@@ -873,25 +894,19 @@ static void query_rec(qctx *c, pfo_node *node, const uint32_t *set, uint64_t n_s
     size_t k = (size_t)c->t->kmer_size;
     int rot = c->t->rot;
     uint8_t *flag = (uint8_t *)malloc(n_set ? n_set : 1);
-    uint64_t pr_ref = 0, pr_sched = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : pr_ref, pr_sched)
+    uint64_t pr_ref = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : pr_ref)
     for (uint64_t i = 0; i < n_set; i++) {
         uint64_t p = 0;
-        int pass = query_passes(f, &c->reads[set[i]], k, rot, &p); /* :113-117 */
+        flag[i] = (uint8_t)query_passes(f, &c->reads[set[i]], k, rot, &p); /* :113-117 */
         pr_ref += p;
-        int pass2 = pass;
-        if (g_count_sched) pr_sched += pair_sched(f, &c->reads[set[i]], k, rot, &pass2);
-        flag[i] = (uint8_t)(pass | (pass2 << 1));
     }
     c->out->probes_ref += pr_ref;
-    c->out->probes_sched += pr_sched;
     c->out->pairs += n_set;
     uint32_t *pass = (uint32_t *)malloc((n_set ? n_set : 1) * 4);
     uint64_t n_pass = 0;
-    for (uint64_t i = 0; i < n_set; i++) {
-        if ((flag[i] & 1) != (flag[i] >> 1)) set_err("internal: scheduled pass differs from query_passes");
-        if (flag[i] & 1) pass[n_pass++] = set[i];
-    }
+    for (uint64_t i = 0; i < n_set; i++)
+        if (flag[i]) pass[n_pass++] = set[i];
     free(flag);
     if (!is_leaf(node)) {
         if (n_pass) { /* :122 */
@@ -909,8 +924,108 @@ static void query_rec(qctx *c, pfo_node *node, const uint32_t *set, uint64_t n_s
     free(pass);
 }
 
+/* ---- restatement of the GPU kernel's schedule (not of the reference): step-limited pre-test at
+ * verified-monotone interior nodes, exact evaluation at leaves and everywhere else.  Used to check that the
+ * schedule decides exactly like the reference and to predict the kernel's pair and probe counts. ---- */
+static uint64_t filter_popcount(const pfo_filter *f) {
+    uint64_t c = 0;
+    for (uint64_t i = 0; i < f->nwords; i++) c += (uint64_t)__builtin_popcountll(f->words[i]);
+    return c;
+}
+static int filter_contains_filter(const pfo_filter *parent, const pfo_filter *child) {
+    uint64_t n = parent->nwords < child->nwords ? parent->nwords : child->nwords;
+    for (uint64_t i = 0; i < n; i++)
+        if (child->words[i] & ~parent->words[i]) return 0;
+    return 1;
+}
+/* smallest s in [1,K] with fill^s <= 0.75*threshold (plain double multiplications, no libm) */
+static uint32_t lazy_steps(double fill, double theta, uint32_t K) {
+    double target = 0.75 * theta, p = fill;
+    uint32_t s = 1;
+    while (p > target && s < K) {
+        p *= fill;
+        ++s;
+    }
+    return s;
+}
+static uint32_t pfo_node_steps(const pfo_tree *t, pfo_node *n, float threshold, int lazy) {
+    const pfo_filter *f = t->filters[n->filter];
+    if (!lazy || is_leaf(n)) return f->K;
+    if (!n->analysed) {
+        n->mono = (!n->left || filter_contains_filter(f, t->filters[n->left->filter])) &&
+                  (!n->right || filter_contains_filter(f, t->filters[n->right->filter]));
+        n->pop = filter_popcount(f);
+        n->analysed = 1;
+    }
+    if (!n->mono) return f->K;
+    return lazy_steps((double)n->pop / (double)f->m, (double)threshold, f->K);
+}
+
+typedef struct {
+    pfo_tree *t;
+    const oread *reads;
+    int want_hits, lazy;
+    uint32_t group_rounds;
+    float threshold;
+    pfo_query_result *out;
+    uint64_t hit_cap;
+    uint64_t leaf_cursor;
+} sctx;
+
+static void sched_rec(sctx *c, pfo_node *node, const uint32_t *set, uint64_t n_set) {
+    const pfo_filter *f = c->t->filters[node->filter];
+    size_t k = (size_t)c->t->kmer_size;
+    int rot = c->t->rot;
+    uint32_t n_steps = pfo_node_steps(c->t, node, c->threshold, c->lazy);
+    uint8_t *flag = (uint8_t *)malloc(n_set ? n_set : 1);
+    uint64_t pr = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : pr)
+    for (uint64_t i = 0; i < n_set; i++) {
+        int pass = 0;
+        pr += pair_sched(f, n_steps, c->group_rounds, &c->reads[set[i]], k, rot, &pass);
+        flag[i] = (uint8_t)pass;
+    }
+    c->out->probes_sched += pr;
+    c->out->pairs += n_set;
+    uint32_t *pass = (uint32_t *)malloc((n_set ? n_set : 1) * 4);
+    uint64_t n_pass = 0;
+    for (uint64_t i = 0; i < n_set; i++)
+        if (flag[i]) pass[n_pass++] = set[i];
+    free(flag);
+    if (!is_leaf(node)) {
+        if (n_pass) {
+            if (node->left) sched_rec(c, node->left, pass, n_pass);
+            if (node->right) sched_rec(c, node->right, pass, n_pass);
+        } else {
+            c->leaf_cursor += subtree_leaves(node);
+        }
+    } else {
+        if (c->want_hits) {
+            qctx q = {c->t, c->reads, 1, c->out, c->hit_cap, 0};
+            for (uint64_t i = 0; i < n_pass; i++) push_hit(&q, pass[i], (uint32_t)c->leaf_cursor);
+            c->hit_cap = q.hit_cap;
+        }
+        c->leaf_cursor++;
+    }
+    free(pass);
+}
+
+static int query_impl(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, float threshold,
+                      int threads, int want_hits, int sched, int lazy, uint32_t group_rounds, pfo_query_result *out);
+
 int pfo_query_batch(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, float threshold,
                     int threads, int want_hits, pfo_query_result *out) {
+    return query_impl(t, seqs, offs, n_reads, threshold, threads, want_hits, 0, 0, 1, out);
+}
+/* Leaf counters are NOT touched; hits/pairs/probes_sched describe the kernel schedule. */
+int pfo_query_batch_sched(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, float threshold,
+                          int threads, int want_hits, int lazy, uint32_t group_rounds, pfo_query_result *out) {
+    return query_impl(t, seqs, offs, n_reads, threshold, threads, want_hits, 1, lazy, group_rounds ? group_rounds : 1,
+                      out);
+}
+
+static int query_impl(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, float threshold,
+                      int threads, int want_hits, int sched, int lazy, uint32_t group_rounds, pfo_query_result *out) {
     memset(out, 0, sizeof *out);
     g_err[0] = 0;
     if (!t->root) return 0; /* root.take().map(...) on None (query.rs:72-80) */
@@ -940,8 +1055,14 @@ int pfo_query_batch(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint
     }
     uint32_t *all = (uint32_t *)malloc((n_reads ? n_reads : 1) * 4);
     for (uint32_t i = 0; i < n_reads; i++) all[i] = i;
-    qctx c = {t, reads, want_hits, out, 0, 0};
-    query_rec(&c, t->root, all, n_reads);
+    if (sched) {
+        refresh(t);
+        sctx c = {t, reads, want_hits, lazy, group_rounds, threshold, out, 0, 0};
+        sched_rec(&c, t->root, all, n_reads);
+    } else {
+        qctx c = {t, reads, want_hits, out, 0, 0};
+        query_rec(&c, t->root, all, n_reads);
+    }
     free(all);
     free(koff);
     free(kbuf);

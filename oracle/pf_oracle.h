@@ -110,8 +110,7 @@ typedef struct pfo_query_result {
     uint32_t *hit_leaf;       /* DFS leaf index */
     uint64_t pairs;           /* (read,node) pairs evaluated */
     uint64_t probes_ref;      /* bit probes under the reference's semantics (k-mer early exit only) */
-    uint64_t probes_sched;    /* bit probes under the GPU kernel's schedule (read-level early exit in
-                                 32-k-mer rounds, see pfo_pair_sched) */
+    uint64_t probes_sched;    /* bit probes under the GPU kernel's schedule (pfo_query_batch_sched only) */
 } pfo_query_result;
 
 /* query_batch on one block of reads given as ASCII bytes: seqs concatenated, offs[n+1].
@@ -120,8 +119,13 @@ typedef struct pfo_query_result {
 int pfo_query_batch(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads,
                     float threshold, int threads, int want_hits, pfo_query_result *out);
 void pfo_query_result_free(pfo_query_result *r);
-/* on (default): also count probes_sched; off: only the reference's work (used when timing the CPU baseline) */
-void pfo_set_sched_counting(int on);
+/* Restatement of the GPU kernel's schedule (NOT of the reference): same decisions, different amount of
+ * work.  lazy=1: verified-monotone interior nodes get the step-limited pre-test (see pfo_node_steps);
+ * lazy=0: every node exact with read-level early exit.  Fills hits, pairs and probes_sched; leaf counters
+ * of the tree are not touched. */
+int pfo_query_batch_sched(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads,
+                          float threshold, int threads, int want_hits, int lazy, uint32_t group_rounds,
+                          pfo_query_result *out);
 /* need = (threshold * n_k as f32).ceil() as usize (query.rs:48) -- saturating cast */
 uint64_t pfo_need(float threshold, uint64_t n_kmers);
 /* save_leaf_counts (query.rs:173-183): returns bytes written to buf (cap), or needed size */

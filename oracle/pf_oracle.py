@@ -104,7 +104,8 @@ def lib():
     L.pfo_query_batch.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, C.c_float, C.c_int, C.c_int,
                                   C.POINTER(_QueryResult)]
     L.pfo_query_result_free.argtypes = [C.POINTER(_QueryResult)]
-    L.pfo_set_sched_counting.argtypes = [C.c_int]
+    L.pfo_query_batch_sched.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, C.c_float, C.c_int, C.c_int,
+                                        C.c_int, C.c_uint32, C.POINTER(_QueryResult)]
     L.pfo_need.restype = C.c_uint64
     L.pfo_need.argtypes = [C.c_float, C.c_uint64]
     L.pfo_classification_csv.restype = C.c_uint64
@@ -331,6 +332,32 @@ class Tree:
         lib().pfo_query_result_free(C.byref(res))
         return out
 
+    def query_sched(self, reads: Sequence[bytes], threshold: float, lazy: bool = True, threads: int = 0,
+                    concat: Tuple[bytes, np.ndarray] | None = None, group_rounds: int | None = None) -> QueryResult:
+        """The GPU kernel's schedule restated on the CPU (same decisions as query_batch, different work).
+        group_rounds: rounds of 32 k-mers a lane owns at once; default = the kernel's rule
+        clamp(ceil(max k-mers per read / 32), 1, 8)."""
+        seqs, offs = concat if concat is not None else concat_reads(reads)
+        n = len(offs) - 1
+        if group_rounds is None:
+            k = self.kmer_size
+            lens = np.diff(offs.astype(np.int64)) if n else np.zeros(0, dtype=np.int64)
+            max_nk = int(max(0, (lens.max() - k + 1) if n and k and lens.max() >= k else 0))
+            group_rounds = min(8, max(1, -(-max_nk // 32)))
+        res = _QueryResult()
+        rc = lib().pfo_query_batch_sched(self._p, seqs, offs.ctypes.data_as(C.POINTER(C.c_uint64)), n,
+                                         C.c_float(threshold), threads, 1, int(lazy), group_rounds, C.byref(res))
+        if rc:
+            raise RuntimeError(lib().pfo_last_error().decode())
+        nh = int(res.n_hits)
+        hits = np.zeros((nh, 2), dtype=np.uint32)
+        if nh:
+            hits[:, 0] = np.ctypeslib.as_array(res.hit_read, shape=(nh,))
+            hits[:, 1] = np.ctypeslib.as_array(res.hit_leaf, shape=(nh,))
+        out = QueryResult(hits, int(res.pairs), int(res.probes_ref), int(res.probes_sched))
+        lib().pfo_query_result_free(C.byref(res))
+        return out
+
     def classification_csv(self) -> str:
         """save_leaf_counts (query.rs:173-183)."""
         n = lib().pfo_classification_csv(self._p, None, 0)
@@ -343,6 +370,3 @@ class Tree:
             lib().pfo_tree_free(self._p)
             self._p = None
 
-
-def set_sched_counting(on: bool) -> None:
-    lib().pfo_set_sched_counting(int(on))

@@ -30,6 +30,7 @@ class DbInfo(C.Structure):
         ("filter_bytes", C.c_uint64), ("seed1", C.c_uint64), ("seed2", C.c_uint64),
         ("num_hashes", C.c_uint32), ("largest_genome", C.c_uint32), ("false_pos_rate", C.c_float),
         ("device", C.c_int32), ("hash_rot", C.c_int32), ("fast_path", C.c_int32),
+        ("n_internal", C.c_uint64), ("n_monotone", C.c_uint64),
     ]
 
 
@@ -52,7 +53,7 @@ class Stats(C.Structure):
         ("blocks", C.c_uint64), ("reads", C.c_uint64), ("pairs", C.c_uint64), ("probes_issued", C.c_uint64),
         ("levels", C.c_uint64), ("probe_launches", C.c_uint64), ("other_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-        ("probe_kernel_ms", C.c_double), ("device_ms", C.c_double),
+        ("probe_kernel_ms", C.c_double), ("device_ms", C.c_double), ("group_rounds", C.c_uint64),
     ]
 
 
@@ -83,6 +84,9 @@ SYMBOLS = {
     "pf_reset_stats": (C.c_int, [_VP]),
     "pf_db_stream": (_VP, [_VP]),
     "pf_db_set_exhaustive": (C.c_int, [_VP, C.c_int]),
+    "pf_db_set_lazy": (C.c_int, [_VP, C.c_int]),
+    "pf_db_set_hash_cache_bytes": (C.c_int, [_VP, C.c_uint64]),
+    "pf_db_node_steps": (C.c_int, [_VP, C.c_float, C.POINTER(C.c_uint32)]),
     "pf_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "pf_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, C.c_char_p]),
     "pf_allreduce_counts": (C.c_int, [_VP]),

@@ -68,6 +68,17 @@ class BloomTree:
     def set_exhaustive(self, on: bool) -> None:
         _lib.check(_lib.lib().pf_db_set_exhaustive(self._h, int(on)))
 
+    def set_hash_cache_bytes(self, nbytes: int) -> None:
+        _lib.check(_lib.lib().pf_db_set_hash_cache_bytes(self._h, nbytes))
+
+    def set_lazy(self, on: bool) -> None:
+        _lib.check(_lib.lib().pf_db_set_lazy(self._h, int(on)))
+
+    def node_steps(self, threshold: float) -> np.ndarray:
+        out = np.zeros(int(self._info.n_nodes), dtype=np.uint32)
+        _lib.check(_lib.lib().pf_db_node_steps(self._h, C.c_float(threshold), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
     def stats(self) -> _lib.Stats:
         s = _lib.Stats()
         _lib.check(_lib.lib().pf_get_stats(self._h, C.byref(s)))

@@ -1,9 +1,14 @@
 // pf_kernels.cuh -- device code of the query path (sm_100a).
 //
-//   probe_kernel    one warp owns one (read,node) pair of the frontier: lanes take consecutive k-mers
-//                   in rounds of 32, re-create the reference's canonical-k-mer hashes in registers
-//                   from 2-bit codes, and gather filter bits with k-mer-level early exit
-//                   (BloomFilter::contains, bloom_filter.rs:312-332; query_passes, query.rs:38-49).
+//   hash_kernel<k>  once per batch: one warp per read, lanes take 32 consecutive k-mers per round and
+//                   re-create the reference's canonical k-mer bytes in registers from 2-bit codes
+//                   (file_parser.rs:114-148), then rustc-hash's hash_bytes over them.  The 64-bit result is
+//                   seed- and node-independent, so it is cached (8 B per k-mer) for the whole descent; the
+//                   reference re-hashes every k-mer at every node (hash_iter.rs:31-45).
+//   probe_kernel    one warp owns one (read,node) pair of the frontier: h1,h2 from the cached value, then
+//                   step i tests bit g_i mod m of the node's filter -- BloomFilter::contains
+//                   (bloom_filter.rs:312-332) with its k-mer-level early exit, query_passes (query.rs:38-49)
+//                   with a result-identical read-level early exit.
 //   level_scan_kernel / scatter_kernel
 //                   prune the frontier at the threshold and expand the survivors to both children,
 //                   node-major, with warp-aggregated atomics and a prefix sum (_query_batch,
@@ -17,21 +22,94 @@ namespace pf {
 constexpr uint32_t NONE32_D = 0xFFFFFFFFu;  // "no child" / "not an exception read"
 constexpr int PROBE_THREADS = 256;
 constexpr int PROBE_CHUNK = 8;  // pairs fetched per warp per work-counter atomic
+constexpr int HASH_THREADS = 256;
 
-struct ProbeArgs {
-    // frontier
-    const uint32_t *fr_read;
-    const uint32_t *fr_node;
-    uint32_t n_pairs;
-    // read batch
+PF_D uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
+
+// number of k-mers of a read (file_parser.rs:136-139)
+PF_HD uint32_t kmers_of(uint32_t len, uint32_t k) { return (k == 0u || k > len) ? 0u : len - k + 1u; }
+
+// ---- hash_kernel ---------------------------------------------------------------------------------
+struct HashArgs {
     const uint32_t *lengths;
     const uint64_t *word_off;
     const uint32_t *packed;
     const uint32_t *exc_index;  // may be null
     const uint64_t *exc_off;
     const uint8_t *exc_bytes;
+    const uint64_t *kmer_off;   // [n_reads + 1] prefix sum of k-mer counts
+    uint64_t *hb;               // out: hash_bytes(canonical k-mer), index kmer_off[r] - kmer_base + pos
+    uint64_t kmer_base;         // kmer_off[read0]
+    uint32_t read0, n_reads;    // reads [read0, read0 + n_reads) of the batch
+    uint32_t k;
+    unsigned int *work_ctr;
+};
+
+struct ByteSrc {
+    const uint8_t *ascii;    // exception read: raw bytes
+    const uint32_t *packed;  // otherwise 2-bit codes
+};
+PF_D uint8_t src_byte(const ByteSrc &s, uint32_t j) {
+    if (s.ascii) return s.ascii[j];
+    uint32_t w = ldg32(s.packed + (j >> 4));
+    uint32_t c = (w >> (2u * (j & 15u))) & 3u;
+    return (uint8_t)(0x54474341u >> (8u * c));
+}
+
+// KM in 17..32: 2-bit register path for reads of pure upper-case ACGT; KM == 0: byte path for every read.
+// Exception reads (any other byte) always take the byte path, which is what the reference hashes.
+template <int KM>
+__global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArgs a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t i0 = 0;
+        if (lane == 0) i0 = atomicAdd(a.work_ctr, 4u);
+        i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
+        if (i0 >= a.n_reads) break;
+        const uint32_t i1 = min(i0 + 4u, a.n_reads);
+        for (uint32_t i = i0; i < i1; ++i) {
+            const uint32_t r = a.read0 + i;
+            const uint32_t n_k = kmers_of(ldg32(a.lengths + r), a.k);
+            if (n_k == 0) continue;
+            uint64_t *out = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
+            const uint64_t woff = __ldg(a.word_off + r);
+            const uint32_t e = a.exc_index ? ldg32(a.exc_index + r) : NONE32_D;
+            if (KM != 0 && e == NONE32_D) {
+                const uint64_t *w64 = reinterpret_cast<const uint64_t *>(a.packed + woff);
+                uint64_t lo = __ldg(w64);
+                for (uint32_t base = 0; base < n_k; base += 32u) {
+                    const uint64_t hi = __ldg(w64 + (base >> 5) + 1);
+                    const uint32_t sh = 2u * lane;
+                    const uint64_t x = (lo >> sh) | ((hi << 1) << (63u - sh));
+                    const uint64_t hb = canonical_hash_2bit<(KM ? KM : 17)>(x);
+                    if (base + lane < n_k) out[base + lane] = hb;
+                    lo = hi;
+                }
+            } else {
+                ByteSrc s;
+                s.ascii = e == NONE32_D ? nullptr : a.exc_bytes + __ldg(a.exc_off + e);
+                s.packed = a.packed + woff;
+                for (uint32_t pos = lane; pos < n_k; pos += 32u)
+                    out[pos] = canonical_hash_bytes([&](uint32_t j) { return src_byte(s, pos + j); }, a.k);
+            }
+        }
+    }
+}
+
+// ---- probe_kernel --------------------------------------------------------------------------------
+struct ProbeArgs {
+    // frontier
+    const uint32_t *fr_read;
+    const uint32_t *fr_node;
+    uint32_t n_pairs;
+    // reads
+    const uint32_t *lengths;
+    const uint64_t *kmer_off;
+    const uint64_t *hb;
+    uint64_t kmer_base;
     // tree
     const uint32_t *node_slot;
+    const uint32_t *node_steps;  // probe steps per k-mer at this node: K (exact) or fewer (sound pre-test)
     const uint64_t *filters;
     uint64_t words_per_filter;
     // outputs
@@ -52,64 +130,124 @@ PF_D uint32_t need_of(float threshold, uint32_t n_k) {
     return (uint32_t)c;
 }
 
-PF_D uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
-
-// One round: every active lane owns one k-mer (h1,h2).  Step i makes each still-alive lane test bit
-// g_i mod m.  Returns the mask of lanes whose k-mer is contained.  `failed` is set as soon as the
-// pair can no longer reach its bound (read-level early exit; result-identical to counting all).
-template <bool SMALL_M>
-PF_D uint32_t probe_round(const uint32_t *__restrict__ filt, const HashParams &hp, uint64_t h1, uint64_t h2, bool active,
-                          uint32_t misses_before, uint32_t allowed, bool exhaustive, uint32_t &probes, bool &failed) {
-    const uint32_t act_mask = __ballot_sync(0xFFFFFFFFu, active);
-    uint32_t alive_mask = act_mask;
-    bool alive = active;
-    uint64_t g = h1;
-    const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
-    for (uint32_t i = 0; i < hp.K; ++i) {
-        probes += __popc(alive_mask);
-        if (alive) {
-            uint32_t w, bit;
-            if (SMALL_M) {
-                uint32_t idx = mod_small(g, M0, M1, m32);
-                w = ldg32(filt + (idx >> 5));
-                bit = idx & 31u;
-            } else {
-                uint64_t idx = mod_any(g, hp.m, hp.M);
-                w = ldg32(filt + (idx >> 5));
-                bit = (uint32_t)idx & 31u;
-            }
-            alive = (w >> bit) & 1u;
-        }
-        alive_mask = __ballot_sync(0xFFFFFFFFu, alive);
-        if (!exhaustive && misses_before + __popc(act_mask & ~alive_mask) > allowed) {
-            failed = true;
-            return alive_mask;
-        }
-        if (alive_mask == 0u) break;
-        // g_{i+1}: g1 = h2, g2 = (h1+2)*h2, then g_{i+1} = g_i + h2   (hash_iter.rs:17-24)
-        g = i == 0 ? h2 : (i == 1 ? (h1 + 2ULL) * h2 : g + h2);
-    }
-    return alive_mask;
-}
-
-struct ByteSrc {
-    const uint8_t *ascii;    // exception read: raw bytes
-    const uint32_t *packed;  // otherwise 2-bit codes
+// One group = up to G rounds of 32 consecutive k-mers; lane L owns k-mers gbase + j*32 + L, j < G, so up to
+// G independent gathers per lane are in flight in every step.  Steps follow BloomFilter::contains: step i
+// tests bit g_i mod m for every k-mer that is still alive (g0 = h1, g1 = h2, g_i = (h1+i)*h2 = g_{i-1} + h2;
+// hash_iter.rs:17-24).  Phases: step 0 of the first round alone (cheap rejection of reads that do not
+// belong below this node), step 0 of the other rounds, then steps 1..n_steps-1 of all rounds.  After every
+// phase the pair fails as soon as more than `limit` k-mers of the group are known to be absent
+// (read-level early exit; counting on could not change the outcome).
+template <int G, bool SMALL_M>
+struct GroupState {
+    uint64_t h1[G], h2[G], g[G];
+    uint32_t alive;  // bit j: k-mer j of this lane has had no clear bit so far
 };
-PF_D uint8_t src_byte(const ByteSrc &s, uint32_t j) {
-    if (s.ascii) return s.ascii[j];
-    uint32_t w = ldg32(s.packed + (j >> 4));
-    uint32_t c = (w >> (2u * (j & 15u))) & 3u;
-    return (uint8_t)(0x54474341u >> (8u * c));
+
+template <int G, bool SMALL_M, int J0, int J1>
+PF_D uint32_t probe_phase(const uint32_t *__restrict__ filt, const HashParams &hp, GroupState<G, SMALL_M> &st) {
+    const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
+    uint32_t w[G], bit[G];
+#pragma unroll
+    for (int j = J0; j < J1; ++j) {  // issue every gather of the phase before using any
+        w[j] = 0xFFFFFFFFu;
+        bit[j] = 0;
+        if ((st.alive >> j) & 1u) {
+            if (SMALL_M) {
+                const uint32_t idx = mod_small(st.g[j], M0, M1, m32);
+                w[j] = ldg32(filt + (idx >> 5));
+                bit[j] = idx & 31u;
+            } else {
+                const uint64_t idx = mod_any(st.g[j], hp.m, hp.M);
+                w[j] = ldg32(filt + (idx >> 5));
+                bit[j] = (uint32_t)idx & 31u;
+            }
+        }
+    }
+    uint32_t died = 0;
+#pragma unroll
+    for (int j = J0; j < J1; ++j) {
+        if (!((w[j] >> bit[j]) & 1u)) {
+            st.alive &= ~(1u << j);
+            ++died;
+        }
+    }
+    return died;  // this lane's k-mers found absent in this phase
 }
+
+// Returns true when the pair's outcome is decided (failed or passed set); hits/misses updated otherwise.
+template <int G, bool SMALL_M>
+PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, uint32_t n_steps,
+                      const uint64_t *__restrict__ hbp, uint32_t gbase, uint32_t n_k, uint32_t lane, uint32_t need,
+                      uint32_t allowed, bool exhaustive, uint32_t &hits, uint32_t &misses, uint32_t &probes,
+                      bool &pass) {
+    GroupState<G, SMALL_M> st;
+    st.alive = 0;
+    uint64_t hb[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        const uint32_t pos = gbase + (uint32_t)j * 32u + lane;
+        hb[j] = 0;
+        if (pos < n_k) {
+            hb[j] = __ldg(hbp + pos);
+            st.alive |= 1u << j;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        st.h1[j] = fx_finish(hp.c1, hb[j], hp.rot);
+        st.h2[j] = fx_finish(hp.c2, hb[j], hp.rot);
+        st.g[j] = st.h1[j];
+    }
+    const uint32_t cnt = min(32u * G, n_k - gbase);
+    const uint32_t limit = allowed - misses;  // only used when !exhaustive (misses <= allowed then)
+    uint32_t dead = 0;
+    // step 0, first round
+    probes += min(32u, cnt);
+    dead += __reduce_add_sync(0xFFFFFFFFu, probe_phase<G, SMALL_M, 0, 1>(filt, hp, st));
+    if (!exhaustive && dead > limit) {
+        pass = false;
+        return true;
+    }
+    // step 0, remaining rounds
+    if (G > 1 && cnt > 32u) {
+        probes += cnt - 32u;
+        dead += __reduce_add_sync(0xFFFFFFFFu, probe_phase<G, SMALL_M, (G > 1 ? 1 : 0), G>(filt, hp, st));
+        if (!exhaustive && dead > limit) {
+            pass = false;
+            return true;
+        }
+    }
+    for (uint32_t i = 1; i < n_steps; ++i) {
+        const uint32_t n_alive = cnt - dead;
+        if (n_alive == 0u) break;
+        probes += n_alive;
+#pragma unroll
+        for (int j = 0; j < G; ++j) st.g[j] = i == 1 ? st.h2[j] : (i == 2 ? (st.h1[j] + 2ULL) * st.h2[j] : st.g[j] + st.h2[j]);
+        dead += __reduce_add_sync(0xFFFFFFFFu, probe_phase<G, SMALL_M, 0, G>(filt, hp, st));
+        if (!exhaustive && dead > limit) {
+            pass = false;
+            return true;
+        }
+    }
+    misses += dead;
+    hits += cnt - dead;
+    if (!exhaustive && hits >= need) {
+        pass = true;
+        return true;
+    }
+    return false;
+}
+
+struct PairMeta {
+    uint32_t r, u, len, slot, steps;
+    uint64_t koff;
+};
 
 // Evaluate one (read,node) pair; warp-uniform control flow.  Returns pass/fail (query_passes).
-template <int KM>
-PF_D bool probe_pair(const ProbeArgs &a, uint32_t r, uint32_t u, uint32_t lane, uint32_t &probes) {
+template <int G, bool SMALL_M>
+PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, uint32_t &probes) {
     const HashParams &hp = a.hp;
-    const uint32_t len = ldg32(a.lengths + r);
-    const uint32_t k = hp.k;
-    const uint32_t n_k = (k == 0u || k > len) ? 0u : len - k + 1u;  // file_parser.rs:136-139
+    const uint32_t n_k = kmers_of(pm.len, hp.k);
     const uint32_t need = need_of(a.threshold, n_k);
     const bool exhaustive = a.exhaustive != 0;
     if (!exhaustive) {
@@ -117,60 +255,22 @@ PF_D bool probe_pair(const ProbeArgs &a, uint32_t r, uint32_t u, uint32_t lane, 
         if (need > n_k) return false;  // hits <= n_k < need
     }
     const uint32_t allowed = need > n_k ? 0u : n_k - need;
-    const uint32_t *filt =
-        reinterpret_cast<const uint32_t *>(a.filters + (uint64_t)ldg32(a.node_slot + u) * a.words_per_filter);
-    const uint64_t woff = __ldg(a.word_off + r);
-    uint32_t e = a.exc_index ? ldg32(a.exc_index + r) : NONE32_D;
+    const uint32_t *filt = reinterpret_cast<const uint32_t *>(a.filters + (uint64_t)pm.slot * a.words_per_filter);
+    const uint64_t *hbp = a.hb + (pm.koff - a.kmer_base);
     uint32_t hits = 0, misses = 0;
-    bool failed = false;
-
-    if (KM != 0 && e == NONE32_D) {
-        const uint64_t *w64 = reinterpret_cast<const uint64_t *>(a.packed + woff);
-        for (uint32_t base = 0; base < n_k; base += 32u) {
-            const uint64_t lo = __ldg(w64 + (base >> 5)), hi = __ldg(w64 + (base >> 5) + 1);
-            const uint32_t sh = 2u * lane;
-            const uint64_t x = (lo >> sh) | ((hi << 1) << (63u - sh));
-            const uint64_t hb = canonical_hash_2bit<(KM ? KM : 17)>(x);
-            const uint64_t h1 = fx_finish(hp.c1, hb, hp.rot), h2 = fx_finish(hp.c2, hb, hp.rot);
-            const bool active = base + lane < n_k;
-            const uint32_t cnt = min(32u, n_k - base);
-            const uint32_t ok = probe_round<true>(filt, hp, h1, h2, active, misses, allowed, exhaustive, probes, failed);
-            if (failed) return false;
-            const uint32_t h = __popc(ok);
-            hits += h;
-            misses += cnt - h;
-            if (!exhaustive && hits >= need) return true;
-        }
-    } else {
-        ByteSrc s;
-        s.ascii = e == NONE32_D ? nullptr : a.exc_bytes + __ldg(a.exc_off + e);
-        s.packed = a.packed + woff;
-        for (uint32_t base = 0; base < n_k; base += 32u) {
-            const uint32_t pos = base + lane;
-            const bool active = pos < n_k;
-            uint64_t h1 = 0, h2 = 0;
-            if (active) {
-                const uint64_t hb = canonical_hash_bytes([&](uint32_t j) { return src_byte(s, pos + j); }, k);
-                h1 = fx_finish(hp.c1, hb, hp.rot);
-                h2 = fx_finish(hp.c2, hb, hp.rot);
-            }
-            const uint32_t cnt = min(32u, n_k - base);
-            uint32_t ok;
-            if (hp.small_m) ok = probe_round<true>(filt, hp, h1, h2, active, misses, allowed, exhaustive, probes, failed);
-            else ok = probe_round<false>(filt, hp, h1, h2, active, misses, allowed, exhaustive, probes, failed);
-            if (failed) return false;
-            const uint32_t h = __popc(ok);
-            hits += h;
-            misses += cnt - h;
-            if (!exhaustive && hits >= need) return true;
-        }
-    }
+    bool pass = false;
+    for (uint32_t gbase = 0; gbase < n_k; gbase += 32u * G)
+        if (probe_group<G, SMALL_M>(filt, hp, pm.steps, hbp, gbase, n_k, lane, need, allowed, exhaustive, hits, misses,
+                                    probes, pass))
+            return pass;
     return hits >= need;
 }
 
-// Persistent grid; warps pull PROBE_CHUNK consecutive pairs at a time from a global counter.
-template <int KM>
-__global__ void __launch_bounds__(PROBE_THREADS, 4) probe_kernel(const ProbeArgs a) {
+// Persistent grid; warps pull PROBE_CHUNK consecutive pairs at a time from a global counter.  The chunk's
+// pair records and per-read / per-node metadata are fetched by PROBE_CHUNK lanes in parallel (two dependent
+// memory round trips per chunk instead of per pair) and broadcast with shuffles.
+template <int G, bool SMALL_M>
+__global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : 4)) probe_kernel(const ProbeArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t probes = 0;
     unsigned long long probes_total = 0;
@@ -179,14 +279,31 @@ __global__ void __launch_bounds__(PROBE_THREADS, 4) probe_kernel(const ProbeArgs
         if (lane == 0) i0 = atomicAdd(a.work_ctr, (unsigned)PROBE_CHUNK);
         i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
         if (i0 >= a.n_pairs) break;
-        const uint32_t i1 = min(i0 + (uint32_t)PROBE_CHUNK, a.n_pairs);
-        for (uint32_t i = i0; i < i1; ++i) {
-            const uint32_t r = ldg32(a.fr_read + i), u = ldg32(a.fr_node + i);
-            const bool pass = probe_pair<KM>(a, r, u, lane, probes);
-            if (lane == 0) {
-                a.pass[i] = pass ? 1 : 0;
-                if (pass) atomicAdd(a.node_pass + u, 1u);
-            }
+        const uint32_t n_here = min((uint32_t)PROBE_CHUNK, a.n_pairs - i0);
+        PairMeta mine{};
+        if (lane < n_here) {
+            mine.r = ldg32(a.fr_read + i0 + lane);
+            mine.u = ldg32(a.fr_node + i0 + lane);
+            mine.len = ldg32(a.lengths + mine.r);
+            mine.koff = __ldg(a.kmer_off + mine.r);
+            mine.slot = ldg32(a.node_slot + mine.u);
+            mine.steps = ldg32(a.node_steps + mine.u);
+        }
+        uint32_t pass_bits = 0;
+        for (uint32_t p = 0; p < n_here; ++p) {
+            PairMeta pm;
+            pm.r = __shfl_sync(0xFFFFFFFFu, mine.r, p);
+            pm.u = __shfl_sync(0xFFFFFFFFu, mine.u, p);
+            pm.len = __shfl_sync(0xFFFFFFFFu, mine.len, p);
+            pm.slot = __shfl_sync(0xFFFFFFFFu, mine.slot, p);
+            pm.steps = __shfl_sync(0xFFFFFFFFu, mine.steps, p);
+            pm.koff = __shfl_sync(0xFFFFFFFFu, mine.koff, p);
+            if (probe_pair<G, SMALL_M>(a, pm, lane, probes)) pass_bits |= 1u << p;
+        }
+        if (lane < n_here) {
+            const bool pass = (pass_bits >> lane) & 1u;
+            a.pass[i0 + lane] = pass ? 1 : 0;
+            if (pass) atomicAdd(a.node_pass + mine.u, 1u);
         }
         probes_total += probes;
         probes = 0;
@@ -195,9 +312,9 @@ __global__ void __launch_bounds__(PROBE_THREADS, 4) probe_kernel(const ProbeArgs
 }
 
 // ---- frontier bookkeeping ------------------------------------------------------------------
-__global__ void init_frontier_kernel(uint32_t *fr_read, uint32_t *fr_node, uint32_t n) {
+__global__ void init_frontier_kernel(uint32_t *fr_read, uint32_t *fr_node, uint32_t read0, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        fr_read[i] = i;
+        fr_read[i] = read0 + i;
         fr_node[i] = 0u;  // root has level-order id 0
     }
 }
@@ -301,6 +418,37 @@ __global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, const uint3
             nx_node[p] = rr;
         }
     }
+}
+
+// ---- load-time analysis of the tree --------------------------------------------------------------
+// pop[slot] += popcount(filter[slot]); grid = (blocks, n_slots_in_chunk)
+__global__ void fill_kernel(const uint64_t *__restrict__ filters, uint64_t wpf, uint32_t slot0, unsigned long long *pop) {
+    const uint32_t slot = slot0 + blockIdx.y;
+    const uint64_t *f = filters + (uint64_t)slot * wpf;
+    unsigned long long c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < wpf; i += (uint64_t)gridDim.x * blockDim.x)
+        c += __popcll(f[i]);
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(pop + slot, c);
+}
+// viol[u] += popcount(filter(child) & ~filter(u)) over both children; grid = (blocks, nodes_in_chunk)
+__global__ void subset_kernel(const uint64_t *__restrict__ filters, uint64_t wpf, const uint32_t *__restrict__ slot,
+                              const uint32_t *__restrict__ left, const uint32_t *__restrict__ right, uint32_t node0,
+                              unsigned long long *viol) {
+    const uint32_t u = node0 + blockIdx.y;
+    const uint32_t l = left[u], r = right[u];
+    if (l == NONE32_D && r == NONE32_D) return;
+    const uint64_t *fu = filters + (uint64_t)slot[u] * wpf;
+    const uint64_t *fl = l != NONE32_D ? filters + (uint64_t)slot[l] * wpf : nullptr;
+    const uint64_t *fr = r != NONE32_D ? filters + (uint64_t)slot[r] * wpf : nullptr;
+    unsigned long long c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < wpf; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p = ~fu[i];
+        if (fl) c += __popcll(fl[i] & p);
+        if (fr) c += __popcll(fr[i] & p);
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(viol + u, c);
 }
 
 __global__ void add_counts_kernel(unsigned long long *dst, const unsigned long long *src, uint32_t n) {

@@ -96,14 +96,17 @@ struct pf_dev_batch {
     uint32_t n_reads = 0, n_exc = 0;
     uint64_t n_words = 0, exc_nbytes = 0;
     DevBuf<uint32_t> lengths, packed, exc_index;
-    DevBuf<uint64_t> word_off, exc_off;
+    DevBuf<uint64_t> word_off, exc_off, kmer_off;
     DevBuf<uint8_t> exc_bytes;
+    std::vector<uint64_t> h_kmer_off;  // [n_reads + 1] prefix sum of k-mer counts (host copy for chunking)
+    uint64_t kmer_size = 0, max_kmers = 0;
     uint64_t bytes = 0;
     void release() {
         lengths.release();
         packed.release();
         exc_index.release();
         word_off.release();
+        kmer_off.release();
         exc_off.release();
         exc_bytes.release();
     }
@@ -158,6 +161,14 @@ struct pf_db {
     BfHeader geom;
     HashParams hp{};
     int exhaustive = 0;
+    int lazy = 1;                      // step-limited pre-test at verified-monotone interior nodes
+    std::vector<uint64_t> h_pop;       // set bits of each node's filter
+    std::vector<uint8_t> h_mono;       // interior node whose filter contains both children's filters
+    std::vector<uint32_t> h_steps;     // probe steps per node for the current (threshold, mode)
+    uint32_t *d_steps = nullptr;
+    float steps_theta = -1.f;
+    int steps_mode = -1;
+    uint64_t n_internal = 0, n_monotone = 0;
     // device tree
     uint32_t *d_left = nullptr, *d_right = nullptr, *d_slot = nullptr;
     int32_t *d_leaf = nullptr;
@@ -171,6 +182,8 @@ struct pf_db {
     LevelTotals *d_totals = nullptr, *h_totals = nullptr;
     DevBuf<uint32_t> fr_read[2], fr_node[2], hit_read, hit_leaf;
     DevBuf<uint8_t> pass;
+    DevBuf<uint64_t> hb;                       // cached hash_bytes per k-mer of the current chunk
+    uint64_t hash_cache_bytes = 16ULL << 30;   // chunk reads so the cache stays below this
     pf_dev_batch own_batch;  // device copy used by pf_query_block
     // outputs
     std::vector<uint64_t> out_off;
@@ -191,6 +204,7 @@ static void db_free(pf_db *db) {
     cudaFree(db->d_slot);
     cudaFree(db->d_leaf);
     cudaFree(db->d_filters);
+    cudaFree(db->d_steps);
     cudaFree(db->d_counts);
     cudaFree(db->d_blk_counts);
     cudaFree(db->d_node_pass);
@@ -207,6 +221,7 @@ static void db_free(pf_db *db) {
     db->hit_read.release();
     db->hit_leaf.release();
     db->pass.release();
+    db->hb.release();
     db->own_batch.release();
     if (db->ev_begin) cudaEventDestroy(db->ev_begin);
     if (db->ev_end) cudaEventDestroy(db->ev_end);
@@ -296,6 +311,8 @@ static int upload(T **dst, const std::vector<T> &v, cudaStream_t s) {
     if (!v.empty()) PF_CUDA_OK(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
     return PF_OK;
 }
+
+static int analyse_tree(pf_db *db);
 
 static int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     int ndev = 0;
@@ -394,33 +411,127 @@ static int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     PF_CUDA_OK(cudaMalloc(&db->d_totals, sizeof(LevelTotals)));
     PF_CUDA_OK(cudaMallocHost(&db->h_totals, sizeof(LevelTotals)));
     PF_CUDA_OK(cudaMemsetAsync(db->d_counts, 0, nl * 8, db->stream));
+    PF_CUDA_OK(cudaMalloc(&db->d_steps, nn * 4));
+    if ((rc = analyse_tree(db))) return rc;
     PF_CUDA_OK(cudaEventCreate(&db->ev_begin));
     PF_CUDA_OK(cudaEventCreate(&db->ev_end));
     PF_CUDA_OK(cudaStreamSynchronize(db->stream));
     return PF_OK;
 }
 
-// ---- probe kernel dispatch on k ----------------------------------------------------------------
-template <int KM>
-static void launch_probe_k(const ProbeArgs &a, int grid, cudaStream_t s) {
-    probe_kernel<KM><<<grid, PROBE_THREADS, 0, s>>>(a);
-}
-static bool fast_path_ok(const HashParams &hp) { return hp.k >= 17 && hp.k <= 32 && hp.small_m; }
-static void launch_probe(const ProbeArgs &a, int grid, cudaStream_t s) {
-    if (!fast_path_ok(a.hp)) {
-        launch_probe_k<0>(a, grid, s);
-        return;
+// Load-time analysis: fill of every filter and, per interior node, whether its filter is a bitwise
+// superset of its children's.  Where that holds, "child passes => parent passes" for every read and
+// threshold (a k-mer contained in the child has all K bits set in the parent too), so the parent only
+// needs a sound cannot-pass test; the reference's u16 name collisions (bloom_tree.rs:232-234) can break
+// the superset property, and such nodes stay exact.
+static int analyse_tree(pf_db *db) {
+    const size_t nn = db->n_nodes;
+    unsigned long long *d_pop = nullptr, *d_viol = nullptr;
+    PF_CUDA_OK(cudaMalloc(&d_pop, std::max<size_t>(db->n_slots, 1) * 8));
+    PF_CUDA_OK(cudaMalloc(&d_viol, nn * 8));
+    PF_CUDA_OK(cudaMemsetAsync(d_pop, 0, std::max<size_t>(db->n_slots, 1) * 8, db->stream));
+    PF_CUDA_OK(cudaMemsetAsync(d_viol, 0, nn * 8, db->stream));
+    const uint32_t bx = (uint32_t)std::min<uint64_t>((db->wpf + 1023) / 1024, 64);
+    for (uint64_t s0 = 0; s0 < db->n_slots; s0 += 65535) {
+        const uint32_t ny = (uint32_t)std::min<uint64_t>(65535, db->n_slots - s0);
+        fill_kernel<<<dim3(bx, ny), 256, 0, db->stream>>>(db->d_filters, db->wpf, (uint32_t)s0, d_pop);
     }
-    switch (a.hp.k) {
+    for (uint64_t u0 = 0; u0 < nn; u0 += 65535) {
+        const uint32_t ny = (uint32_t)std::min<uint64_t>(65535, nn - u0);
+        subset_kernel<<<dim3(bx, ny), 256, 0, db->stream>>>(db->d_filters, db->wpf, db->d_slot, db->d_left, db->d_right,
+                                                           (uint32_t)u0, d_viol);
+    }
+    std::vector<unsigned long long> pop(std::max<size_t>(db->n_slots, 1)), viol(nn);
+    cudaMemcpyAsync(pop.data(), d_pop, db->n_slots * 8, cudaMemcpyDeviceToHost, db->stream);
+    cudaMemcpyAsync(viol.data(), d_viol, nn * 8, cudaMemcpyDeviceToHost, db->stream);
+    cudaError_t e = cudaStreamSynchronize(db->stream);
+    cudaFree(d_pop);
+    cudaFree(d_viol);
+    PF_CUDA_OK(e);
+    PF_CUDA_OK(cudaGetLastError());
+    db->h_pop.resize(nn);
+    db->h_mono.assign(nn, 0);
+    db->n_internal = db->n_monotone = 0;
+    for (size_t u = 0; u < nn; ++u) {
+        db->h_pop[u] = pop[db->h_slot[u]];
+        if (db->h_leaf[u] >= 0) continue;
+        db->n_internal++;
+        db->h_mono[u] = viol[u] == 0;
+        db->n_monotone += db->h_mono[u];
+    }
+    return PF_OK;
+}
+
+// Probe steps per node.  Leaves, unverified nodes and the reference-faithful modes use all K steps.
+// A verified-monotone interior node with fill f uses the smallest s with f^s <= 0.75 * threshold: a k-mer
+// that is absent then survives the pre-test with probability <= 0.75*threshold, so reads that do not
+// belong below the node are still pruned there, while reads that do belong cost s instead of K probes.
+static uint32_t lazy_steps(double fill, double theta, uint32_t K) {
+    const double target = 0.75 * theta;
+    double p = fill;
+    uint32_t s = 1;
+    while (p > target && s < K) {
+        p *= fill;
+        ++s;
+    }
+    return s;
+}
+static int update_steps(pf_db *db, float threshold) {
+    const int mode = db->exhaustive ? 2 : (db->lazy ? 1 : 0);
+    if (mode == db->steps_mode && (mode != 1 || threshold == db->steps_theta)) return PF_OK;
+    const uint32_t K = db->geom.num_hashes;
+    db->h_steps.assign(db->n_nodes, K);
+    if (mode == 1) {
+        for (size_t u = 0; u < db->n_nodes; ++u)
+            if (db->h_leaf[u] < 0 && db->h_mono[u])
+                db->h_steps[u] = lazy_steps((double)db->h_pop[u] / (double)db->geom.num_bits, (double)threshold, K);
+    }
+    PF_CUDA_OK(cudaMemcpyAsync(db->d_steps, db->h_steps.data(), db->n_nodes * 4, cudaMemcpyHostToDevice, db->stream));
+    PF_CUDA_OK(cudaStreamSynchronize(db->stream));
+    db->steps_mode = mode;
+    db->steps_theta = threshold;
+    return PF_OK;
+}
+
+// ---- kernel dispatch ---------------------------------------------------------------------------
+static bool fast_path_ok(const HashParams &hp) { return hp.k >= 17 && hp.k <= 32; }
+template <int KM>
+static void launch_hash_k(const HashArgs &a, int grid, cudaStream_t s) {
+    hash_kernel<KM><<<grid, HASH_THREADS, 0, s>>>(a);
+}
+static void launch_hash(const HashArgs &a, int grid, cudaStream_t s) {
+    switch (a.k) {
 #define PF_CASE(K) \
     case K:        \
-        launch_probe_k<K>(a, grid, s); \
+        launch_hash_k<K>(a, grid, s); \
         break;
         PF_CASE(17) PF_CASE(18) PF_CASE(19) PF_CASE(20) PF_CASE(21) PF_CASE(22) PF_CASE(23) PF_CASE(24)
         PF_CASE(25) PF_CASE(26) PF_CASE(27) PF_CASE(28) PF_CASE(29) PF_CASE(30) PF_CASE(31) PF_CASE(32)
 #undef PF_CASE
         default:
-            launch_probe_k<0>(a, grid, s);
+            launch_hash_k<0>(a, grid, s);  // byte path for every other k
+    }
+}
+// Rounds of 32 k-mers a lane owns at once: enough to cover the longest read of the batch, at most 8.
+static uint32_t group_rounds_for(uint64_t max_kmers, bool small_m) {
+    if (!small_m) return 1;  // 64-bit remainder path (m >= 2^31): kept simple
+    return (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (max_kmers + 31) / 32));
+}
+static void launch_probe(const ProbeArgs &a, uint32_t G, int sm_count, cudaStream_t s) {
+    const int g4 = sm_count * 4, g6 = sm_count * 6;
+    if (!a.hp.small_m) {
+        probe_kernel<1, false><<<g6, PROBE_THREADS, 0, s>>>(a);
+        return;
+    }
+    switch (G) {
+        case 1: probe_kernel<1, true><<<g6, PROBE_THREADS, 0, s>>>(a); break;
+        case 2: probe_kernel<2, true><<<g6, PROBE_THREADS, 0, s>>>(a); break;
+        case 3: probe_kernel<3, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
+        case 4: probe_kernel<4, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
+        case 5: probe_kernel<5, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
+        case 6: probe_kernel<6, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
+        case 7: probe_kernel<7, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
+        default: probe_kernel<8, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
     }
 }
 
@@ -433,7 +544,8 @@ static int ensure_events(pf_db *db, size_t n) {
     return PF_OK;
 }
 
-// The level-synchronous descent for one resident batch.
+// The level-synchronous descent for one resident batch.  Reads are processed in chunks whose cached k-mer
+// hashes (8 B per k-mer) fit the hash-cache budget; hits and counters accumulate over the chunks.
 static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, pf_hits *out) {
     PF_CUDA_OK(cudaSetDevice(db->device));
     cudaStream_t s = db->stream;
@@ -447,76 +559,116 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         if (out) out->read_off = db->out_off.data();
         return PF_OK;
     }
-    if ((rc = ensure_events(db, 2 * n_levels))) return rc;
+    if (bt->kmer_size != db->tree.kmer_size) {
+        set_error("batch was uploaded for k=%llu but the database has k=%llu", (unsigned long long)bt->kmer_size,
+                  (unsigned long long)db->tree.kmer_size);
+        return PF_ERR_STATE;
+    }
+    if ((rc = update_steps(db, threshold))) return rc;
     PF_CUDA_OK(cudaEventRecord(db->ev_begin, s));
-    PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, 2 * db->n_nodes * 4, s));
-    PF_CUDA_OK(cudaMemsetAsync(db->d_work, 0, db->level_start.size() * 4, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_blk_counts, 0, std::max<uint64_t>(db->n_leaves, 1) * 8, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_probes, 0, 8, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_totals, 0, sizeof(LevelTotals), s));
-    if ((rc = db->fr_read[0].ensure(n_reads)) || (rc = db->fr_node[0].ensure(n_reads))) return rc;
-    init_frontier_kernel<<<std::min<uint32_t>((n_reads + 255) / 256, 4096), 256, 0, s>>>(db->fr_read[0].p,
-                                                                                        db->fr_node[0].p, n_reads);
-    uint64_t other_launches = 1, probe_launches = 0, pairs = 0, levels = 0, hits_total = 0, probes = 0;
-    uint64_t n = n_reads, hits_before = 0;
-    int cur = 0;
-    const int grid = db->sm_count * 4;
-    for (size_t l = 0; l < n_levels && n > 0; ++l) {
-        if ((rc = db->pass.ensure(n))) return rc;
-        ProbeArgs a{};
-        a.fr_read = db->fr_read[cur].p;
-        a.fr_node = db->fr_node[cur].p;
-        a.n_pairs = (uint32_t)n;
-        a.lengths = bt->lengths.p;
-        a.word_off = bt->word_off.p;
-        a.packed = bt->packed.p;
-        a.exc_index = bt->n_exc ? bt->exc_index.p : nullptr;
-        a.exc_off = bt->exc_off.p;
-        a.exc_bytes = bt->exc_bytes.p;
-        a.node_slot = db->d_slot;
-        a.filters = db->d_filters;
-        a.words_per_filter = db->wpf;
-        a.pass = db->pass.p;
-        a.node_pass = db->d_node_pass;
-        a.work_ctr = db->d_work + l;
-        a.probes = db->d_probes;
-        a.hp = db->hp;
-        a.threshold = threshold;
-        a.exhaustive = db->exhaustive;
-        PF_CUDA_OK(cudaEventRecord(db->ev_probe[2 * l], s));
-        launch_probe(a, grid, s);
-        PF_CUDA_OK(cudaEventRecord(db->ev_probe[2 * l + 1], s));
-        probe_launches++;
-        pairs += n;
-        levels++;
-        level_scan_kernel<<<1, 1024, 0, s>>>(db->level_start[l], db->level_start[l + 1], db->d_node_pass, db->d_left,
-                                             db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base, db->d_blk_counts,
-                                             db->d_totals, db->d_probes);
-        other_launches++;
-        PF_CUDA_OK(cudaMemcpyAsync(db->h_totals, db->d_totals, sizeof(LevelTotals), cudaMemcpyDeviceToHost, s));
-        PF_CUDA_OK(cudaStreamSynchronize(s));
-        const uint64_t next_n = db->h_totals->next_pairs;
-        hits_total = db->h_totals->hits_total;
-        probes = db->h_totals->probes;
-        if (next_n > 0xFFFFFFF0ULL) {
-            set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
-                      (unsigned long long)next_n);
-            return PF_ERR_NOMEM;
+    uint64_t other_launches = 0, probe_launches = 0, pairs = 0, levels = 0, hits_total = 0, probes = 0, hits_before = 0;
+    size_t n_ev = 0;
+    const uint32_t G = group_rounds_for(bt->max_kmers, db->hp.small_m != 0);
+    db->stats.group_rounds = G;
+    const uint64_t budget_kmers = std::max<uint64_t>(db->hash_cache_bytes / 8, 1);
+    const std::vector<uint64_t> &ko = bt->h_kmer_off;
+    for (uint32_t r0 = 0; r0 < n_reads;) {
+        // chunk [r0, r1): as many reads as the hash cache holds (always at least one)
+        uint32_t r1 = (uint32_t)(std::upper_bound(ko.begin() + r0 + 1, ko.begin() + n_reads + 1, ko[r0] + budget_kmers) -
+                                 ko.begin()) - 1;
+        if (r1 <= r0) r1 = r0 + 1;
+        const uint32_t n_chunk = r1 - r0;
+        const uint64_t chunk_kmers = ko[r1] - ko[r0];
+        if ((rc = db->hb.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
+        PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, 2 * db->n_nodes * 4, s));
+        PF_CUDA_OK(cudaMemsetAsync(db->d_work, 0, db->level_start.size() * 4, s));
+        if ((rc = db->fr_read[0].ensure(n_chunk)) || (rc = db->fr_node[0].ensure(n_chunk))) return rc;
+        HashArgs h{};
+        h.lengths = bt->lengths.p;
+        h.word_off = bt->word_off.p;
+        h.packed = bt->packed.p;
+        h.exc_index = bt->n_exc ? bt->exc_index.p : nullptr;
+        h.exc_off = bt->exc_off.p;
+        h.exc_bytes = bt->exc_bytes.p;
+        h.kmer_off = bt->kmer_off.p;
+        h.hb = db->hb.p;
+        h.kmer_base = ko[r0];
+        h.read0 = r0;
+        h.n_reads = n_chunk;
+        h.k = db->hp.k;
+        h.work_ctr = db->d_work + n_levels;
+        if (chunk_kmers) {
+            launch_hash(h, db->sm_count * 8, s);
+            other_launches++;
         }
-        const int nxt = cur ^ 1;
-        if (next_n && ((rc = db->fr_read[nxt].ensure(next_n)) || (rc = db->fr_node[nxt].ensure(next_n)))) return rc;
-        // hits of earlier levels live in the same arrays: grow with copy
-        if (want_hits && hits_total &&
-            ((rc = db->hit_read.grow_keep(hits_total, hits_before, s)) || (rc = db->hit_leaf.grow_keep(hits_total, hits_before, s))))
-            return rc;
-        hits_before = hits_total;
-        scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(
-            db->fr_read[cur].p, db->fr_node[cur].p, db->pass.p, (uint32_t)n, db->d_node_pass, db->d_cursor, db->d_left,
-            db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base, db->fr_read[nxt].p, db->fr_node[nxt].p,
-            db->hit_read.p, db->hit_leaf.p, want_hits);
+        init_frontier_kernel<<<std::min<uint32_t>((n_chunk + 255) / 256, 4096), 256, 0, s>>>(db->fr_read[0].p,
+                                                                                             db->fr_node[0].p, r0, n_chunk);
         other_launches++;
-        n = next_n;
-        cur = nxt;
+        uint64_t n = n_chunk;
+        int cur = 0;
+        for (size_t l = 0; l < n_levels && n > 0; ++l) {
+            if ((rc = db->pass.ensure(n))) return rc;
+            ProbeArgs a{};
+            a.fr_read = db->fr_read[cur].p;
+            a.fr_node = db->fr_node[cur].p;
+            a.n_pairs = (uint32_t)n;
+            a.lengths = bt->lengths.p;
+            a.kmer_off = bt->kmer_off.p;
+            a.hb = db->hb.p;
+            a.kmer_base = ko[r0];
+            a.node_slot = db->d_slot;
+            a.node_steps = db->d_steps;
+            a.filters = db->d_filters;
+            a.words_per_filter = db->wpf;
+            a.pass = db->pass.p;
+            a.node_pass = db->d_node_pass;
+            a.work_ctr = db->d_work + l;
+            a.probes = db->d_probes;
+            a.hp = db->hp;
+            a.threshold = threshold;
+            a.exhaustive = db->exhaustive;
+            if ((rc = ensure_events(db, n_ev + 2))) return rc;
+            PF_CUDA_OK(cudaEventRecord(db->ev_probe[n_ev], s));
+            launch_probe(a, G, db->sm_count, s);
+            PF_CUDA_OK(cudaEventRecord(db->ev_probe[n_ev + 1], s));
+            n_ev += 2;
+            probe_launches++;
+            pairs += n;
+            levels++;
+            level_scan_kernel<<<1, 1024, 0, s>>>(db->level_start[l], db->level_start[l + 1], db->d_node_pass, db->d_left,
+                                                 db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base,
+                                                 db->d_blk_counts, db->d_totals, db->d_probes);
+            other_launches++;
+            PF_CUDA_OK(cudaMemcpyAsync(db->h_totals, db->d_totals, sizeof(LevelTotals), cudaMemcpyDeviceToHost, s));
+            PF_CUDA_OK(cudaStreamSynchronize(s));
+            const uint64_t next_n = db->h_totals->next_pairs;
+            hits_total = db->h_totals->hits_total;
+            probes = db->h_totals->probes;
+            if (next_n > 0xFFFFFFF0ULL) {
+                set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
+                          (unsigned long long)next_n);
+                return PF_ERR_NOMEM;
+            }
+            const int nxt = cur ^ 1;
+            if (next_n && ((rc = db->fr_read[nxt].ensure(next_n)) || (rc = db->fr_node[nxt].ensure(next_n)))) return rc;
+            // hits of earlier levels and chunks live in the same arrays: grow with copy
+            if (want_hits && hits_total &&
+                ((rc = db->hit_read.grow_keep(hits_total, hits_before, s)) ||
+                 (rc = db->hit_leaf.grow_keep(hits_total, hits_before, s))))
+                return rc;
+            hits_before = hits_total;
+            scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(
+                db->fr_read[cur].p, db->fr_node[cur].p, db->pass.p, (uint32_t)n, db->d_node_pass, db->d_cursor,
+                db->d_left, db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base, db->fr_read[nxt].p,
+                db->fr_node[nxt].p, db->hit_read.p, db->hit_leaf.p, want_hits);
+            other_launches++;
+            n = next_n;
+            cur = nxt;
+        }
+        r0 = r1;
     }
     add_counts_kernel<<<(uint32_t)((db->n_leaves + 255) / 256), 256, 0, s>>>(db->d_counts, db->d_blk_counts,
                                                                             (uint32_t)db->n_leaves);
@@ -540,7 +692,8 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         std::vector<uint64_t> fill(db->out_off.begin(), db->out_off.end() - 1);
         for (uint64_t i = 0; i < hits_total; ++i) db->out_leaf[fill[db->tmp_read[i]]++] = db->tmp_leaf[i];
         for (uint32_t r = 0; r < n_reads; ++r)
-            std::sort(db->out_leaf.begin() + db->out_off[r], db->out_leaf.begin() + db->out_off[r + 1]);
+            if (db->out_off[r + 1] - db->out_off[r] > 1)
+                std::sort(db->out_leaf.begin() + db->out_off[r], db->out_leaf.begin() + db->out_off[r + 1]);
         if (out) {
             out->n_hits = hits_total;
             out->read_off = db->out_off.data();
@@ -552,9 +705,9 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     float ms = 0.f;
     cudaEventElapsedTime(&ms, db->ev_begin, db->ev_end);
     db->stats.device_ms += ms;
-    for (size_t l = 0; l < levels; ++l) {
+    for (size_t e = 0; e + 1 < n_ev; e += 2) {
         float pm = 0.f;
-        cudaEventElapsedTime(&pm, db->ev_probe[2 * l], db->ev_probe[2 * l + 1]);
+        cudaEventElapsedTime(&pm, db->ev_probe[e], db->ev_probe[e + 1]);
         db->stats.probe_kernel_ms += pm;
     }
     db->stats.blocks++;
@@ -593,6 +746,17 @@ static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b
     PF_CUDA_OK(cudaMemcpyAsync(b->packed.p, in->packed, (size_t)in->n_words * 4, cudaMemcpyHostToDevice, s));
     PF_CUDA_OK(cudaMemsetAsync(b->packed.p + in->n_words, 0, 16, s));
     b->bytes = (uint64_t)in->n_reads * 12 + in->n_words * 4;
+    // k-mer offsets (device-side bookkeeping derived from `lengths`; not part of the host batch)
+    b->kmer_size = db->tree.kmer_size;
+    b->h_kmer_off.assign((size_t)in->n_reads + 1, 0);
+    b->max_kmers = 0;
+    for (uint32_t r = 0; r < in->n_reads; ++r) {
+        const uint64_t nk = kmers_of(in->lengths[r], (uint32_t)db->tree.kmer_size);
+        b->h_kmer_off[r + 1] = b->h_kmer_off[r] + nk;
+        b->max_kmers = std::max(b->max_kmers, nk);
+    }
+    if ((rc = b->kmer_off.ensure((size_t)in->n_reads + 1))) return rc;
+    PF_CUDA_OK(cudaMemcpyAsync(b->kmer_off.p, b->h_kmer_off.data(), ((size_t)in->n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
     if (in->n_exc) {
         b->exc_nbytes = in->exc_off[in->n_exc];
         if ((rc = b->exc_index.ensure(in->n_reads)) || (rc = b->exc_off.ensure((size_t)in->n_exc + 1)) ||
@@ -655,6 +819,8 @@ int pf_db_info(const pf_db *db, pf_db_info_t *o) {
     o->device = db->device;
     o->hash_rot = (int32_t)db->hp.rot;
     o->fast_path = fast_path_ok(db->hp) ? 1 : 0;
+    o->n_internal = db->n_internal;
+    o->n_monotone = db->n_monotone;
     return PF_OK;
 }
 
@@ -675,6 +841,24 @@ int pf_db_set_hash_rot(pf_db *db, int rot) {
 int pf_db_set_exhaustive(pf_db *db, int on) {
     if (!db) return PF_ERR_ARG;
     db->exhaustive = on ? 1 : 0;
+    return PF_OK;
+}
+int pf_db_set_hash_cache_bytes(pf_db *db, uint64_t bytes) {
+    if (!db || bytes < 8) return PF_ERR_ARG;
+    db->hash_cache_bytes = bytes;
+    return PF_OK;
+}
+int pf_db_set_lazy(pf_db *db, int on) {
+    if (!db) return PF_ERR_ARG;
+    db->lazy = on ? 1 : 0;
+    return PF_OK;
+}
+int pf_db_node_steps(pf_db *db, float threshold, uint32_t *steps) {
+    if (!db || !steps) return PF_ERR_ARG;
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    int rc = update_steps(db, threshold);
+    if (rc != PF_OK) return rc;
+    memcpy(steps, db->h_steps.data(), db->n_nodes * 4);
     return PF_OK;
 }
 

@@ -25,25 +25,33 @@ def _compare(oracle, otree, gtree, reads, theta, check_probes=True):
     """Run both sides on one block; compare hits, counters, csv and probe counts."""
     from phagefilter_b200.query import get_leaf_counts
     otree.reset_counts()
-    gtree.reset_counts()
-    gtree.reset_stats()
-    gtree.set_exhaustive(False)
-    ores = otree.query_batch(reads, theta)
-    ghits = gpu_query(gtree, reads, theta)
-    assert ghits == ores.hit_sets(len(reads))
-    assert get_leaf_counts(gtree) == otree.leaf_counts()
-    st = gtree.stats()
-    assert st.pairs == ores.pairs
+    ores = otree.query_batch(reads, theta)  # the reference's semantics
+    want = ores.hit_sets(len(reads))
+    ghits = None
+    for lazy in (True, False):
+        gtree.reset_counts()
+        gtree.reset_stats()
+        gtree.set_exhaustive(False)
+        gtree.set_lazy(lazy)
+        ghits = gpu_query(gtree, reads, theta)
+        assert ghits == want, f"lazy={lazy}"
+        assert get_leaf_counts(gtree) == otree.leaf_counts()
+        if check_probes:
+            # the oracle's restatement of the kernel schedule predicts the kernel's work exactly
+            sched = otree.query_sched(reads, theta, lazy=lazy)
+            assert sched.hit_sets(len(reads)) == want
+            st = gtree.stats()
+            assert (st.pairs, st.probes_issued) == (sched.pairs, sched.probes_sched), f"lazy={lazy}"
     if check_probes:
-        assert st.probes_issued == ores.probes_sched
-        # reference-faithful probing: every k-mer until its first clear bit
+        # reference-faithful probing: every k-mer of every pair until its first clear bit
         gtree.reset_counts()
         gtree.reset_stats()
         gtree.set_exhaustive(True)
-        ghits2 = gpu_query(gtree, reads, theta)
-        assert ghits2 == ghits
-        assert gtree.stats().probes_issued == ores.probes_ref
+        assert gpu_query(gtree, reads, theta) == want
+        st = gtree.stats()
+        assert (st.pairs, st.probes_issued) == (ores.pairs, ores.probes_ref)
         gtree.set_exhaustive(False)
+    gtree.set_lazy(True)
 
 
 @pytest.mark.parametrize("k", [3, 4, 5])
@@ -226,3 +234,64 @@ def test_gpu_builder_writes_identical_db(oracle, tmp_path):
                 assert a[:cut] == c[:cut], name
             else:
                 assert a == c, name
+
+
+def test_non_monotone_tree_stays_exact(oracle, tmp_path):
+    """The reference names interior nodes with a random u16 (bloom_tree.rs:232-234); colliding names share
+    one .bf, so an interior filter need not contain its children.  Such nodes must be evaluated exactly:
+    emulate a collision by overwriting one interior node's file with a sibling subtree's filter."""
+    import shutil
+    rng = np.random.default_rng(77)
+    genomes = random_genomes(rng, 10, 1500, 2500)
+    d = str(tmp_path / "db")
+    ot = oracle_build_db(oracle, genomes, 20, d, largest=4000)
+    pre = ot.preorder()
+    internals = [n for n, leaf, depth in pre if not leaf and depth >= 1]
+    assert len(internals) >= 2
+    shutil.copyfile(os.path.join(d, internals[-1] + ".bf"), os.path.join(d, internals[0] + ".bf"))
+    shutil.copyfile(os.path.join(d, genomes[0][0] + ".bf"), os.path.join(d, pre[0][0] + ".bf"))  # root too
+    ot = oracle.Tree.load(d)
+    gt = _open(d)
+    assert gt.info.n_monotone < gt.info.n_internal
+    steps = gt.node_steps(1.0)
+    assert steps[0] == gt.info.num_hashes  # the broken root is exact
+    reads = sample_reads(rng, genomes, 300, 120, 0.0) + sample_reads(rng, genomes, 200, 120, 0.03)
+    for theta in (0.5, 1.0):
+        _compare(oracle, ot, gt, reads, theta)
+    gt.close()
+
+
+def test_lazy_steps_table(oracle, tmp_path):
+    """Leaves are always exact; verified interior nodes use fewer steps at high thresholds."""
+    rng = np.random.default_rng(78)
+    genomes = random_genomes(rng, 16, 2000, 3000)
+    d = str(tmp_path / "db")
+    oracle_build_db(oracle, genomes, 20, d, largest=4000)
+    gt = _open(d)
+    K = gt.info.num_hashes
+    assert gt.info.n_monotone == gt.info.n_internal == 15
+    s1 = gt.node_steps(1.0)
+    gt.set_lazy(False)
+    assert (gt.node_steps(1.0) == K).all()
+    gt.set_lazy(True)
+    s3 = gt.node_steps(0.3)
+    assert (s1 <= s3).all() and (s1 >= 1).all() and s1.min() < K
+    gt.set_exhaustive(True)
+    assert (gt.node_steps(1.0) == K).all()
+    gt.close()
+
+
+def test_chunked_hash_cache(oracle, tmp_path):
+    """A batch whose cached k-mer hashes exceed the budget is processed in several chunks of reads;
+    hits, counters and work counts must not depend on the chunking."""
+    rng = np.random.default_rng(79)
+    genomes = random_genomes(rng, 8, 1500, 2500)
+    d = str(tmp_path / "db")
+    ot = oracle_build_db(oracle, genomes, 20, d, largest=4000)
+    gt = _open(d)
+    reads = sample_reads(rng, genomes, 300, 150, 0.0) + sample_reads(rng, genomes, 300, 150, 0.02) + [b"", b"ACGT"]
+    reads += sample_reads(rng, genomes, 5, 1200, 0.0)
+    for budget in (8 * 131 * 7, 8, 1 << 30):  # ~7 reads per chunk; one read per chunk; everything at once
+        gt.set_hash_cache_bytes(budget)
+        _compare(oracle, ot, gt, reads, 0.8)
+    gt.close()

@@ -222,10 +222,11 @@ def test_probe_counts_consistent(oracle):
     for i, g in enumerate(gs):
         t.insert(f"g{i}", g)
     reads = [g[s:s + 150] for g in gs for s in (0, 500, 1000)] + [acgt[rng.integers(0, 4, size=150)].tobytes() for _ in range(20)]
-    for th in (0.3, 1.0):
+    for th in (0.3, 0.8, 1.0):
         r = t.query_batch(reads, th)
-        assert 0 < r.probes_sched <= r.probes_ref
-    oracle.set_sched_counting(False)
-    r2 = t.query_batch(reads, 1.0)
-    oracle.set_sched_counting(True)
-    assert r2.probes_sched == 0 and r2.probes_ref > 0
+        want = r.hit_sets(len(reads))
+        exact = t.query_sched(reads, th, lazy=False)
+        lazy = t.query_sched(reads, th, lazy=True)
+        assert exact.hit_sets(len(reads)) == want and lazy.hit_sets(len(reads)) == want
+        assert exact.pairs == r.pairs and lazy.pairs >= r.pairs
+        assert 0 < exact.probes_sched <= r.probes_ref and 0 < lazy.probes_sched
