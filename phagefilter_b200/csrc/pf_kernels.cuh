@@ -384,7 +384,7 @@ __global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, const uint3
                                uint32_t *cursor, const uint32_t *__restrict__ left, const uint32_t *__restrict__ right,
                                const int32_t *__restrict__ leaf, const unsigned long long *__restrict__ next_base,
                                const unsigned long long *__restrict__ hit_base, uint32_t *nx_read, uint32_t *nx_node,
-                               uint32_t *hit_read, uint32_t *hit_leaf, int want_hits) {
+                               uint32_t *hit_read, uint32_t *hit_leaf, uint32_t *read_hits, int want_hits) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = i < n && pass[i];
     const uint32_t act = __ballot_sync(0xFFFFFFFFu, on);
@@ -403,6 +403,7 @@ __global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, const uint3
             const unsigned long long p = hit_base[u] + rank;
             hit_read[p] = r;
             hit_leaf[p] = (uint32_t)lf;
+            atomicAdd(read_hits + r, 1u);  // per-read hit count for the CSR built at the end of the block
         }
     } else {
         unsigned long long p = next_base[u] + rank;
@@ -449,6 +450,96 @@ __global__ void subset_kernel(const uint64_t *__restrict__ filters, uint64_t wpf
     }
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(viol + u, c);
+}
+
+// ---- per-read hit lists (ResultMap, result_map.rs:9-46) as CSR, built on the device ------------------
+// exclusive scan of cnt[0..n) into off[0..n] (u64), 1024 elements per block: block sums, scan of the sums,
+// then the in-block scan with the block's base.
+__global__ void csr_block_sums_kernel(const uint32_t *__restrict__ cnt, uint32_t n, unsigned long long *bsum) {
+    __shared__ unsigned long long s[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    unsigned long long v = i < n ? cnt[i] : 0;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = s[threadIdx.x];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (threadIdx.x == 0) bsum[blockIdx.x] = v;
+    }
+}
+__global__ void csr_scan_sums_kernel(unsigned long long *bsum, uint32_t nb) {  // one block, in place, exclusive
+    __shared__ unsigned long long s[1024];
+    const uint32_t t = threadIdx.x, per = (nb + 1023u) / 1024u;
+    const uint32_t b = min(nb, t * per), e = min(nb, (t + 1) * per);
+    unsigned long long sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += bsum[i];
+    s[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long a = 0;
+        for (uint32_t i = 0; i < 1024; ++i) {
+            unsigned long long x = s[i];
+            s[i] = a;
+            a += x;
+        }
+    }
+    __syncthreads();
+    unsigned long long a = s[t];
+    for (uint32_t i = b; i < e; ++i) {
+        unsigned long long x = bsum[i];
+        bsum[i] = a;
+        a += x;
+    }
+}
+__global__ void csr_offsets_kernel(const uint32_t *__restrict__ cnt, uint32_t n, const unsigned long long *__restrict__ bsum,
+                                   unsigned long long *off) {
+    __shared__ unsigned long long s[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const unsigned long long c = i < n ? cnt[i] : 0;
+    unsigned long long v = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= (uint32_t)o) v += y;
+    }
+    if (lane == 31) s[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long x = s[lane], z = x;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, z, o);
+            if (lane >= (uint32_t)o) z += y;
+        }
+        s[lane] = z - x;  // exclusive warp bases
+    }
+    __syncthreads();
+    const unsigned long long excl = bsum[blockIdx.x] + s[w] + v - c;
+    if (i < n) off[i] = excl;
+    if (i == n - 1) off[n] = excl + c;
+}
+// place every hit in its read's segment (any order), then sort each segment ascending by DFS leaf index
+__global__ void csr_fill_kernel(const uint32_t *__restrict__ hit_read, const uint32_t *__restrict__ hit_leaf,
+                                unsigned long long n_hits, const unsigned long long *__restrict__ off, uint32_t *cnt,
+                                uint32_t *out_leaf) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_hits) return;
+    const uint32_t r = hit_read[i];
+    const uint32_t k = atomicSub(cnt + r, 1u) - 1u;
+    out_leaf[off[r] + k] = hit_leaf[i];
+}
+__global__ void csr_sort_kernel(const unsigned long long *__restrict__ off, uint32_t n, uint32_t *out_leaf) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const unsigned long long b = off[r], e = off[r + 1];
+    for (unsigned long long i = b + 1; i < e; ++i) {
+        const uint32_t x = out_leaf[i];
+        unsigned long long j = i;
+        while (j > b && out_leaf[j - 1] > x) {
+            out_leaf[j] = out_leaf[j - 1];
+            --j;
+        }
+        out_leaf[j] = x;
+    }
 }
 
 __global__ void add_counts_kernel(unsigned long long *dst, const unsigned long long *src, uint32_t n) {

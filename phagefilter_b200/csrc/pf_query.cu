@@ -83,6 +83,31 @@ struct DevBuf {  // grow-only device array
     }
 };
 
+template <class T>
+struct PinnedBuf {  // grow-only pinned host array
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return PF_OK;
+        const size_t want = std::max(n, cap + cap / 2);
+        T *q = nullptr;
+        if (cudaMallocHost(&q, want * sizeof(T)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("pinned host allocation of %zu bytes failed", want * sizeof(T));
+            return PF_ERR_NOMEM;
+        }
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = want;
+        return PF_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 // pf_build.cu
 int build_leaf_filter(const uint8_t *h_seq, uint64_t len, const HashParams &hp, uint64_t *d_filter, uint64_t wpf,
                       cudaStream_t s);
@@ -185,9 +210,12 @@ struct pf_db {
     DevBuf<uint64_t> hb;                       // cached hash_bytes per k-mer of the current chunk
     uint64_t hash_cache_bytes = 16ULL << 30;   // chunk reads so the cache stays below this
     pf_dev_batch own_batch;  // device copy used by pf_query_block
-    // outputs
+    // outputs: per-read hit lists as CSR, built on the device, returned through pinned host arrays
+    DevBuf<uint32_t> read_hits, csr_leaf;
+    DevBuf<unsigned long long> csr_off, csr_bsum;
+    PinnedBuf<uint64_t> pin_off;
+    PinnedBuf<uint32_t> pin_leaf;
     std::vector<uint64_t> out_off;
-    std::vector<uint32_t> out_leaf, tmp_read, tmp_leaf;
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_probe;  // 2 per level
@@ -222,6 +250,12 @@ static void db_free(pf_db *db) {
     db->hit_leaf.release();
     db->pass.release();
     db->hb.release();
+    db->read_hits.release();
+    db->csr_leaf.release();
+    db->csr_off.release();
+    db->csr_bsum.release();
+    db->pin_off.release();
+    db->pin_leaf.release();
     db->own_batch.release();
     if (db->ev_begin) cudaEventDestroy(db->ev_begin);
     if (db->ev_end) cudaEventDestroy(db->ev_end);
@@ -553,9 +587,8 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     const size_t n_levels = db->level_start.size() - 1;
     int rc;
     if (out) *out = pf_hits{};
-    db->out_off.assign((size_t)n_reads + 1, 0);
-    db->out_leaf.clear();
     if (n_reads == 0) {
+        db->out_off.assign(1, 0);
         if (out) out->read_off = db->out_off.data();
         return PF_OK;
     }
@@ -569,6 +602,10 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     PF_CUDA_OK(cudaMemsetAsync(db->d_blk_counts, 0, std::max<uint64_t>(db->n_leaves, 1) * 8, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_probes, 0, 8, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_totals, 0, sizeof(LevelTotals), s));
+    if (want_hits) {
+        if ((rc = db->read_hits.ensure(n_reads))) return rc;
+        PF_CUDA_OK(cudaMemsetAsync(db->read_hits.p, 0, (size_t)n_reads * 4, s));
+    }
     uint64_t other_launches = 0, probe_launches = 0, pairs = 0, levels = 0, hits_total = 0, probes = 0, hits_before = 0;
     size_t n_ev = 0;
     const uint32_t G = group_rounds_for(bt->max_kmers, db->hp.small_m != 0);
@@ -663,7 +700,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
             scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(
                 db->fr_read[cur].p, db->fr_node[cur].p, db->pass.p, (uint32_t)n, db->d_node_pass, db->d_cursor,
                 db->d_left, db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base, db->fr_read[nxt].p,
-                db->fr_node[nxt].p, db->hit_read.p, db->hit_leaf.p, want_hits);
+                db->fr_node[nxt].p, db->hit_read.p, db->hit_leaf.p, db->read_hits.p, want_hits);
             other_launches++;
             n = next_n;
             cur = nxt;
@@ -673,34 +710,43 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     add_counts_kernel<<<(uint32_t)((db->n_leaves + 255) / 256), 256, 0, s>>>(db->d_counts, db->d_blk_counts,
                                                                             (uint32_t)db->n_leaves);
     other_launches++;
-    PF_CUDA_OK(cudaEventRecord(db->ev_end, s));
     uint64_t d2h = levels * sizeof(LevelTotals);
-    if (want_hits && hits_total) {
-        db->tmp_read.resize(hits_total);
-        db->tmp_leaf.resize(hits_total);
-        PF_CUDA_OK(cudaMemcpyAsync(db->tmp_read.data(), db->hit_read.p, hits_total * 4, cudaMemcpyDeviceToHost, s));
-        PF_CUDA_OK(cudaMemcpyAsync(db->tmp_leaf.data(), db->hit_leaf.p, hits_total * 4, cudaMemcpyDeviceToHost, s));
-        d2h += hits_total * 8;
+    if (want_hits) {
+        // CSR by read, leaves ascending within a read (ResultMap holds a set per read id), built on the device
+        const uint32_t nb = (n_reads + 1023u) / 1024u;
+        if ((rc = db->csr_off.ensure((size_t)n_reads + 1)) || (rc = db->csr_bsum.ensure(nb)) ||
+            (rc = db->csr_leaf.ensure(std::max<uint64_t>(hits_total, 1))))
+            return rc;
+        csr_block_sums_kernel<<<nb, 1024, 0, s>>>(db->read_hits.p, n_reads, db->csr_bsum.p);
+        csr_scan_sums_kernel<<<1, 1024, 0, s>>>(db->csr_bsum.p, nb);
+        csr_offsets_kernel<<<nb, 1024, 0, s>>>(db->read_hits.p, n_reads, db->csr_bsum.p, db->csr_off.p);
+        other_launches += 3;
+        if (hits_total) {
+            csr_fill_kernel<<<(uint32_t)((hits_total + 255) / 256), 256, 0, s>>>(db->hit_read.p, db->hit_leaf.p, hits_total,
+                                                                                db->csr_off.p, db->read_hits.p,
+                                                                                db->csr_leaf.p);
+            csr_sort_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(db->csr_off.p, n_reads, db->csr_leaf.p);
+            other_launches += 2;
+        }
+        if ((rc = db->pin_off.ensure((size_t)n_reads + 1)) || (rc = db->pin_leaf.ensure(std::max<uint64_t>(hits_total, 1))))
+            return rc;
+        PF_CUDA_OK(cudaMemcpyAsync(db->pin_off.p, db->csr_off.p, ((size_t)n_reads + 1) * 8, cudaMemcpyDeviceToHost, s));
+        if (hits_total)
+            PF_CUDA_OK(cudaMemcpyAsync(db->pin_leaf.p, db->csr_leaf.p, hits_total * 4, cudaMemcpyDeviceToHost, s));
+        d2h += ((uint64_t)n_reads + 1) * 8 + hits_total * 4;
     }
+    PF_CUDA_OK(cudaEventRecord(db->ev_end, s));
     PF_CUDA_OK(cudaStreamSynchronize(s));
     PF_CUDA_OK(cudaGetLastError());
-    if (want_hits) {
-        // CSR by read, leaves ascending within a read (ResultMap holds a set per read id)
-        for (uint64_t i = 0; i < hits_total; ++i) db->out_off[(size_t)db->tmp_read[i] + 1]++;
-        for (uint32_t r = 0; r < n_reads; ++r) db->out_off[r + 1] += db->out_off[r];
-        db->out_leaf.resize(hits_total);
-        std::vector<uint64_t> fill(db->out_off.begin(), db->out_off.end() - 1);
-        for (uint64_t i = 0; i < hits_total; ++i) db->out_leaf[fill[db->tmp_read[i]]++] = db->tmp_leaf[i];
-        for (uint32_t r = 0; r < n_reads; ++r)
-            if (db->out_off[r + 1] - db->out_off[r] > 1)
-                std::sort(db->out_leaf.begin() + db->out_off[r], db->out_leaf.begin() + db->out_off[r + 1]);
-        if (out) {
+    if (out) {
+        if (want_hits) {
             out->n_hits = hits_total;
+            out->read_off = db->pin_off.p;
+            out->leaf = db->pin_leaf.p;
+        } else {
+            db->out_off.assign((size_t)n_reads + 1, 0);
             out->read_off = db->out_off.data();
-            out->leaf = db->out_leaf.data();
         }
-    } else if (out) {
-        out->read_off = db->out_off.data();
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, db->ev_begin, db->ev_end);
