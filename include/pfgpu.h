@@ -187,6 +187,8 @@ int pf_allreduce_counts(pf_db *db);
 typedef struct pf_builder pf_builder;
 int pf_builder_create(uint64_t kmer_size, float false_pos_rate, uint32_t largest_genome, uint64_t seed1,
                       uint64_t seed2, int device, int name_mode, uint64_t name_seed, pf_builder **out);
+/* BloomTree::load for `add` (main.rs:220-221): continue inserting into an existing database. */
+int pf_builder_open(const char *db_path, int device, pf_builder **out);
 int pf_builder_set_hash_rot(pf_builder *b, int rot);
 int pf_builder_insert(pf_builder *b, const char *id, const uint8_t *seq, uint64_t len);
 int pf_builder_save(pf_builder *b, const char *db_path);

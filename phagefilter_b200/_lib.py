@@ -92,6 +92,7 @@ SYMBOLS = {
     "pf_allreduce_counts": (C.c_int, [_VP]),
     "pf_builder_create": (C.c_int, [C.c_uint64, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                     C.c_uint64, C.POINTER(_VP)]),
+    "pf_builder_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_VP)]),
     "pf_builder_set_hash_rot": (C.c_int, [_VP, C.c_int]),
     "pf_builder_insert": (C.c_int, [_VP, C.c_char_p, C.c_char_p, C.c_uint64]),
     "pf_builder_save": (C.c_int, [_VP, C.c_char_p]),

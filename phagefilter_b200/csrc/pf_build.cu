@@ -218,6 +218,93 @@ int pf_builder_create(uint64_t kmer_size, float fpr, uint32_t largest_genome, ui
     return PF_OK;
 }
 
+// BloomTree::load for the `add` subcommand (main.rs:202-247): every node's filter goes back to the device.
+int pf_builder_open(const char *db_path, int device, pf_builder **out) {
+    if (!db_path || !out) return PF_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libpfgpu has no CPU fallback");
+        return PF_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("device %d out of range", device);
+        return PF_ERR_ARG;
+    }
+    std::string dir(db_path), err;
+    pf_builder *b = new pf_builder();
+    b->device = device;
+    if (!read_tree_bin(join_path(dir, "tree.bin"), b->tree, err)) {
+        set_error("%s", err.c_str());
+        delete b;
+        return err.rfind("cannot open", 0) == 0 ? PF_ERR_IO : PF_ERR_FORMAT;
+    }
+    if (b->tree.root < 0) {
+        set_error("tree.bin holds no root");
+        delete b;
+        return PF_ERR_FORMAT;
+    }
+    BfHeader h;
+    if (!read_bf_header(join_path(dir, b->tree.nodes[b->tree.root].bf_path), h, err)) {
+        set_error("%s", err.c_str());
+        delete b;
+        return PF_ERR_FORMAT;
+    }
+    b->m = h.num_bits;
+    b->K = h.num_hashes;
+    b->n_words = h.n_words;
+    b->wpf = (b->n_words + 15) / 16 * 16;
+    b->tree.seed1 = h.seed1;
+    b->tree.seed2 = h.seed2;
+    b->hp = make_hash_params(h.seed1, h.seed2, b->tree.kmer_size, b->m, b->K, 26);
+    b->name_mode = 1;
+    b->name_state = h.seed1 ^ h.seed2 ^ (uint64_t)b->tree.nodes.size();
+    b->name_used.assign(65536, 0);
+    cudaSetDevice(device);
+    uint64_t *stage = nullptr;
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&b->d_dist, 16) != cudaSuccess || cudaMallocHost(&b->h_dist, 16) != cudaSuccess ||
+        cudaMallocHost(&stage, b->wpf * 8) != cudaSuccess) {
+        set_error("CUDA error opening builder: %s", cudaGetErrorString(cudaGetLastError()));
+        pf_builder_free(b);
+        return PF_ERR_CUDA;
+    }
+    int rc = PF_OK;
+    for (size_t i = 0; i < b->tree.nodes.size() && rc == PF_OK; ++i) {
+        const HostNode &n = b->tree.nodes[i];
+        unsigned v = 0;
+        if (sscanf(n.tax_id.c_str(), "Internal_Node_%u", &v) == 1) {
+            if (v < 65536) b->name_used[v] = 1;
+            b->name_counter++;
+        }
+        uint64_t *f = nullptr;
+        if (cudaMalloc(&f, b->wpf * 8) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cannot allocate filter %zu", i);
+            rc = PF_ERR_NOMEM;
+            break;
+        }
+        b->filters.push_back(f);
+        memset(stage, 0, b->wpf * 8);
+        BfHeader hh;
+        if (!read_bf(join_path(dir, n.bf_path), hh, stage, b->wpf, err) || hh.num_bits != b->m || hh.num_hashes != b->K) {
+            set_error("%s", err.empty() ? "filter geometry differs inside the database" : err.c_str());
+            rc = PF_ERR_FORMAT;
+            break;
+        }
+        cudaMemcpyAsync(f, stage, b->wpf * 8, cudaMemcpyHostToDevice, b->stream);
+        cudaStreamSynchronize(b->stream);
+    }
+    cudaFreeHost(stage);
+    if (rc != PF_OK) {
+        pf_builder_free(b);
+        return rc;
+    }
+    *out = b;
+    return PF_OK;
+}
+
 int pf_builder_set_hash_rot(pf_builder *b, int rot) {
     if (!b || rot < 0 || rot > 63) return PF_ERR_ARG;
     b->hp.rot = (uint32_t)rot;
