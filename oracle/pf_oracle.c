@@ -938,9 +938,11 @@ static int filter_contains_filter(const pfo_filter *parent, const pfo_filter *ch
         if (child->words[i] & ~parent->words[i]) return 0;
     return 1;
 }
-/* smallest s in [1,K] with fill^s <= 0.75*threshold (plain double multiplications, no libm) */
+/* smallest s in [1,K] with fill^s <= 1 - min(0.9, 1.5*(1-threshold) + 0.02) (plain double arithmetic, no libm) */
 static uint32_t lazy_steps(double fill, double theta, uint32_t K) {
-    double target = 0.75 * theta, p = fill;
+    double q = 1.5 * (1.0 - theta) + 0.02;
+    if (q > 0.9) q = 0.9;
+    double target = 1.0 - q, p = fill;
     uint32_t s = 1;
     while (p > target && s < K) {
         p *= fill;

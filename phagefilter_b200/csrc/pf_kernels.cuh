@@ -39,6 +39,8 @@ struct HashArgs {
     const uint8_t *exc_bytes;
     const uint64_t *kmer_off;   // [n_reads + 1] prefix sum of k-mer counts
     uint64_t *hb;               // out: hash_bytes(canonical k-mer), index kmer_off[r] - kmer_base + pos
+    uint32_t *idx0;             // out (m < 2^31 only): bit index of probe step 0, h1 mod m; else null
+    HashParams hp;
     uint64_t kmer_base;         // kmer_off[read0]
     uint32_t read0, n_reads;    // reads [read0, read0 + n_reads) of the batch
     uint32_t k;
@@ -61,6 +63,7 @@ PF_D uint8_t src_byte(const ByteSrc &s, uint32_t j) {
 template <int KM>
 __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t M0 = (uint32_t)a.hp.M, M1 = (uint32_t)(a.hp.M >> 32), m32 = (uint32_t)a.hp.m;
     for (;;) {
         uint32_t i0 = 0;
         if (lane == 0) i0 = atomicAdd(a.work_ctr, 4u);
@@ -71,7 +74,9 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArgs a) {
             const uint32_t r = a.read0 + i;
             const uint32_t n_k = kmers_of(ldg32(a.lengths + r), a.k);
             if (n_k == 0) continue;
-            uint64_t *out = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
+            const uint64_t kofs = __ldg(a.kmer_off + r) - a.kmer_base;
+            uint64_t *out = a.hb + kofs;
+            uint32_t *out0 = a.idx0 ? a.idx0 + kofs : nullptr;
             const uint64_t woff = __ldg(a.word_off + r);
             const uint32_t e = a.exc_index ? ldg32(a.exc_index + r) : NONE32_D;
             if (KM != 0 && e == NONE32_D) {
@@ -82,15 +87,21 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArgs a) {
                     const uint32_t sh = 2u * lane;
                     const uint64_t x = (lo >> sh) | ((hi << 1) << (63u - sh));
                     const uint64_t hb = canonical_hash_2bit<(KM ? KM : 17)>(x);
-                    if (base + lane < n_k) out[base + lane] = hb;
+                    if (base + lane < n_k) {
+                        out[base + lane] = hb;
+                        if (out0) out0[base + lane] = mod_small(fx_finish(a.hp.c1, hb, a.hp.rot), M0, M1, m32);
+                    }
                     lo = hi;
                 }
             } else {
                 ByteSrc s;
                 s.ascii = e == NONE32_D ? nullptr : a.exc_bytes + __ldg(a.exc_off + e);
                 s.packed = a.packed + woff;
-                for (uint32_t pos = lane; pos < n_k; pos += 32u)
-                    out[pos] = canonical_hash_bytes([&](uint32_t j) { return src_byte(s, pos + j); }, a.k);
+                for (uint32_t pos = lane; pos < n_k; pos += 32u) {
+                    const uint64_t hb = canonical_hash_bytes([&](uint32_t j) { return src_byte(s, pos + j); }, a.k);
+                    out[pos] = hb;
+                    if (out0) out0[pos] = mod_small(fx_finish(a.hp.c1, hb, a.hp.rot), M0, M1, m32);
+                }
             }
         }
     }
@@ -106,6 +117,7 @@ struct ProbeArgs {
     const uint32_t *lengths;
     const uint64_t *kmer_off;
     const uint64_t *hb;
+    const uint32_t *idx0;  // step-0 bit indices (m < 2^31), else null
     uint64_t kmer_base;
     // tree
     const uint32_t *node_slot;
@@ -174,59 +186,113 @@ PF_D uint32_t probe_phase(const uint32_t *__restrict__ filt, const HashParams &h
     return died;  // this lane's k-mers found absent in this phase
 }
 
-// Returns true when the pair's outcome is decided (failed or passed set); hits/misses updated otherwise.
-template <int G, bool SMALL_M>
-PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, uint32_t n_steps,
-                      const uint64_t *__restrict__ hbp, uint32_t gbase, uint32_t n_k, uint32_t lane, uint32_t need,
-                      uint32_t allowed, bool exhaustive, uint32_t &hits, uint32_t &misses, uint32_t &probes,
-                      bool &pass) {
-    GroupState<G, SMALL_M> st;
-    st.alive = 0;
-    uint64_t hb[G];
+// one gather per alive k-mer of slots [J0,J1) at precomputed bit indices; returns this lane's newly absent k-mers
+template <int G, int J0, int J1>
+PF_D uint32_t probe_idx_phase(const uint32_t *__restrict__ filt, const uint32_t (&idx)[G], uint32_t &alive) {
+    uint32_t w[G];
 #pragma unroll
-    for (int j = 0; j < G; ++j) {
-        const uint32_t pos = gbase + (uint32_t)j * 32u + lane;
-        hb[j] = 0;
-        if (pos < n_k) {
-            hb[j] = __ldg(hbp + pos);
-            st.alive |= 1u << j;
+    for (int j = J0; j < J1; ++j) {
+        w[j] = 0xFFFFFFFFu;
+        if ((alive >> j) & 1u) w[j] = ldg32(filt + (idx[j] >> 5));
+    }
+    uint32_t died = 0;
+#pragma unroll
+    for (int j = J0; j < J1; ++j) {
+        if (!((w[j] >> (idx[j] & 31u)) & 1u)) {
+            alive &= ~(1u << j);
+            ++died;
         }
     }
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-        st.h1[j] = fx_finish(hp.c1, hb[j], hp.rot);
-        st.h2[j] = fx_finish(hp.c2, hb[j], hp.rot);
-        st.g[j] = st.h1[j];
-    }
+    return died;
+}
+
+// Returns true when the pair's outcome is decided (`pass` set); hits/misses updated otherwise.
+// SMALL_M: step 0 uses the cached bit indices (no hashing, no modulo); the cached hash_bytes values are only
+// fetched when the node needs more than one step -- speculatively, together with the step-0 gathers.
+template <int G, bool SMALL_M>
+PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, uint32_t n_steps,
+                      const uint64_t *__restrict__ hbp, const uint32_t *__restrict__ i0p, uint32_t gbase, uint32_t n_k,
+                      uint32_t lane, uint32_t need, uint32_t allowed, bool exhaustive, uint32_t &hits,
+                      uint32_t &misses, uint32_t &probes, bool &pass) {
+    GroupState<G, SMALL_M> st;
+    st.alive = 0;
     const uint32_t cnt = min(32u * G, n_k - gbase);
     const uint32_t limit = allowed - misses;  // only used when !exhaustive (misses <= allowed then)
     uint32_t dead = 0;
-    // step 0, first round
-    probes += min(32u, cnt);
-    dead += __reduce_add_sync(0xFFFFFFFFu, probe_phase<G, SMALL_M, 0, 1>(filt, hp, st));
-    if (!exhaustive && dead > limit) {
-        pass = false;
-        return true;
+    uint64_t hb[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        hb[j] = 0;
+        if (gbase + (uint32_t)j * 32u + lane < n_k) st.alive |= 1u << j;
     }
-    // step 0, remaining rounds
-    if (G > 1 && cnt > 32u) {
-        probes += cnt - 32u;
-        dead += __reduce_add_sync(0xFFFFFFFFu, probe_phase<G, SMALL_M, (G > 1 ? 1 : 0), G>(filt, hp, st));
+    if (SMALL_M) {
+        uint32_t idx[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) idx[j] = 0;
+        if (st.alive & 1u) idx[0] = ldg32(i0p + gbase + lane);
+        if (n_steps > 1u) {
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if ((st.alive >> j) & 1u) hb[j] = __ldg(hbp + gbase + (uint32_t)j * 32u + lane);
+        }
+        // step 0, first round
+        probes += min(32u, cnt);
+        dead += __reduce_add_sync(0xFFFFFFFFu, probe_idx_phase<G, 0, 1>(filt, idx, st.alive));
         if (!exhaustive && dead > limit) {
             pass = false;
             return true;
         }
-    }
-    for (uint32_t i = 1; i < n_steps; ++i) {
-        const uint32_t n_alive = cnt - dead;
-        if (n_alive == 0u) break;
-        probes += n_alive;
+        // step 0, remaining rounds
+        if (G > 1 && cnt > 32u) {
 #pragma unroll
-        for (int j = 0; j < G; ++j) st.g[j] = i == 1 ? st.h2[j] : (i == 2 ? (st.h1[j] + 2ULL) * st.h2[j] : st.g[j] + st.h2[j]);
-        dead += __reduce_add_sync(0xFFFFFFFFu, probe_phase<G, SMALL_M, 0, G>(filt, hp, st));
+            for (int j = 1; j < G; ++j)
+                if ((st.alive >> j) & 1u) idx[j] = ldg32(i0p + gbase + (uint32_t)j * 32u + lane);
+            probes += cnt - 32u;
+            dead += __reduce_add_sync(0xFFFFFFFFu, probe_idx_phase<G, (G > 1 ? 1 : 0), G>(filt, idx, st.alive));
+            if (!exhaustive && dead > limit) {
+                pass = false;
+                return true;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+            if ((st.alive >> j) & 1u) hb[j] = __ldg(hbp + gbase + (uint32_t)j * 32u + lane);
+#pragma unroll
+        for (int j = 0; j < G; ++j) st.g[j] = fx_finish(hp.c1, hb[j], hp.rot);
+        probes += min(32u, cnt);
+        dead += __reduce_add_sync(0xFFFFFFFFu, probe_phase<G, SMALL_M, 0, 1>(filt, hp, st));
         if (!exhaustive && dead > limit) {
             pass = false;
             return true;
+        }
+        if (G > 1 && cnt > 32u) {
+            probes += cnt - 32u;
+            dead += __reduce_add_sync(0xFFFFFFFFu, probe_phase<G, SMALL_M, (G > 1 ? 1 : 0), G>(filt, hp, st));
+            if (!exhaustive && dead > limit) {
+                pass = false;
+                return true;
+            }
+        }
+    }
+    if (n_steps > 1u && cnt - dead != 0u) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            st.h1[j] = fx_finish(hp.c1, hb[j], hp.rot);
+            st.h2[j] = fx_finish(hp.c2, hb[j], hp.rot);
+        }
+        for (uint32_t i = 1; i < n_steps; ++i) {
+            const uint32_t n_alive = cnt - dead;
+            if (n_alive == 0u) break;
+            probes += n_alive;
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                st.g[j] = i == 1 ? st.h2[j] : (i == 2 ? (st.h1[j] + 2ULL) * st.h2[j] : st.g[j] + st.h2[j]);
+            dead += __reduce_add_sync(0xFFFFFFFFu, probe_phase<G, SMALL_M, 0, G>(filt, hp, st));
+            if (!exhaustive && dead > limit) {
+                pass = false;
+                return true;
+            }
         }
     }
     misses += dead;
@@ -257,11 +323,12 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, uint
     const uint32_t allowed = need > n_k ? 0u : n_k - need;
     const uint32_t *filt = reinterpret_cast<const uint32_t *>(a.filters + (uint64_t)pm.slot * a.words_per_filter);
     const uint64_t *hbp = a.hb + (pm.koff - a.kmer_base);
+    const uint32_t *i0p = a.idx0 + (pm.koff - a.kmer_base);
     uint32_t hits = 0, misses = 0;
     bool pass = false;
     for (uint32_t gbase = 0; gbase < n_k; gbase += 32u * G)
-        if (probe_group<G, SMALL_M>(filt, hp, pm.steps, hbp, gbase, n_k, lane, need, allowed, exhaustive, hits, misses,
-                                    probes, pass))
+        if (probe_group<G, SMALL_M>(filt, hp, pm.steps, hbp, i0p, gbase, n_k, lane, need, allowed, exhaustive, hits,
+                                    misses, probes, pass))
             return pass;
     return hits >= need;
 }

@@ -208,6 +208,7 @@ struct pf_db {
     DevBuf<uint32_t> fr_read[2], fr_node[2], hit_read, hit_leaf;
     DevBuf<uint8_t> pass;
     DevBuf<uint64_t> hb;                       // cached hash_bytes per k-mer of the current chunk
+    DevBuf<uint32_t> idx0;                     // cached step-0 bit index per k-mer (m < 2^31)
     uint64_t hash_cache_bytes = 16ULL << 30;   // chunk reads so the cache stays below this
     pf_dev_batch own_batch;  // device copy used by pf_query_block
     // outputs: per-read hit lists as CSR, built on the device, returned through pinned host arrays
@@ -250,6 +251,7 @@ static void db_free(pf_db *db) {
     db->hit_leaf.release();
     db->pass.release();
     db->hb.release();
+    db->idx0.release();
     db->read_hits.release();
     db->csr_leaf.release();
     db->csr_off.release();
@@ -497,11 +499,14 @@ static int analyse_tree(pf_db *db) {
 }
 
 // Probe steps per node.  Leaves, unverified nodes and the reference-faithful modes use all K steps.
-// A verified-monotone interior node with fill f uses the smallest s with f^s <= 0.75 * threshold: a k-mer
-// that is absent then survives the pre-test with probability <= 0.75*threshold, so reads that do not
-// belong below the node are still pruned there, while reads that do belong cost s instead of K probes.
+// A verified-monotone interior node with fill f uses the smallest s with f^s <= 1 - q, q = min(0.9,
+// 1.5*(1-threshold) + 0.02): an absent k-mer survives s steps with probability ~f^s, so a read unrelated to
+// the subtree shows about q*n_k proven misses -- 1.5x the n_k*(1-threshold) it may afford -- and is still
+// pruned at this node, while reads that do belong cost s instead of K probes per k-mer.
 static uint32_t lazy_steps(double fill, double theta, uint32_t K) {
-    const double target = 0.75 * theta;
+    double q = 1.5 * (1.0 - theta) + 0.02;  // fraction of an unrelated read's k-mers the pre-test should reject
+    if (q > 0.9) q = 0.9;
+    const double target = 1.0 - q;
     double p = fill;
     uint32_t s = 1;
     while (p > target && s < K) {
@@ -610,7 +615,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     size_t n_ev = 0;
     const uint32_t G = group_rounds_for(bt->max_kmers, db->hp.small_m != 0);
     db->stats.group_rounds = G;
-    const uint64_t budget_kmers = std::max<uint64_t>(db->hash_cache_bytes / 8, 1);
+    const uint64_t budget_kmers = std::max<uint64_t>(db->hash_cache_bytes / 12, 1);  // 8 B hash + 4 B index
     const std::vector<uint64_t> &ko = bt->h_kmer_off;
     for (uint32_t r0 = 0; r0 < n_reads;) {
         // chunk [r0, r1): as many reads as the hash cache holds (always at least one)
@@ -620,6 +625,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         const uint32_t n_chunk = r1 - r0;
         const uint64_t chunk_kmers = ko[r1] - ko[r0];
         if ((rc = db->hb.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
+        if (db->hp.small_m && (rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
         PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, 2 * db->n_nodes * 4, s));
         PF_CUDA_OK(cudaMemsetAsync(db->d_work, 0, db->level_start.size() * 4, s));
         if ((rc = db->fr_read[0].ensure(n_chunk)) || (rc = db->fr_node[0].ensure(n_chunk))) return rc;
@@ -632,6 +638,8 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         h.exc_bytes = bt->exc_bytes.p;
         h.kmer_off = bt->kmer_off.p;
         h.hb = db->hb.p;
+        h.idx0 = db->hp.small_m ? db->idx0.p : nullptr;
+        h.hp = db->hp;
         h.kmer_base = ko[r0];
         h.read0 = r0;
         h.n_reads = n_chunk;
@@ -655,6 +663,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
             a.lengths = bt->lengths.p;
             a.kmer_off = bt->kmer_off.p;
             a.hb = db->hb.p;
+            a.idx0 = db->idx0.p;
             a.kmer_base = ko[r0];
             a.node_slot = db->d_slot;
             a.node_steps = db->d_steps;
