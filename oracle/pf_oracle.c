@@ -355,6 +355,7 @@ typedef struct pfo_node {
     /* cache for the kernel-schedule restatement (invalidated whenever the tree changes) */
     int analysed, mono;
     uint64_t pop;
+    uint32_t steps; /* plan of the current pfo_query_batch_sched call */
 } pfo_node;
 
 struct pfo_tree {
@@ -785,7 +786,7 @@ typedef struct {
 static uint64_t pair_sched(const pfo_filter *f, uint32_t n_steps, uint32_t G, const oread *r, size_t k, int rot,
                            int *pass_out) {
     uint64_t probes = 0;
-    if (r->need == 0) {
+    if (n_steps == 0 || r->need == 0) { /* skipped interior node, or nothing to reach */
         *pass_out = 1;
         return 0;
     }
@@ -938,29 +939,65 @@ static int filter_contains_filter(const pfo_filter *parent, const pfo_filter *ch
         if (child->words[i] & ~parent->words[i]) return 0;
     return 1;
 }
-/* smallest s in [1,K] with fill^s <= 1 - min(0.9, 1.5*(1-threshold) + 0.02) (plain double arithmetic, no libm) */
-static uint32_t lazy_steps(double fill, double theta, uint32_t K) {
-    double q = 1.5 * (1.0 - theta) + 0.02;
-    if (q > 0.9) q = 0.9;
-    double target = 1.0 - q, p = fill;
-    uint32_t s = 1;
-    while (p > target && s < K) {
-        p *= fill;
-        ++s;
+/* Steps per node under the kernel's plan (pf_query.cu plan_steps), restated: leaves and unverified nodes use
+ * K; a verified-monotone interior node takes the cheaper of "test with the smallest s reaching the target" and
+ * "skip (0 steps)", bottom-up; plain double arithmetic only. */
+static double probe_cost(double f, uint32_t s) {
+    double c = 0.0, p = 1.0;
+    for (uint32_t i = 0; i < s; ++i) {
+        c += p;
+        p *= f;
     }
-    return s;
+    return c;
 }
-static uint32_t pfo_node_steps(const pfo_tree *t, pfo_node *n, float threshold, int lazy) {
+static double plan_rec(const pfo_tree *t, pfo_node *n, double target, int lazy) {
     const pfo_filter *f = t->filters[n->filter];
-    if (!lazy || is_leaf(n)) return f->K;
+    const uint32_t K = f->K;
     if (!n->analysed) {
         n->mono = (!n->left || filter_contains_filter(f, t->filters[n->left->filter])) &&
                   (!n->right || filter_contains_filter(f, t->filters[n->right->filter]));
         n->pop = filter_popcount(f);
         n->analysed = 1;
     }
-    if (!n->mono) return f->K;
-    return lazy_steps((double)n->pop / (double)f->m, (double)threshold, f->K);
+    const double fill = (double)n->pop / (double)f->m;
+    if (is_leaf(n)) {
+        n->steps = K;
+        return probe_cost(fill, K);
+    }
+    /* children first (their costs feed the parent's choice) */
+    const double cl = n->left ? plan_rec(t, n->left, target, lazy) : 0.0;
+    const double cr = n->right ? plan_rec(t, n->right, target, lazy) : 0.0;
+    const double below = cl + cr;
+    uint32_t s_star = 0;
+    double p = 1.0;
+    for (uint32_t s = 1; s <= K; ++s) {
+        p *= fill;
+        if (p <= target) {
+            s_star = s;
+            break;
+        }
+    }
+    if (!lazy || !n->mono) {
+        n->steps = K;
+        return probe_cost(fill, K) + (s_star ? 0.0 : below);
+    }
+    if (s_star && probe_cost(fill, s_star) <= below) {
+        n->steps = s_star;
+        return probe_cost(fill, s_star);
+    }
+    n->steps = 0;
+    return below;
+}
+static void plan_steps(pfo_tree *t, float threshold, int lazy) {
+    double q = 1.5 * (1.0 - (double)threshold) + 0.02;
+    if (q > 0.9) q = 0.9;
+    if (t->root) plan_rec(t, t->root, 1.0 - q, lazy);
+}
+static uint32_t pfo_node_steps(const pfo_tree *t, pfo_node *n, float threshold, int lazy) {
+    (void)t;
+    (void)threshold;
+    (void)lazy;
+    return n->steps; /* filled by plan_steps for this query */
 }
 
 typedef struct {
@@ -974,7 +1011,14 @@ typedef struct {
     uint64_t leaf_cursor;
 } sctx;
 
-static void sched_rec(sctx *c, pfo_node *node, const uint32_t *set, uint64_t n_set) {
+/* top != 0: every ancestor was skipped by the plan.  The kernel never materialises that region: it starts
+ * the frontier at the first tested nodes (entry nodes), so skipped top nodes count no pairs. */
+static void sched_rec(sctx *c, pfo_node *node, const uint32_t *set, uint64_t n_set, int top) {
+    if (top && node->steps == 0 && !is_leaf(node)) {
+        if (node->left) sched_rec(c, node->left, set, n_set, 1);
+        if (node->right) sched_rec(c, node->right, set, n_set, 1);
+        return;
+    }
     const pfo_filter *f = c->t->filters[node->filter];
     size_t k = (size_t)c->t->kmer_size;
     int rot = c->t->rot;
@@ -996,8 +1040,8 @@ static void sched_rec(sctx *c, pfo_node *node, const uint32_t *set, uint64_t n_s
     free(flag);
     if (!is_leaf(node)) {
         if (n_pass) {
-            if (node->left) sched_rec(c, node->left, pass, n_pass);
-            if (node->right) sched_rec(c, node->right, pass, n_pass);
+            if (node->left) sched_rec(c, node->left, pass, n_pass, 0);
+            if (node->right) sched_rec(c, node->right, pass, n_pass, 0);
         } else {
             c->leaf_cursor += subtree_leaves(node);
         }
@@ -1059,8 +1103,9 @@ static int query_impl(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, ui
     for (uint32_t i = 0; i < n_reads; i++) all[i] = i;
     if (sched) {
         refresh(t);
+        plan_steps(t, threshold, lazy);
         sctx c = {t, reads, want_hits, lazy, group_rounds, threshold, out, 0, 0};
-        sched_rec(&c, t->root, all, n_reads);
+        sched_rec(&c, t->root, all, n_reads, 1);
     } else {
         qctx c = {t, reads, want_hits, out, 0, 0};
         query_rec(&c, t->root, all, n_reads);

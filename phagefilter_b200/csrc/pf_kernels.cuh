@@ -317,8 +317,9 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, uint
     const uint32_t need = need_of(a.threshold, n_k);
     const bool exhaustive = a.exhaustive != 0;
     if (!exhaustive) {
-        if (need == 0u) return true;   // hits >= 0 always
-        if (need > n_k) return false;  // hits <= n_k < need
+        if (pm.steps == 0u) return true;  // skipped interior node: its children decide (verified superset)
+        if (need == 0u) return true;      // hits >= 0 always
+        if (need > n_k) return false;     // hits <= n_k < need
     }
     const uint32_t allowed = need > n_k ? 0u : n_k - need;
     const uint32_t *filt = reinterpret_cast<const uint32_t *>(a.filters + (uint64_t)pm.slot * a.words_per_filter);
@@ -379,10 +380,16 @@ __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : 4)) probe_kernel(
 }
 
 // ---- frontier bookkeeping ------------------------------------------------------------------
-__global__ void init_frontier_kernel(uint32_t *fr_read, uint32_t *fr_node, uint32_t read0, uint32_t n) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        fr_read[i] = read0 + i;
-        fr_node[i] = 0u;  // root has level-order id 0
+// Appends (read, entry node) pairs for every read of the chunk and every entry node of this level, node-major.
+// Entry nodes are the first nodes below the root that are actually tested (the root itself unless the plan
+// skips it): the skipped region above them never enters the frontier.
+__global__ void inject_frontier_kernel(uint32_t *fr_read, uint32_t *fr_node, uint32_t read0, uint32_t n_reads,
+                                       const uint32_t *__restrict__ entry, uint32_t n_entry) {
+    const uint64_t total = (uint64_t)n_reads * n_entry;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t e = (uint32_t)(i / n_reads), r = (uint32_t)(i - (uint64_t)e * n_reads);
+        fr_read[i] = read0 + r;
+        fr_node[i] = entry[e];
     }
 }
 

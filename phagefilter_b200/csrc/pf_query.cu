@@ -191,6 +191,9 @@ struct pf_db {
     std::vector<uint8_t> h_mono;       // interior node whose filter contains both children's filters
     std::vector<uint32_t> h_steps;     // probe steps per node for the current (threshold, mode)
     uint32_t *d_steps = nullptr;
+    std::vector<uint32_t> h_entry;        // entry nodes of the current plan, ordered by level
+    std::vector<uint32_t> entry_start;    // [n_levels + 1] offsets into h_entry per level
+    uint32_t *d_entry = nullptr;
     float steps_theta = -1.f;
     int steps_mode = -1;
     uint64_t n_internal = 0, n_monotone = 0;
@@ -234,6 +237,7 @@ static void db_free(pf_db *db) {
     cudaFree(db->d_leaf);
     cudaFree(db->d_filters);
     cudaFree(db->d_steps);
+    cudaFree(db->d_entry);
     cudaFree(db->d_counts);
     cudaFree(db->d_blk_counts);
     cudaFree(db->d_node_pass);
@@ -448,6 +452,7 @@ static int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     PF_CUDA_OK(cudaMallocHost(&db->h_totals, sizeof(LevelTotals)));
     PF_CUDA_OK(cudaMemsetAsync(db->d_counts, 0, nl * 8, db->stream));
     PF_CUDA_OK(cudaMalloc(&db->d_steps, nn * 4));
+    PF_CUDA_OK(cudaMalloc(&db->d_entry, nn * 4));
     if ((rc = analyse_tree(db))) return rc;
     PF_CUDA_OK(cudaEventCreate(&db->ev_begin));
     PF_CUDA_OK(cudaEventCreate(&db->ev_end));
@@ -498,34 +503,92 @@ static int analyse_tree(pf_db *db) {
     return PF_OK;
 }
 
-// Probe steps per node.  Leaves, unverified nodes and the reference-faithful modes use all K steps.
-// A verified-monotone interior node with fill f uses the smallest s with f^s <= 1 - q, q = min(0.9,
-// 1.5*(1-threshold) + 0.02): an absent k-mer survives s steps with probability ~f^s, so a read unrelated to
-// the subtree shows about q*n_k proven misses -- 1.5x the n_k*(1-threshold) it may afford -- and is still
-// pruned at this node, while reads that do belong cost s instead of K probes per k-mer.
-static uint32_t lazy_steps(double fill, double theta, uint32_t K) {
-    double q = 1.5 * (1.0 - theta) + 0.02;  // fraction of an unrelated read's k-mers the pre-test should reject
+// Probe steps per node.  Leaves, unverified nodes and the reference-faithful modes use all K steps (exact).
+// A verified-monotone interior node never has to CONFIRM a pass (its children imply it); it is only worth
+// probing if that prunes reads that do not belong below it.  With fill f, an absent k-mer survives s steps
+// with probability ~f^s and costs (1-f^s)/(1-f) probes; an unrelated read is (nominally) pruned once
+// 1-f^s >= q, q = min(0.9, 1.5*(1-threshold) + 0.02) -- 1.5x the miss fraction it may afford.  Bottom-up,
+// each node takes the cheaper of "test with the smallest such s" and "skip (0 steps) and let the children
+// prune"; nodes too saturated to reach q within K steps are skipped.  Plain double arithmetic only, so the
+// oracle's restatement reproduces the table bit for bit.
+static double probe_cost(double f, uint32_t s) {  // expected probes per absent k-mer over s steps
+    double c = 0.0, p = 1.0;
+    for (uint32_t i = 0; i < s; ++i) {
+        c += p;
+        p *= f;
+    }
+    return c;
+}
+static void plan_steps(pf_db *db, double theta, std::vector<uint32_t> &steps) {
+    const uint32_t K = db->geom.num_hashes;
+    const size_t nn = db->n_nodes;
+    double q = 1.5 * (1.0 - theta) + 0.02;
     if (q > 0.9) q = 0.9;
     const double target = 1.0 - q;
-    double p = fill;
-    uint32_t s = 1;
-    while (p > target && s < K) {
-        p *= fill;
-        ++s;
+    std::vector<double> cost(nn, 0.0);
+    steps.assign(nn, K);
+    for (size_t u = nn; u-- > 0;) {  // children have larger level-order ids than their parent
+        const double f = (double)db->h_pop[u] / (double)db->geom.num_bits;
+        const uint32_t l = db->h_left[u], r = db->h_right[u];
+        if (db->h_leaf[u] >= 0) {
+            cost[u] = probe_cost(f, K);
+            continue;
+        }
+        const double below = (l != NONE32 ? cost[l] : 0.0) + (r != NONE32 ? cost[r] : 0.0);
+        uint32_t s_star = 0;  // smallest s with f^s <= target, 0 if none within K
+        double p = 1.0;
+        for (uint32_t s = 1; s <= K; ++s) {
+            p *= f;
+            if (p <= target) {
+                s_star = s;
+                break;
+            }
+        }
+        if (!db->h_mono[u]) {  // exact node: all K steps; it prunes only if K steps reach the target
+            steps[u] = K;
+            cost[u] = probe_cost(f, K) + (s_star ? 0.0 : below);
+            continue;
+        }
+        if (s_star && probe_cost(f, s_star) <= below) {
+            steps[u] = s_star;
+            cost[u] = probe_cost(f, s_star);
+        } else {
+            steps[u] = 0;
+            cost[u] = below;
+        }
     }
-    return s;
 }
 static int update_steps(pf_db *db, float threshold) {
     const int mode = db->exhaustive ? 2 : (db->lazy ? 1 : 0);
     if (mode == db->steps_mode && (mode != 1 || threshold == db->steps_theta)) return PF_OK;
     const uint32_t K = db->geom.num_hashes;
     db->h_steps.assign(db->n_nodes, K);
-    if (mode == 1) {
-        for (size_t u = 0; u < db->n_nodes; ++u)
-            if (db->h_leaf[u] < 0 && db->h_mono[u])
-                db->h_steps[u] = lazy_steps((double)db->h_pop[u] / (double)db->geom.num_bits, (double)threshold, K);
+    if (mode == 1) plan_steps(db, (double)threshold, db->h_steps);
+    // entry nodes: descend from the root through skipped (0-step) interior nodes; level-order ids are already
+    // sorted by level, so a sorted list is grouped by level
+    db->h_entry.clear();
+    {
+        std::vector<uint32_t> st{0};
+        while (!st.empty()) {
+            const uint32_t u = st.back();
+            st.pop_back();
+            if (db->h_steps[u] == 0 && db->h_leaf[u] < 0) {
+                if (db->h_left[u] != NONE32) st.push_back(db->h_left[u]);
+                if (db->h_right[u] != NONE32) st.push_back(db->h_right[u]);
+            } else {
+                db->h_entry.push_back(u);
+            }
+        }
+        std::sort(db->h_entry.begin(), db->h_entry.end());
+    }
+    const size_t n_levels = db->level_start.size() - 1;
+    db->entry_start.assign(n_levels + 1, 0);
+    for (size_t l = 0, e = 0; l < n_levels; ++l) {
+        while (e < db->h_entry.size() && db->h_entry[e] < db->level_start[l + 1]) ++e;
+        db->entry_start[l + 1] = (uint32_t)e;
     }
     PF_CUDA_OK(cudaMemcpyAsync(db->d_steps, db->h_steps.data(), db->n_nodes * 4, cudaMemcpyHostToDevice, db->stream));
+    PF_CUDA_OK(cudaMemcpyAsync(db->d_entry, db->h_entry.data(), db->h_entry.size() * 4, cudaMemcpyHostToDevice, db->stream));
     PF_CUDA_OK(cudaStreamSynchronize(db->stream));
     db->steps_mode = mode;
     db->steps_theta = threshold;
@@ -628,7 +691,6 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         if (db->hp.small_m && (rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
         PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, 2 * db->n_nodes * 4, s));
         PF_CUDA_OK(cudaMemsetAsync(db->d_work, 0, db->level_start.size() * 4, s));
-        if ((rc = db->fr_read[0].ensure(n_chunk)) || (rc = db->fr_node[0].ensure(n_chunk))) return rc;
         HashArgs h{};
         h.lengths = bt->lengths.p;
         h.word_off = bt->word_off.p;
@@ -649,12 +711,32 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
             launch_hash(h, db->sm_count * 8, s);
             other_launches++;
         }
-        init_frontier_kernel<<<std::min<uint32_t>((n_chunk + 255) / 256, 4096), 256, 0, s>>>(db->fr_read[0].p,
-                                                                                             db->fr_node[0].p, r0, n_chunk);
-        other_launches++;
-        uint64_t n = n_chunk;
+        uint64_t n = 0;
         int cur = 0;
-        for (size_t l = 0; l < n_levels && n > 0; ++l) {
+        const size_t last_entry_level = [&] {
+            size_t l = 0;
+            for (size_t i = 0; i < n_levels; ++i)
+                if (db->entry_start[i + 1] > db->entry_start[i]) l = i;
+            return l;
+        }();
+        for (size_t l = 0; l < n_levels && (n > 0 || l <= last_entry_level); ++l) {
+            // entry nodes of this level: append (read, node) pairs for every read of the chunk
+            const uint32_t e0 = db->entry_start[l], n_entry = db->entry_start[l + 1] - e0;
+            if (n_entry) {
+                const uint64_t add = (uint64_t)n_chunk * n_entry;
+                if (n + add > 0xFFFFFFF0ULL) {
+                    set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
+                              (unsigned long long)(n + add));
+                    return PF_ERR_NOMEM;
+                }
+                if ((rc = db->fr_read[cur].grow_keep(n + add, n, s)) || (rc = db->fr_node[cur].grow_keep(n + add, n, s)))
+                    return rc;
+                inject_frontier_kernel<<<(uint32_t)std::min<uint64_t>((add + 255) / 256, 8192), 256, 0, s>>>(
+                    db->fr_read[cur].p + n, db->fr_node[cur].p + n, r0, n_chunk, db->d_entry + e0, n_entry);
+                other_launches++;
+                n += add;
+            }
+            if (n == 0) continue;
             if ((rc = db->pass.ensure(n))) return rc;
             ProbeArgs a{};
             a.fr_read = db->fr_read[cur].p;

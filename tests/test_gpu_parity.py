@@ -275,7 +275,8 @@ def test_lazy_steps_table(oracle, tmp_path):
     assert (gt.node_steps(1.0) == K).all()
     gt.set_lazy(True)
     s3 = gt.node_steps(0.3)
-    assert (s1 <= s3).all() and (s1 >= 1).all() and s1.min() < K
+    assert s1.max() == K and s1.min() < K and s3.max() == K  # leaves exact, interior nodes cheaper or skipped
+    assert int((s1 == K).sum()) >= gt.info.n_leaves
     gt.set_exhaustive(True)
     assert (gt.node_steps(1.0) == K).all()
     gt.close()
