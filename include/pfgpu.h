@@ -99,6 +99,8 @@ typedef struct pf_read_batch {
     const uint32_t *exc_index; /* [n_reads] index into exc_off for exception reads, 0xFFFFFFFF otherwise; NULL if n_exc==0 */
     const uint64_t *exc_off;   /* [n_exc+1] byte offsets into exc_bytes */
     const uint8_t *exc_bytes;  /* raw bytes of the exception reads */
+    uint32_t max_length;       /* longest read in bases; 0 = unknown (the library then scans `lengths`) */
+    uint64_t total_bases;      /* sum of lengths; 0 = unknown */
 } pf_read_batch;
 
 /* Host-side packer from raw ASCII reads (seqs concatenated, offs[n_reads+1]) into pinned memory. */
@@ -127,6 +129,11 @@ int pf_query_block(pf_db *db, const pf_read_batch *in, float threshold, int want
 typedef struct pf_dev_batch pf_dev_batch;
 int pf_batch_upload(pf_db *db, const pf_read_batch *in, pf_dev_batch **out);
 int pf_query_device(pf_db *db, pf_dev_batch *batch, float threshold, int want_hits, pf_hits *out);
+/* Pipelined ingest: starts the H2D copies of `in` on the handle's copy stream and returns at once, so the
+ * upload of block i+1 overlaps pf_query_device on block i (which waits for its own batch's copies only).
+ * *inout == NULL allocates a device batch; otherwise that batch is reused (it must not be in use by a
+ * running query).  The caller keeps the host arrays alive until pf_query_device on the batch has returned. */
+int pf_batch_upload_async(pf_db *db, const pf_read_batch *in, pf_dev_batch **inout);
 void pf_batch_free(pf_db *db, pf_dev_batch *batch);
 
 /* Leaf counters: BloomNode.mapped_reads in DFS leaf order (query.rs:197-218). */

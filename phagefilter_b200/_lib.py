@@ -41,6 +41,7 @@ class ReadBatch(C.Structure):
         ("packed", C.POINTER(C.c_uint32)), ("n_words", C.c_uint64),
         ("exc_index", C.POINTER(C.c_uint32)), ("exc_off", C.POINTER(C.c_uint64)),
         ("exc_bytes", C.POINTER(C.c_uint8)),
+        ("max_length", C.c_uint32), ("total_bases", C.c_uint64),
     ]
 
 
@@ -76,6 +77,7 @@ SYMBOLS = {
     "pf_query_block": (C.c_int, [_VP, C.POINTER(ReadBatch), C.c_float, C.c_int, C.POINTER(Hits)]),
     "pf_batch_upload": (C.c_int, [_VP, C.POINTER(ReadBatch), C.POINTER(_VP)]),
     "pf_query_device": (C.c_int, [_VP, _VP, C.c_float, C.c_int, C.POINTER(Hits)]),
+    "pf_batch_upload_async": (C.c_int, [_VP, C.POINTER(ReadBatch), C.POINTER(_VP)]),
     "pf_batch_free": (None, [_VP, _VP]),
     "pf_leaf_counts": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "pf_reset_counts": (C.c_int, [_VP]),

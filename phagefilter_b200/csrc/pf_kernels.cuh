@@ -526,6 +526,12 @@ __global__ void subset_kernel(const uint64_t *__restrict__ filters, uint64_t wpf
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(viol + u, c);
 }
 
+// k-mer count per read (file_parser.rs:136-139); its exclusive scan (csr_* kernels below) is kmer_off
+__global__ void kmer_counts_kernel(const uint32_t *__restrict__ lengths, uint32_t n, uint32_t k, uint32_t *cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cnt[i] = kmers_of(lengths[i], k);
+}
+
 // ---- per-read hit lists (ResultMap, result_map.rs:9-46) as CSR, built on the device ------------------
 // exclusive scan of cnt[0..n) into off[0..n] (u64), 1024 elements per block: block sums, scan of the sums,
 // then the in-block scan with the block's base.

@@ -51,8 +51,8 @@ int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, p
     }
     *out = nullptr;
     // pass 1: sizes
-    uint64_t n_words = 0, exc_bytes = 0;
-    uint32_t n_exc = 0;
+    uint64_t n_words = 0, exc_bytes = 0, total_bases = 0;
+    uint32_t n_exc = 0, max_length = 0;
     std::vector<uint8_t> is_exc(n_reads, 0);
     for (uint32_t r = 0; r < n_reads; ++r) {
         const uint64_t len = offs[r + 1] - offs[r];
@@ -61,6 +61,8 @@ int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, p
             return PF_ERR_ARG;
         }
         const uint8_t *s = seqs + offs[r];
+        total_bases += len;
+        if (len > max_length) max_length = (uint32_t)len;
         bool exc = false;
         for (uint64_t j = 0; j < len; ++j)
             if (code_of(s[j]) < 0) {
@@ -134,6 +136,8 @@ int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, p
     p->b.exc_index = exc_index;
     p->b.exc_off = exc_off;
     p->b.exc_bytes = exc_b;
+    p->b.max_length = max_length;
+    p->b.total_bases = total_bases;
     *out = p;
     return PF_OK;
 }

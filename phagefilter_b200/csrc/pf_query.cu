@@ -122,9 +122,13 @@ struct pf_dev_batch {
     uint64_t n_words = 0, exc_nbytes = 0;
     DevBuf<uint32_t> lengths, packed, exc_index;
     DevBuf<uint64_t> word_off, exc_off, kmer_off;
+    DevBuf<uint32_t> kcnt;                 // scratch of the device-side k-mer prefix sum
+    DevBuf<unsigned long long> kbsum;
     DevBuf<uint8_t> exc_bytes;
     std::vector<uint64_t> h_kmer_off;  // [n_reads + 1] prefix sum of k-mer counts (host copy for chunking)
+    cudaEvent_t ready = nullptr;       // recorded after the H2D copies of an asynchronous upload
     uint64_t kmer_size = 0, max_kmers = 0;
+    uint64_t total_bases_bound = 0;  // upper bound on the batch's k-mers when the prefix sum is device-only
     uint64_t bytes = 0;
     void release() {
         lengths.release();
@@ -132,8 +136,12 @@ struct pf_dev_batch {
         exc_index.release();
         word_off.release();
         kmer_off.release();
+        kcnt.release();
+        kbsum.release();
         exc_off.release();
         exc_bytes.release();
+        if (ready) cudaEventDestroy(ready);
+        ready = nullptr;
     }
 };
 
@@ -174,6 +182,7 @@ static int load_nccl() {
 struct pf_db {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of the next batch overlaps the query of the current one
     int sm_count = 148;
     // host copy of the flattened tree (level order)
     HostTree tree;
@@ -267,6 +276,7 @@ static void db_free(pf_db *db) {
     if (db->ev_end) cudaEventDestroy(db->ev_end);
     for (auto e : db->ev_probe) cudaEventDestroy(e);
     if (db->stream) cudaStreamDestroy(db->stream);
+    if (db->copy_stream) cudaStreamDestroy(db->copy_stream);
     delete db;
 }
 
@@ -367,6 +377,7 @@ static int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     }
     PF_CUDA_OK(cudaSetDevice(db->device));
     PF_CUDA_OK(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+    PF_CUDA_OK(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
     PF_CUDA_OK(cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, db->device));
     std::string err;
     std::string dir(db_path);
@@ -680,13 +691,18 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     db->stats.group_rounds = G;
     const uint64_t budget_kmers = std::max<uint64_t>(db->hash_cache_bytes / 12, 1);  // 8 B hash + 4 B index
     const std::vector<uint64_t> &ko = bt->h_kmer_off;
+    const bool one_chunk = ko.empty();  // prefix sum lives on the device only; the whole batch fits the cache
     for (uint32_t r0 = 0; r0 < n_reads;) {
         // chunk [r0, r1): as many reads as the hash cache holds (always at least one)
-        uint32_t r1 = (uint32_t)(std::upper_bound(ko.begin() + r0 + 1, ko.begin() + n_reads + 1, ko[r0] + budget_kmers) -
-                                 ko.begin()) - 1;
-        if (r1 <= r0) r1 = r0 + 1;
+        uint32_t r1 = n_reads;
+        if (!one_chunk) {
+            r1 = (uint32_t)(std::upper_bound(ko.begin() + r0 + 1, ko.begin() + n_reads + 1, ko[r0] + budget_kmers) -
+                            ko.begin()) - 1;
+            if (r1 <= r0) r1 = r0 + 1;
+        }
         const uint32_t n_chunk = r1 - r0;
-        const uint64_t chunk_kmers = ko[r1] - ko[r0];
+        const uint64_t chunk_kmers = one_chunk ? bt->total_bases_bound : ko[r1] - ko[r0];
+        const uint64_t kmer_base = one_chunk ? 0 : ko[r0];
         if ((rc = db->hb.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
         if (db->hp.small_m && (rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
         PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, 2 * db->n_nodes * 4, s));
@@ -702,7 +718,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         h.hb = db->hb.p;
         h.idx0 = db->hp.small_m ? db->idx0.p : nullptr;
         h.hp = db->hp;
-        h.kmer_base = ko[r0];
+        h.kmer_base = kmer_base;
         h.read0 = r0;
         h.n_reads = n_chunk;
         h.k = db->hp.k;
@@ -746,7 +762,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
             a.kmer_off = bt->kmer_off.p;
             a.hb = db->hb.p;
             a.idx0 = db->idx0.p;
-            a.kmer_base = ko[r0];
+            a.kmer_base = kmer_base;
             a.node_slot = db->d_slot;
             a.node_steps = db->d_steps;
             a.filters = db->d_filters;
@@ -858,7 +874,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     return PF_OK;
 }
 
-static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b) {
+static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b, cudaStream_t s) {
     if (!in || (in->n_reads && (!in->lengths || !in->word_off || !in->packed))) {
         set_error("pf_read_batch: null array");
         return PF_ERR_ARG;
@@ -868,7 +884,6 @@ static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b
         return PF_ERR_ARG;
     }
     PF_CUDA_OK(cudaSetDevice(db->device));
-    cudaStream_t s = db->stream;
     int rc;
     b->n_reads = in->n_reads;
     b->n_exc = in->n_exc;
@@ -883,17 +898,36 @@ static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b
     PF_CUDA_OK(cudaMemcpyAsync(b->packed.p, in->packed, (size_t)in->n_words * 4, cudaMemcpyHostToDevice, s));
     PF_CUDA_OK(cudaMemsetAsync(b->packed.p + in->n_words, 0, 16, s));
     b->bytes = (uint64_t)in->n_reads * 12 + in->n_words * 4;
-    // k-mer offsets (device-side bookkeeping derived from `lengths`; not part of the host batch)
+    // k-mer offsets: bookkeeping derived from `lengths`, not part of the host batch.  When the packer supplied
+    // max_length / total_bases and the batch fits the hash cache in one chunk, the prefix sum is done on the
+    // device; otherwise the host builds it (it is then also needed to cut the batch into chunks).
+    const uint32_t k = (uint32_t)db->tree.kmer_size;
     b->kmer_size = db->tree.kmer_size;
-    b->h_kmer_off.assign((size_t)in->n_reads + 1, 0);
-    b->max_kmers = 0;
-    for (uint32_t r = 0; r < in->n_reads; ++r) {
-        const uint64_t nk = kmers_of(in->lengths[r], (uint32_t)db->tree.kmer_size);
-        b->h_kmer_off[r + 1] = b->h_kmer_off[r] + nk;
-        b->max_kmers = std::max(b->max_kmers, nk);
-    }
     if ((rc = b->kmer_off.ensure((size_t)in->n_reads + 1))) return rc;
-    PF_CUDA_OK(cudaMemcpyAsync(b->kmer_off.p, b->h_kmer_off.data(), ((size_t)in->n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+    const bool one_chunk = in->max_length != 0 && in->total_bases != 0 && in->total_bases <= db->hash_cache_bytes / 12;
+    b->total_bases_bound = in->total_bases;
+    if (one_chunk) {
+        b->h_kmer_off.clear();
+        b->max_kmers = kmers_of(in->max_length, k);
+        const uint32_t nb = (in->n_reads + 1023u) / 1024u;
+        if ((rc = b->kcnt.ensure(in->n_reads)) || (rc = b->kbsum.ensure(nb))) return rc;
+        kmer_counts_kernel<<<(in->n_reads + 255) / 256, 256, 0, s>>>(b->lengths.p, in->n_reads, k, b->kcnt.p);
+        csr_block_sums_kernel<<<nb, 1024, 0, s>>>(b->kcnt.p, in->n_reads, b->kbsum.p);
+        csr_scan_sums_kernel<<<1, 1024, 0, s>>>(b->kbsum.p, nb);
+        csr_offsets_kernel<<<nb, 1024, 0, s>>>(b->kcnt.p, in->n_reads, b->kbsum.p,
+                                               reinterpret_cast<unsigned long long *>(b->kmer_off.p));
+        db->stats.other_launches += 4;
+    } else {
+        b->h_kmer_off.assign((size_t)in->n_reads + 1, 0);
+        b->max_kmers = 0;
+        for (uint32_t r = 0; r < in->n_reads; ++r) {
+            const uint64_t nk = kmers_of(in->lengths[r], k);
+            b->h_kmer_off[r + 1] = b->h_kmer_off[r] + nk;
+            b->max_kmers = std::max(b->max_kmers, nk);
+        }
+        PF_CUDA_OK(cudaMemcpyAsync(b->kmer_off.p, b->h_kmer_off.data(), ((size_t)in->n_reads + 1) * 8,
+                                   cudaMemcpyHostToDevice, s));
+    }
     if (in->n_exc) {
         b->exc_nbytes = in->exc_off[in->n_exc];
         if ((rc = b->exc_index.ensure(in->n_reads)) || (rc = b->exc_off.ensure((size_t)in->n_exc + 1)) ||
@@ -906,6 +940,8 @@ static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b
         b->bytes += (uint64_t)in->n_reads * 4 + ((uint64_t)in->n_exc + 1) * 8 + b->exc_nbytes;
     }
     db->stats.h2d_bytes += b->bytes;
+    if (!b->ready) PF_CUDA_OK(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
+    PF_CUDA_OK(cudaEventRecord(b->ready, s));
     return PF_OK;
 }
 
@@ -1037,7 +1073,7 @@ int pf_batch_upload(pf_db *db, const pf_read_batch *in, pf_dev_batch **out) {
         return PF_ERR_ARG;
     }
     pf_dev_batch *b = new pf_dev_batch();
-    int rc = batch_upload_impl(db, in, b);
+    int rc = batch_upload_impl(db, in, b, db->stream);
     if (rc == PF_OK && cudaStreamSynchronize(db->stream) != cudaSuccess) {
         set_error("CUDA error in pf_batch_upload: %s", cudaGetErrorString(cudaGetLastError()));
         rc = PF_ERR_CUDA;
@@ -1063,7 +1099,27 @@ int pf_query_device(pf_db *db, pf_dev_batch *batch, float threshold, int want_hi
         set_error("pf_query_device: null argument");
         return PF_ERR_ARG;
     }
+    PF_CUDA_OK(cudaSetDevice(db->device));
+    if (batch->ready) PF_CUDA_OK(cudaStreamWaitEvent(db->stream, batch->ready, 0));  // asynchronous upload
     return query_impl(db, batch, threshold, want_hits, out);
+}
+
+int pf_batch_upload_async(pf_db *db, const pf_read_batch *in, pf_dev_batch **inout) {
+    if (!db || !in || !inout) {
+        set_error("pf_batch_upload_async: null argument");
+        return PF_ERR_ARG;
+    }
+    pf_dev_batch *b = *inout ? *inout : new pf_dev_batch();
+    int rc = batch_upload_impl(db, in, b, db->copy_stream);
+    if (rc != PF_OK) {
+        if (!*inout) {
+            b->release();
+            delete b;
+        }
+        return rc;
+    }
+    *inout = b;
+    return PF_OK;
 }
 
 int pf_query_block(pf_db *db, const pf_read_batch *in, float threshold, int want_hits, pf_hits *out) {
@@ -1071,7 +1127,7 @@ int pf_query_block(pf_db *db, const pf_read_batch *in, float threshold, int want
         set_error("pf_query_block: null argument");
         return PF_ERR_ARG;
     }
-    int rc = batch_upload_impl(db, in, &db->own_batch);
+    int rc = batch_upload_impl(db, in, &db->own_batch, db->stream);
     if (rc != PF_OK) return rc;
     return query_impl(db, &db->own_batch, threshold, want_hits, out);
 }
