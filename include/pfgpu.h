@@ -172,8 +172,9 @@ int pf_db_set_lazy(pf_db *db, int on);
 /* hash_bytes of every k-mer is computed once per batch and cached in HBM (8 B per k-mer); a batch whose
  * cache would exceed `bytes` (default 16 GiB) is processed in several chunks of reads. */
 int pf_db_set_hash_cache_bytes(pf_db *db, uint64_t bytes);
-/* Probe steps per node (level order, n_nodes entries) the next query with `threshold` will use. */
-int pf_db_node_steps(pf_db *db, float threshold, uint32_t *steps);
+/* Probe steps per node (level order, n_nodes entries) a query with `threshold` uses for a batch whose reads
+ * of mean length have `nominal_kmers` k-mers (K = exact, 0 = skipped). */
+int pf_db_node_steps(pf_db *db, float threshold, uint64_t nominal_kmers, uint32_t *steps);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU: reads are sharded by rank, every rank holds a replica of the tree, and the

@@ -939,10 +939,25 @@ static int filter_contains_filter(const pfo_filter *parent, const pfo_filter *ch
         if (child->words[i] & ~parent->words[i]) return 0;
     return 1;
 }
-/* Steps per node under the kernel's plan (pf_query.cu plan_steps), restated: leaves and unverified nodes use
- * K; a verified-monotone interior node takes the cheaper of "test with the smallest s reaching the target" and
- * "skip (0 steps)", bottom-up; plain double arithmetic only. */
-static double probe_cost(double f, uint32_t s) {
+/* ---- expected-cost step plan -------------------------------------------------------------------------
+ * The same text (modulo the node accessors) lives in oracle/pf_oracle.c and phagefilter_b200/csrc/pf_query.cu;
+ * only +,-,*,/ and sqrt on doubles and a fixed table, so both produce the same table bit for bit.
+ * Model: a read unrelated to the subtree has n absent k-mers; at a node with fill f probed for s steps each
+ * k-mer is proven absent with probability p = 1 - f^s after (1-f^s)/(1-f) expected probes; the read is pruned
+ * when more than `allowed` k-mers are proven absent: P = Phi((n p - allowed - 0.5) / sqrt(n p (1-p))).
+ * Bottom-up, a verified interior node picks s in {0 (skip), 1..K} minimising
+ *     probes(f,s) + PAIR_OVERHEAD + (1 - P) * (cost(left) + cost(right))            [s = 0: just the children]
+ * Leaves and unverified nodes are exact (s = K). */
+#define PF_PLAN_PAIR_OVERHEAD 0.25
+static double plan_phi(double z) { /* standard normal CDF: 33-point table on [-4,4], linear interpolation */
+    static const double T[33] = {3.167124183312e-05, 8.841728520081e-05, 2.326290790355e-04, 5.770250423908e-04, 1.349898031630e-03, 2.979763235055e-03, 6.209665325776e-03, 1.222447265504e-02, 2.275013194818e-02, 4.005915686382e-02, 6.680720126886e-02, 1.056497736669e-01, 1.586552539315e-01, 2.266273523769e-01, 3.085375387260e-01, 4.012936743171e-01, 5.000000000000e-01, 5.987063256829e-01, 6.914624612740e-01, 7.733726476231e-01, 8.413447460685e-01, 8.943502263331e-01, 9.331927987311e-01, 9.599408431362e-01, 9.772498680518e-01, 9.877755273450e-01, 9.937903346742e-01, 9.970202367649e-01, 9.986501019684e-01, 9.994229749576e-01, 9.997673709210e-01, 9.999115827148e-01, 9.999683287582e-01};
+    if (z <= -4.0) return 0.0;
+    if (z >= 4.0) return 1.0;
+    const double x = (z + 4.0) * 4.0;
+    const int i = (int)x;
+    return T[i] + (T[i + 1] - T[i]) * (x - (double)i);
+}
+static double plan_probe_cost(double f, uint32_t s) { /* expected probes per absent k-mer over s steps */
     double c = 0.0, p = 1.0;
     for (uint32_t i = 0; i < s; ++i) {
         c += p;
@@ -950,7 +965,32 @@ static double probe_cost(double f, uint32_t s) {
     }
     return c;
 }
-static double plan_rec(const pfo_tree *t, pfo_node *n, double target, int lazy) {
+static double plan_prune_prob(double n, double allowed, double f, uint32_t s) {
+    double surv = 1.0;
+    for (uint32_t i = 0; i < s; ++i) surv *= f;
+    const double p = 1.0 - surv, mean = n * p, var = n * p * (1.0 - p);
+    if (var < 1e-9) return mean > allowed ? 1.0 : 0.0;
+    return plan_phi((mean - allowed - 0.5) / sqrt(var));
+}
+/* best steps for one verified interior node; *cost_out = its expected cost */
+static uint32_t plan_choose(double f, uint32_t K, double n, double allowed, double below, double *cost_out) {
+    uint32_t best_s = 0;
+    double best = below;
+    for (uint32_t s = 1; s <= K; ++s) {
+        const double c = plan_probe_cost(f, s) + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(n, allowed, f, s)) * below;
+        if (c < best) {
+            best = c;
+            best_s = s;
+        }
+    }
+    *cost_out = best;
+    return best_s;
+}
+static double plan_exact_cost(double f, uint32_t K, double n, double allowed, double below) {
+    return plan_probe_cost(f, K) + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(n, allowed, f, K)) * below;
+}
+
+static double plan_rec(const pfo_tree *t, pfo_node *n, double nn, double allowed, int lazy) {
     const pfo_filter *f = t->filters[n->filter];
     const uint32_t K = f->K;
     if (!n->analysed) {
@@ -962,36 +1002,23 @@ static double plan_rec(const pfo_tree *t, pfo_node *n, double target, int lazy) 
     const double fill = (double)n->pop / (double)f->m;
     if (is_leaf(n)) {
         n->steps = K;
-        return probe_cost(fill, K);
+        return plan_probe_cost(fill, K) + PF_PLAN_PAIR_OVERHEAD;
     }
-    /* children first (their costs feed the parent's choice) */
-    const double cl = n->left ? plan_rec(t, n->left, target, lazy) : 0.0;
-    const double cr = n->right ? plan_rec(t, n->right, target, lazy) : 0.0;
+    const double cl = n->left ? plan_rec(t, n->left, nn, allowed, lazy) : 0.0;
+    const double cr = n->right ? plan_rec(t, n->right, nn, allowed, lazy) : 0.0;
     const double below = cl + cr;
-    uint32_t s_star = 0;
-    double p = 1.0;
-    for (uint32_t s = 1; s <= K; ++s) {
-        p *= fill;
-        if (p <= target) {
-            s_star = s;
-            break;
-        }
-    }
     if (!lazy || !n->mono) {
         n->steps = K;
-        return probe_cost(fill, K) + (s_star ? 0.0 : below);
+        return plan_exact_cost(fill, K, nn, allowed, below);
     }
-    if (s_star && probe_cost(fill, s_star) <= below) {
-        n->steps = s_star;
-        return probe_cost(fill, s_star);
-    }
-    n->steps = 0;
-    return below;
+    double c = 0.0;
+    n->steps = plan_choose(fill, K, nn, allowed, below, &c);
+    return c;
 }
-static void plan_steps(pfo_tree *t, float threshold, int lazy) {
-    double q = 1.5 * (1.0 - (double)threshold) + 0.02;
-    if (q > 0.9) q = 0.9;
-    if (t->root) plan_rec(t, t->root, 1.0 - q, lazy);
+static void plan_steps(pfo_tree *t, float threshold, uint64_t n_nominal, int lazy) {
+    const uint64_t need = pfo_need(threshold, n_nominal);
+    const double allowed = need > n_nominal ? 0.0 : (double)(n_nominal - need);
+    if (t->root) plan_rec(t, t->root, (double)n_nominal, allowed, lazy);
 }
 static uint32_t pfo_node_steps(const pfo_tree *t, pfo_node *n, float threshold, int lazy) {
     (void)t;
@@ -1103,7 +1130,11 @@ static int query_impl(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, ui
     for (uint32_t i = 0; i < n_reads; i++) all[i] = i;
     if (sched) {
         refresh(t);
-        plan_steps(t, threshold, lazy);
+        {   /* nominal read: mean length of the block, as the kernel's planner */
+            uint64_t mean_len = n_reads ? (offs[n_reads] - offs[0]) / n_reads : 0;
+            uint64_t nk = pfo_num_kmers((size_t)mean_len, k);
+            plan_steps(t, threshold, nk ? nk : 1, lazy);
+        }
         sctx c = {t, reads, want_hits, lazy, group_rounds, threshold, out, 0, 0};
         sched_rec(&c, t->root, all, n_reads, 1);
     } else {

@@ -74,9 +74,10 @@ class BloomTree:
     def set_lazy(self, on: bool) -> None:
         _lib.check(_lib.lib().pf_db_set_lazy(self._h, int(on)))
 
-    def node_steps(self, threshold: float) -> np.ndarray:
+    def node_steps(self, threshold: float, nominal_kmers: int = 131) -> np.ndarray:
         out = np.zeros(int(self._info.n_nodes), dtype=np.uint32)
-        _lib.check(_lib.lib().pf_db_node_steps(self._h, C.c_float(threshold), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        _lib.check(_lib.lib().pf_db_node_steps(self._h, C.c_float(threshold), nominal_kmers,
+                                               out.ctypes.data_as(C.POINTER(C.c_uint32))))
         return out
 
     def stats(self) -> _lib.Stats:

@@ -129,6 +129,7 @@ struct pf_dev_batch {
     cudaEvent_t ready = nullptr;       // recorded after the H2D copies of an asynchronous upload
     uint64_t kmer_size = 0, max_kmers = 0;
     uint64_t total_bases_bound = 0;  // upper bound on the batch's k-mers when the prefix sum is device-only
+    uint64_t nominal_kmers = 1;      // k-mers of a read of mean length: what the step plan is made for
     uint64_t bytes = 0;
     void release() {
         lengths.release();
@@ -204,6 +205,7 @@ struct pf_db {
     std::vector<uint32_t> entry_start;    // [n_levels + 1] offsets into h_entry per level
     uint32_t *d_entry = nullptr;
     float steps_theta = -1.f;
+    uint64_t steps_n = 0;  // nominal k-mers per read the plan was made for
     int steps_mode = -1;
     uint64_t n_internal = 0, n_monotone = 0;
     // device tree
@@ -516,13 +518,26 @@ static int analyse_tree(pf_db *db) {
 
 // Probe steps per node.  Leaves, unverified nodes and the reference-faithful modes use all K steps (exact).
 // A verified-monotone interior node never has to CONFIRM a pass (its children imply it); it is only worth
-// probing if that prunes reads that do not belong below it.  With fill f, an absent k-mer survives s steps
-// with probability ~f^s and costs (1-f^s)/(1-f) probes; an unrelated read is (nominally) pruned once
-// 1-f^s >= q, q = min(0.9, 1.5*(1-threshold) + 0.02) -- 1.5x the miss fraction it may afford.  Bottom-up,
-// each node takes the cheaper of "test with the smallest such s" and "skip (0 steps) and let the children
-// prune"; nodes too saturated to reach q within K steps are skipped.  Plain double arithmetic only, so the
-// oracle's restatement reproduces the table bit for bit.
-static double probe_cost(double f, uint32_t s) {  // expected probes per absent k-mer over s steps
+// probing if that prunes reads that do not belong below it.
+/* ---- expected-cost step plan -------------------------------------------------------------------------
+ * Only +,-,*,/ and sqrt on doubles and a fixed table are used, so the CPU checker's independent restatement of
+ * this planner reproduces the table bit for bit (the tests compare the kernel's work counts with it).
+ * Model: a read unrelated to the subtree has n absent k-mers; at a node with fill f probed for s steps each
+ * k-mer is proven absent with probability p = 1 - f^s after (1-f^s)/(1-f) expected probes; the read is pruned
+ * when more than `allowed` k-mers are proven absent: P = Phi((n p - allowed - 0.5) / sqrt(n p (1-p))).
+ * Bottom-up, a verified interior node picks s in {0 (skip), 1..K} minimising
+ *     probes(f,s) + PAIR_OVERHEAD + (1 - P) * (cost(left) + cost(right))            [s = 0: just the children]
+ * Leaves and unverified nodes are exact (s = K). */
+#define PF_PLAN_PAIR_OVERHEAD 0.25
+static double plan_phi(double z) { /* standard normal CDF: 33-point table on [-4,4], linear interpolation */
+    static const double T[33] = {3.167124183312e-05, 8.841728520081e-05, 2.326290790355e-04, 5.770250423908e-04, 1.349898031630e-03, 2.979763235055e-03, 6.209665325776e-03, 1.222447265504e-02, 2.275013194818e-02, 4.005915686382e-02, 6.680720126886e-02, 1.056497736669e-01, 1.586552539315e-01, 2.266273523769e-01, 3.085375387260e-01, 4.012936743171e-01, 5.000000000000e-01, 5.987063256829e-01, 6.914624612740e-01, 7.733726476231e-01, 8.413447460685e-01, 8.943502263331e-01, 9.331927987311e-01, 9.599408431362e-01, 9.772498680518e-01, 9.877755273450e-01, 9.937903346742e-01, 9.970202367649e-01, 9.986501019684e-01, 9.994229749576e-01, 9.997673709210e-01, 9.999115827148e-01, 9.999683287582e-01};
+    if (z <= -4.0) return 0.0;
+    if (z >= 4.0) return 1.0;
+    const double x = (z + 4.0) * 4.0;
+    const int i = (int)x;
+    return T[i] + (T[i + 1] - T[i]) * (x - (double)i);
+}
+static double plan_probe_cost(double f, uint32_t s) { /* expected probes per absent k-mer over s steps */
     double c = 0.0, p = 1.0;
     for (uint32_t i = 0; i < s; ++i) {
         c += p;
@@ -530,51 +545,68 @@ static double probe_cost(double f, uint32_t s) {  // expected probes per absent 
     }
     return c;
 }
-static void plan_steps(pf_db *db, double theta, std::vector<uint32_t> &steps) {
+static double plan_prune_prob(double n, double allowed, double f, uint32_t s) {
+    double surv = 1.0;
+    for (uint32_t i = 0; i < s; ++i) surv *= f;
+    const double p = 1.0 - surv, mean = n * p, var = n * p * (1.0 - p);
+    if (var < 1e-9) return mean > allowed ? 1.0 : 0.0;
+    return plan_phi((mean - allowed - 0.5) / sqrt(var));
+}
+/* best steps for one verified interior node; *cost_out = its expected cost */
+static uint32_t plan_choose(double f, uint32_t K, double n, double allowed, double below, double *cost_out) {
+    uint32_t best_s = 0;
+    double best = below;
+    for (uint32_t s = 1; s <= K; ++s) {
+        const double c = plan_probe_cost(f, s) + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(n, allowed, f, s)) * below;
+        if (c < best) {
+            best = c;
+            best_s = s;
+        }
+    }
+    *cost_out = best;
+    return best_s;
+}
+static double plan_exact_cost(double f, uint32_t K, double n, double allowed, double below) {
+    return plan_probe_cost(f, K) + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(n, allowed, f, K)) * below;
+}
+
+// (threshold * n as f32).ceil() as usize  (query.rs:48), on the host
+static uint64_t host_need(float threshold, uint64_t n) {
+    volatile float prod = threshold * (float)n;
+    const float c = ceilf(prod);
+    if (!(c > 0.0f)) return 0;
+    if (c >= 18446744073709551616.0f) return ~0ULL;
+    return (uint64_t)c;
+}
+static void plan_steps(pf_db *db, float threshold, uint64_t n_nominal, std::vector<uint32_t> &steps) {
     const uint32_t K = db->geom.num_hashes;
     const size_t nn = db->n_nodes;
-    double q = 1.5 * (1.0 - theta) + 0.02;
-    if (q > 0.9) q = 0.9;
-    const double target = 1.0 - q;
+    const uint64_t need = host_need(threshold, n_nominal);
+    const double n = (double)n_nominal, allowed = need > n_nominal ? 0.0 : (double)(n_nominal - need);
     std::vector<double> cost(nn, 0.0);
     steps.assign(nn, K);
     for (size_t u = nn; u-- > 0;) {  // children have larger level-order ids than their parent
         const double f = (double)db->h_pop[u] / (double)db->geom.num_bits;
         const uint32_t l = db->h_left[u], r = db->h_right[u];
         if (db->h_leaf[u] >= 0) {
-            cost[u] = probe_cost(f, K);
+            cost[u] = plan_probe_cost(f, K) + PF_PLAN_PAIR_OVERHEAD;
             continue;
         }
         const double below = (l != NONE32 ? cost[l] : 0.0) + (r != NONE32 ? cost[r] : 0.0);
-        uint32_t s_star = 0;  // smallest s with f^s <= target, 0 if none within K
-        double p = 1.0;
-        for (uint32_t s = 1; s <= K; ++s) {
-            p *= f;
-            if (p <= target) {
-                s_star = s;
-                break;
-            }
-        }
-        if (!db->h_mono[u]) {  // exact node: all K steps; it prunes only if K steps reach the target
+        if (!db->h_mono[u]) {
             steps[u] = K;
-            cost[u] = probe_cost(f, K) + (s_star ? 0.0 : below);
-            continue;
-        }
-        if (s_star && probe_cost(f, s_star) <= below) {
-            steps[u] = s_star;
-            cost[u] = probe_cost(f, s_star);
+            cost[u] = plan_exact_cost(f, K, n, allowed, below);
         } else {
-            steps[u] = 0;
-            cost[u] = below;
+            steps[u] = plan_choose(f, K, n, allowed, below, &cost[u]);
         }
     }
 }
-static int update_steps(pf_db *db, float threshold) {
+static int update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
     const int mode = db->exhaustive ? 2 : (db->lazy ? 1 : 0);
-    if (mode == db->steps_mode && (mode != 1 || threshold == db->steps_theta)) return PF_OK;
+    if (mode == db->steps_mode && (mode != 1 || (threshold == db->steps_theta && n_nominal == db->steps_n))) return PF_OK;
     const uint32_t K = db->geom.num_hashes;
     db->h_steps.assign(db->n_nodes, K);
-    if (mode == 1) plan_steps(db, (double)threshold, db->h_steps);
+    if (mode == 1) plan_steps(db, threshold, n_nominal, db->h_steps);
     // entry nodes: descend from the root through skipped (0-step) interior nodes; level-order ids are already
     // sorted by level, so a sorted list is grouped by level
     db->h_entry.clear();
@@ -603,6 +635,7 @@ static int update_steps(pf_db *db, float threshold) {
     PF_CUDA_OK(cudaStreamSynchronize(db->stream));
     db->steps_mode = mode;
     db->steps_theta = threshold;
+    db->steps_n = n_nominal;
     return PF_OK;
 }
 
@@ -676,7 +709,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
                   (unsigned long long)db->tree.kmer_size);
         return PF_ERR_STATE;
     }
-    if ((rc = update_steps(db, threshold))) return rc;
+    if ((rc = update_steps(db, threshold, bt->nominal_kmers))) return rc;
     PF_CUDA_OK(cudaEventRecord(db->ev_begin, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_blk_counts, 0, std::max<uint64_t>(db->n_leaves, 1) * 8, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_probes, 0, 8, s));
@@ -906,6 +939,13 @@ static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b
     if ((rc = b->kmer_off.ensure((size_t)in->n_reads + 1))) return rc;
     const bool one_chunk = in->max_length != 0 && in->total_bases != 0 && in->total_bases <= db->hash_cache_bytes / 12;
     b->total_bases_bound = in->total_bases;
+    {
+        uint64_t tb = in->total_bases;
+        if (tb == 0)
+            for (uint32_t r = 0; r < in->n_reads; ++r) tb += in->lengths[r];
+        const uint64_t mean_len = tb / in->n_reads;
+        b->nominal_kmers = std::max<uint64_t>(1, kmers_of((uint32_t)std::min<uint64_t>(mean_len, 0xFFFFFFFFu), k));
+    }
     if (one_chunk) {
         b->h_kmer_off.clear();
         b->max_kmers = kmers_of(in->max_length, k);
@@ -1026,10 +1066,10 @@ int pf_db_set_lazy(pf_db *db, int on) {
     db->lazy = on ? 1 : 0;
     return PF_OK;
 }
-int pf_db_node_steps(pf_db *db, float threshold, uint32_t *steps) {
+int pf_db_node_steps(pf_db *db, float threshold, uint64_t nominal_kmers, uint32_t *steps) {
     if (!db || !steps) return PF_ERR_ARG;
     PF_CUDA_OK(cudaSetDevice(db->device));
-    int rc = update_steps(db, threshold);
+    int rc = update_steps(db, threshold, nominal_kmers ? nominal_kmers : 1);
     if (rc != PF_OK) return rc;
     memcpy(steps, db->h_steps.data(), db->n_nodes * 4);
     return PF_OK;
