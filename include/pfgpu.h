@@ -103,7 +103,10 @@ typedef struct pf_read_batch {
     uint64_t total_bases;      /* sum of lengths; 0 = unknown */
 } pf_read_batch;
 
-/* Host-side packer from raw ASCII reads (seqs concatenated, offs[n_reads+1]) into pinned memory. */
+/* Host-side packer from raw ASCII reads (seqs concatenated, offs[n_reads+1]) into pinned memory, on several
+ * host threads (PF_PACK_THREADS overrides the count).  *out must be NULL (a new pf_packed is allocated) or a
+ * pf_packed from an earlier call, whose buffers are then recycled -- page-locking memory is slower than
+ * packing it. */
 typedef struct pf_packed pf_packed;
 int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, pf_packed **out);
 const pf_read_batch *pf_packed_batch(const pf_packed *p);

@@ -4,31 +4,108 @@
 // travels as 2 bits per base and k-mers are re-created on the GPU.  Reads holding any byte other than
 // upper-case A/C/G/T are hashed verbatim by the reference, so they are carried as raw bytes too
 // (exception side channel) and take the byte-exact path on the device.
+//
+// One pass over the bases on several host threads (table lookup, 16 bases per word); the pinned buffers of
+// a previous batch can be recycled, because page-locking memory costs more than packing it.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "pf_common.h"
 
-struct pf_packed {
-    pf_read_batch b{};
-    void *pinned = nullptr;  // one allocation carved into the arrays below
-    size_t pinned_bytes = 0;
-    bool is_pinned = false;  // false: pageable memory (no CUDA device present; packing is host logic)
+namespace {
+
+struct HostBuf {  // pinned when a CUDA device is present, pageable otherwise (packing is host logic)
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap) return true;
+        release();
+        const size_t want = bytes + bytes / 4 + 64;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+            if (cudaMallocHost(&p, want) == cudaSuccess) pinned = true;
+            else {
+                cudaGetLastError();
+                p = nullptr;
+            }
+        } else {
+            cudaGetLastError();
+        }
+        if (!p) {
+            p = aligned_alloc(64, (want + 63) / 64 * 64);
+            pinned = false;
+        }
+        cap = p ? want : 0;
+        return p != nullptr;
+    }
+    void release() {
+        if (p) {
+            if (pinned) cudaFreeHost(p);
+            else free(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
 };
 
-namespace {
-inline int code_of(uint8_t c) {
-    switch (c) {
-        case 'A': return 0;
-        case 'C': return 1;
-        case 'G': return 2;
-        case 'T': return 3;
-        default: return -1;
+struct Lut {
+    uint8_t code[256];
+    Lut() {
+        memset(code, 0xFF, sizeof code);
+        code[(uint8_t)'A'] = 0;
+        code[(uint8_t)'C'] = 1;
+        code[(uint8_t)'G'] = 2;
+        code[(uint8_t)'T'] = 3;
     }
-}
+};
+const Lut kLut;
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline uint64_t words_of(uint64_t len) { return ((len + 15) / 16 + 1) & ~1ULL; }  // even: 8-byte aligned reads
+
+// packs one read into nw zero-padded words; returns false (all zeros) if it holds a byte outside {A,C,G,T}
+inline bool pack_read(const uint8_t *s, uint64_t len, uint32_t *dst, uint64_t nw) {
+    const uint64_t full = len / 16;
+    uint32_t bad = 0;
+    for (uint64_t w = 0; w < full; ++w) {
+        const uint8_t *q = s + w * 16;
+        uint32_t v = 0;
+#pragma GCC unroll 16
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t c = kLut.code[q[j]];
+            bad |= c;
+            v |= (c & 3u) << (2 * j);
+        }
+        dst[w] = v;
+    }
+    uint64_t used = full;
+    if (len % 16) {
+        uint32_t v = 0;
+        for (uint64_t j = 0; j < len % 16; ++j) {
+            const uint32_t c = kLut.code[s[full * 16 + j]];
+            bad |= c;
+            v |= (c & 3u) << (2 * j);
+        }
+        dst[used++] = v;
+    }
+    for (; used < nw; ++used) dst[used] = 0;
+    if (bad & 0x80u) {
+        memset(dst, 0, nw * 4);
+        return false;
+    }
+    return true;
+}
+
 }  // namespace
+
+struct pf_packed {
+    pf_read_batch b{};
+    HostBuf main, exc;
+};
 
 extern "C" {
 
@@ -45,95 +122,113 @@ void pf_free_pinned(void *p) {
 }
 
 int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, pf_packed **out) {
-    if (!out || !offs || (!seqs && n_reads && offs[n_reads] > 0)) {
+    if (!out || !offs || (!seqs && n_reads && offs[n_reads] > offs[0])) {
         pf::set_error("pf_pack_reads: null argument");
         return PF_ERR_ARG;
     }
-    *out = nullptr;
-    // pass 1: sizes
-    uint64_t n_words = 0, exc_bytes = 0, total_bases = 0;
-    uint32_t n_exc = 0, max_length = 0;
-    std::vector<uint8_t> is_exc(n_reads, 0);
+    pf_packed *p = *out ? *out : new pf_packed();
+    auto fail = [&](int rc) {
+        if (!*out) {
+            p->main.release();
+            p->exc.release();
+            delete p;
+        }
+        return rc;
+    };
+    // sizes from the offsets alone
+    uint64_t total_bases = 0, n_words = 0;
+    uint32_t max_length = 0;
     for (uint32_t r = 0; r < n_reads; ++r) {
         const uint64_t len = offs[r + 1] - offs[r];
         if (len > 0xFFFFFFFFull) {
             pf::set_error("read %u longer than 2^32-1 bases", r);
-            return PF_ERR_ARG;
+            return fail(PF_ERR_ARG);
         }
-        const uint8_t *s = seqs + offs[r];
         total_bases += len;
-        if (len > max_length) max_length = (uint32_t)len;
-        bool exc = false;
-        for (uint64_t j = 0; j < len; ++j)
-            if (code_of(s[j]) < 0) {
-                exc = true;
-                break;
-            }
-        is_exc[r] = exc;
-        if (exc) {
-            n_exc++;
-            exc_bytes += len;
-        }
-        n_words += align_up((len + 15) / 16, 2);  // every read starts on an 8-byte boundary
+        max_length = std::max<uint32_t>(max_length, (uint32_t)len);
+        n_words += words_of(len);
     }
     const uint64_t pad_words = 4;
-    size_t o_len = 0;
-    size_t o_woff = align_up(o_len + (size_t)n_reads * 4, 16);
-    size_t o_packed = align_up(o_woff + (size_t)n_reads * 8, 16);
-    size_t o_excidx = align_up(o_packed + (size_t)(n_words + pad_words) * 4, 16);
-    size_t o_excoff = align_up(o_excidx + (n_exc ? (size_t)n_reads * 4 : 0), 16);
-    size_t o_excbytes = align_up(o_excoff + (n_exc ? ((size_t)n_exc + 1) * 8 : 0), 16);
-    size_t total = o_excbytes + (size_t)exc_bytes + 16;
-    pf_packed *p = new pf_packed();
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
-        p->pinned = pf_alloc_pinned(total);
-        p->is_pinned = p->pinned != nullptr;
-    } else {
-        cudaGetLastError();
-    }
-    if (!p->pinned) p->pinned = aligned_alloc(64, align_up(total, 64));
-    if (!p->pinned) {
-        delete p;
+    const size_t o_len = 0;
+    const size_t o_woff = align_up(o_len + (size_t)n_reads * 4, 16);
+    const size_t o_packed = align_up(o_woff + (size_t)n_reads * 8, 16);
+    const size_t o_excidx = align_up(o_packed + (size_t)(n_words + pad_words) * 4, 16);
+    const size_t total = o_excidx + (size_t)n_reads * 4 + 16;
+    if (!p->main.ensure(total)) {
         pf::set_error("pf_pack_reads: out of host memory (%zu bytes)", total);
-        return PF_ERR_NOMEM;
+        return fail(PF_ERR_NOMEM);
     }
-    p->pinned_bytes = total;
-    uint8_t *base = static_cast<uint8_t *>(p->pinned);
+    uint8_t *base = static_cast<uint8_t *>(p->main.p);
     uint32_t *lengths = reinterpret_cast<uint32_t *>(base + o_len);
     uint64_t *word_off = reinterpret_cast<uint64_t *>(base + o_woff);
     uint32_t *packed = reinterpret_cast<uint32_t *>(base + o_packed);
-    uint32_t *exc_index = n_exc ? reinterpret_cast<uint32_t *>(base + o_excidx) : nullptr;
-    uint64_t *exc_off = n_exc ? reinterpret_cast<uint64_t *>(base + o_excoff) : nullptr;
-    uint8_t *exc_b = n_exc ? base + o_excbytes : nullptr;
-    memset(packed, 0, (size_t)(n_words + pad_words) * 4);
-    // pass 2: fill
-    uint64_t w = 0, eb = 0;
-    uint32_t e = 0;
-    for (uint32_t r = 0; r < n_reads; ++r) {
-        const uint64_t len = offs[r + 1] - offs[r];
-        const uint8_t *s = seqs + offs[r];
-        lengths[r] = (uint32_t)len;
-        word_off[r] = w;
-        if (!is_exc[r]) {
-            for (uint64_t j = 0; j < len; ++j) packed[w + (j >> 4)] |= (uint32_t)code_of(s[j]) << (2 * (j & 15));
+    uint32_t *exc_index = reinterpret_cast<uint32_t *>(base + o_excidx);
+    {
+        uint64_t w = 0;
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            const uint64_t len = offs[r + 1] - offs[r];
+            lengths[r] = (uint32_t)len;
+            word_off[r] = w;
+            w += words_of(len);
         }
-        if (exc_index) exc_index[r] = is_exc[r] ? e : pf::NONE32;
-        if (is_exc[r]) {
-            exc_off[e++] = eb;
-            memcpy(exc_b + eb, s, len);
-            eb += len;
-        }
-        w += align_up((len + 15) / 16, 2);
+        memset(packed + n_words, 0, pad_words * 4);
     }
-    if (exc_off) exc_off[n_exc] = eb;
+    // one pass over the bases, in parallel over contiguous ranges of reads
+    unsigned n_thr = std::thread::hardware_concurrency();
+    if (const char *e = getenv("PF_PACK_THREADS")) n_thr = (unsigned)atoi(e);
+    n_thr = std::max(1u, std::min(n_thr, 32u));
+    if (total_bases < (1u << 20)) n_thr = 1;
+    std::vector<std::vector<uint32_t>> exc_lists(n_thr);
+    auto work = [&](unsigned t) {
+        const uint32_t r0 = (uint32_t)((uint64_t)n_reads * t / n_thr), r1 = (uint32_t)((uint64_t)n_reads * (t + 1) / n_thr);
+        for (uint32_t r = r0; r < r1; ++r) {
+            const uint64_t len = offs[r + 1] - offs[r];
+            exc_index[r] = pf::NONE32;
+            if (!pack_read(seqs + offs[r], len, packed + word_off[r], words_of(len))) exc_lists[t].push_back(r);
+        }
+    };
+    if (n_thr == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < n_thr; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    // exception side channel (rare): raw bytes of the reads that could not be packed
+    uint32_t n_exc = 0;
+    uint64_t exc_bytes = 0;
+    for (auto &l : exc_lists) {
+        n_exc += (uint32_t)l.size();
+        for (uint32_t r : l) exc_bytes += lengths[r];
+    }
+    uint64_t *exc_off = nullptr;
+    uint8_t *exc_b = nullptr;
+    if (n_exc) {
+        const size_t o_b = align_up(((size_t)n_exc + 1) * 8, 16);
+        if (!p->exc.ensure(o_b + exc_bytes + 16)) {
+            pf::set_error("pf_pack_reads: out of host memory");
+            return fail(PF_ERR_NOMEM);
+        }
+        exc_off = reinterpret_cast<uint64_t *>(p->exc.p);
+        exc_b = static_cast<uint8_t *>(p->exc.p) + o_b;
+        uint32_t e = 0;
+        uint64_t eb = 0;
+        for (auto &l : exc_lists)  // thread ranges are contiguous and ascending: indices stay sorted
+            for (uint32_t r : l) {
+                exc_index[r] = e;
+                exc_off[e++] = eb;
+                memcpy(exc_b + eb, seqs + offs[r], lengths[r]);
+                eb += lengths[r];
+            }
+        exc_off[n_exc] = eb;
+    }
     p->b.n_reads = n_reads;
     p->b.n_exc = n_exc;
     p->b.lengths = lengths;
     p->b.word_off = word_off;
     p->b.packed = packed;
     p->b.n_words = n_words + pad_words;
-    p->b.exc_index = exc_index;
+    p->b.exc_index = n_exc ? exc_index : nullptr;
     p->b.exc_off = exc_off;
     p->b.exc_bytes = exc_b;
     p->b.max_length = max_length;
@@ -146,8 +241,8 @@ const pf_read_batch *pf_packed_batch(const pf_packed *p) { return p ? &p->b : nu
 
 void pf_packed_free(pf_packed *p) {
     if (!p) return;
-    if (p->is_pinned) pf_free_pinned(p->pinned);
-    else free(p->pinned);
+    p->main.release();
+    p->exc.release();
     delete p;
 }
 
