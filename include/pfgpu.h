@@ -109,6 +109,8 @@ typedef struct pf_read_batch {
  * packing it. */
 typedef struct pf_packed pf_packed;
 int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, pf_packed **out);
+/* Same, for reads scattered in memory (e.g. slices of a parsed FASTQ buffer): one pointer and length per read. */
+int pf_pack_reads_ptrs(const uint8_t *const *seq_ptrs, const uint32_t *lengths, uint32_t n_reads, pf_packed **out);
 const pf_read_batch *pf_packed_batch(const pf_packed *p);
 void pf_packed_free(pf_packed *p);
 void *pf_alloc_pinned(size_t bytes);

@@ -70,6 +70,7 @@ SYMBOLS = {
     "pf_db_detect_hash_rot": (C.c_int, [_VP, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_int)]),
     "pf_db_close": (None, [_VP]),
     "pf_pack_reads": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(_VP)]),
+    "pf_pack_reads_ptrs": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(_VP)]),
     "pf_packed_batch": (C.POINTER(ReadBatch), [_VP]),
     "pf_packed_free": (None, [_VP]),
     "pf_alloc_pinned": (_VP, [C.c_size_t]),

@@ -121,11 +121,34 @@ void pf_free_pinned(void *p) {
     if (p) cudaFreeHost(p);
 }
 
+// seq(r) / len(r) accessors: contiguous (seqs + offs) or scattered (one pointer per read)
+struct ReadSrcView {
+    const uint8_t *seqs;
+    const uint64_t *offs;
+    const uint8_t *const *ptrs;
+    const uint32_t *lens;
+    const uint8_t *seq(uint32_t r) const { return ptrs ? ptrs[r] : seqs + offs[r]; }
+    uint64_t len(uint32_t r) const { return ptrs ? lens[r] : offs[r + 1] - offs[r]; }
+};
+static int pack_impl(const ReadSrcView &src, uint32_t n_reads, pf_packed **out);
+
 int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, pf_packed **out) {
     if (!out || !offs || (!seqs && n_reads && offs[n_reads] > offs[0])) {
         pf::set_error("pf_pack_reads: null argument");
         return PF_ERR_ARG;
     }
+    return pack_impl(ReadSrcView{seqs, offs, nullptr, nullptr}, n_reads, out);
+}
+
+int pf_pack_reads_ptrs(const uint8_t *const *seq_ptrs, const uint32_t *lengths, uint32_t n_reads, pf_packed **out) {
+    if (!out || (n_reads && (!seq_ptrs || !lengths))) {
+        pf::set_error("pf_pack_reads_ptrs: null argument");
+        return PF_ERR_ARG;
+    }
+    return pack_impl(ReadSrcView{nullptr, nullptr, seq_ptrs, lengths}, n_reads, out);
+}
+
+static int pack_impl(const ReadSrcView &src, uint32_t n_reads, pf_packed **out) {
     pf_packed *p = *out ? *out : new pf_packed();
     auto fail = [&](int rc) {
         if (!*out) {
@@ -139,7 +162,7 @@ int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, p
     uint64_t total_bases = 0, n_words = 0;
     uint32_t max_length = 0;
     for (uint32_t r = 0; r < n_reads; ++r) {
-        const uint64_t len = offs[r + 1] - offs[r];
+        const uint64_t len = src.len(r);
         if (len > 0xFFFFFFFFull) {
             pf::set_error("read %u longer than 2^32-1 bases", r);
             return fail(PF_ERR_ARG);
@@ -166,7 +189,7 @@ int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, p
     {
         uint64_t w = 0;
         for (uint32_t r = 0; r < n_reads; ++r) {
-            const uint64_t len = offs[r + 1] - offs[r];
+            const uint64_t len = src.len(r);
             lengths[r] = (uint32_t)len;
             word_off[r] = w;
             w += words_of(len);
@@ -182,9 +205,9 @@ int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, p
     auto work = [&](unsigned t) {
         const uint32_t r0 = (uint32_t)((uint64_t)n_reads * t / n_thr), r1 = (uint32_t)((uint64_t)n_reads * (t + 1) / n_thr);
         for (uint32_t r = r0; r < r1; ++r) {
-            const uint64_t len = offs[r + 1] - offs[r];
+            const uint64_t len = src.len(r);
             exc_index[r] = pf::NONE32;
-            if (!pack_read(seqs + offs[r], len, packed + word_off[r], words_of(len))) exc_lists[t].push_back(r);
+            if (!pack_read(src.seq(r), len, packed + word_off[r], words_of(len))) exc_lists[t].push_back(r);
         }
     };
     if (n_thr == 1) {
@@ -217,7 +240,7 @@ int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, p
             for (uint32_t r : l) {
                 exc_index[r] = e;
                 exc_off[e++] = eb;
-                memcpy(exc_b + eb, seqs + offs[r], lengths[r]);
+                memcpy(exc_b + eb, src.seq(r), lengths[r]);
                 eb += lengths[r];
             }
         exc_off[n_exc] = eb;

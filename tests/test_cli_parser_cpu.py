@@ -1,0 +1,112 @@
+"""CPU test of the host driver's block parser (`phage_filter parse`): FASTA/FASTQ, multi-line records, CRLF,
+blank lines, missing trailing newline, gzip, directories, tiny buffers that force refills and growth -- against
+the simple Python reader."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "phagefilter_b200", "bin", "phage_filter")
+
+
+def parse_cli(path, buf=1 << 20, chunk=1000, fmt=None):
+    args = [BIN, "parse", "-r", str(path), "--buf-bytes", str(buf), "--chunk", str(chunk)]
+    if fmt:
+        args += ["-F", fmt]
+    p = subprocess.run(args, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    out = []
+    for line in p.stdout.split(b"\n"):
+        if not line:
+            continue
+        rid, seq, qual = line.split(b"\t")
+        out.append((rid.decode(), seq, None if qual == b"-" else qual))
+    return out
+
+
+def want(path, fmt="auto"):
+    from phagefilter_b200.file_parser import read_records
+    return [(r.id, r.sequence, r.quality) for r in read_records(str(path), fmt)]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not os.path.exists(BIN):
+        pytest.skip("phage_filter binary not built")
+
+
+def test_fastq_variants(tmp_path):
+    rng = np.random.default_rng(0)
+    acgt = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    recs = []
+    for i in range(3000):
+        L = int(rng.choice([0, 1, 20, 100, 150, 151, 5000])) if i % 50 == 0 else 100
+        s = acgt[rng.integers(0, 5, size=L)].tobytes()
+        q = bytes(rng.integers(33, 74, size=L, dtype=np.uint8))  # may contain '@' and '+'
+        recs.append((f"read{i}", s, q))
+    p = tmp_path / "a.fq"
+    with open(p, "wb") as f:
+        for i, (rid, s, q) in enumerate(recs):
+            desc = b" extra words" if i % 3 == 0 else b""
+            f.write(b"@" + rid.encode() + desc + b"\n" + s + b"\n+" + (rid.encode() if i % 7 == 0 else b"") + b"\n" + q + b"\n")
+    got = parse_cli(p)
+    assert got == [(r, s, q) for r, s, q in recs]
+    for buf in (64, 300, 4096, 20000):  # refills, carry-over and buffer growth (a 5000-base record)
+        assert parse_cli(p, buf=buf, chunk=7) == got
+    # CRLF + blank lines + no trailing newline + gzip
+    p2 = tmp_path / "b.fastq.gz"
+    with gzip.open(p2, "wb") as f:
+        f.write(b"\r\n@x1 d\r\nACGT\r\n+\r\nIIII\r\n\r\n@x2\r\nGG\r\n+\r\n##")
+    assert parse_cli(p2) == [("x1", b"ACGT", b"IIII"), ("x2", b"GG", b"##")]
+    # multi-line FASTQ
+    p3 = tmp_path / "c.fq"
+    p3.write_bytes(b"@m1\nACGT\nTTGA\nC\n+\nIIII\nJJJJ\nK\n@m2\nAC\n+\n@@\n")
+    assert parse_cli(p3, buf=16) == [("m1", b"ACGTTTGAC", b"IIIIJJJJK"), ("m2", b"AC", b"@@")]
+
+
+def test_fasta_variants_and_directory(tmp_path):
+    rng = np.random.default_rng(1)
+    acgt = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    d = tmp_path / "reads"
+    d.mkdir()
+    all_recs = {}
+    for name, wrap, crlf in (("a.fa", 60, False), ("b.fasta", 0, True), ("c.fna.gz", 13, False)):
+        recs = []
+        for i in range(200):
+            L = int(rng.choice([0, 5, 59, 60, 61, 500, 3000]))
+            recs.append((f"{name}_{i}", acgt[rng.integers(0, 9, size=L)].tobytes()))
+        nl = b"\r\n" if crlf else b"\n"
+        blob = b""
+        for i, (rid, s) in enumerate(recs):
+            blob += b">" + rid.encode() + (b"\tdesc > with gt" if i % 5 == 0 else b"") + nl
+            if wrap:
+                for j in range(0, len(s), wrap):
+                    blob += s[j:j + wrap] + nl
+            else:
+                blob += s + nl
+            if i % 17 == 0:
+                blob += nl
+        if name.endswith(".gz"):
+            with gzip.open(d / name, "wb") as f:
+                f.write(blob.rstrip(b"\r\n"))  # no trailing newline
+        else:
+            (d / name).write_bytes(blob)
+        all_recs[name] = [(r, s, None) for r, s in recs]
+    (d / "notes.txt").write_text("ignored")
+    for name in all_recs:
+        for buf in (1 << 20, 97, 5000):
+            assert parse_cli(d / name, buf=buf, chunk=11) == all_recs[name], (name, buf)
+            assert want(d / name) == all_recs[name]
+    # directory: files are popped from the END of the sorted listing
+    got = parse_cli(d)
+    assert got == all_recs["c.fna.gz"] + all_recs["b.fasta"] + all_recs["a.fa"]
+
+
+def test_golden_reads_match_python_reader():
+    p = os.path.join(ROOT, "tests", "golden", "reads.fq")
+    assert parse_cli(p, buf=1000) == want(p)
+    g = os.path.join(ROOT, "tests", "golden", "genomes.fa")
+    assert parse_cli(g, buf=500) == want(g)
