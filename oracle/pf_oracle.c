@@ -477,13 +477,15 @@ static int is_leaf(const pfo_node *n) { return !n->left && !n->right; } /* bloom
 /* init_internal_node (bloom_tree.rs:226-246) */
 static pfo_node *init_internal_node(pfo_tree *t, pfo_node *current, pfo_node *new_node) {
     char name[64];
-    if (t->name_mode == 1) {
+    if (t->name_mode == 1 && t->name_counter < 65536) {
         uint16_t n2;
         do {
             n2 = (uint16_t)splitmix64(&t->name_state);
-        } while (t->name_used[n2] && t->name_counter < 65536);
+        } while (t->name_used[n2]);
         t->name_used[n2] = 1;
         snprintf(name, sizeof name, "Internal_Node_%u", (unsigned)n2);
+    } else if (t->name_mode == 1) {
+        snprintf(name, sizeof name, "Internal_Node_%llu", (unsigned long long)t->name_counter);
     } else {
         snprintf(name, sizeof name, "Internal_Node_%llu", (unsigned long long)t->name_counter);
     }

@@ -351,13 +351,17 @@ int pf_builder_insert(pf_builder *b, const char *id, const uint8_t *seq, uint64_
         } else if (cn.left < 0 && cn.right < 0) {
             // init_internal_node (bloom_tree.rs:226-246)
             char name[64];
-            if (b->name_mode == 1) {
+            if (b->name_mode == 1 && b->name_counter < 65536) {
+                // a random u16 like the reference (bloom_tree.rs:232-234), redrawn until unused; once all 65,536
+                // are taken the names continue above the u16 range instead of colliding
                 uint16_t n2;
                 do {
                     n2 = (uint16_t)splitmix64(b->name_state);
-                } while (b->name_used[n2] && b->name_counter < 65536);
+                } while (b->name_used[n2]);
                 b->name_used[n2] = 1;
                 snprintf(name, sizeof name, "Internal_Node_%u", (unsigned)n2);
+            } else if (b->name_mode == 1) {
+                snprintf(name, sizeof name, "Internal_Node_%llu", (unsigned long long)b->name_counter);
             } else {
                 snprintf(name, sizeof name, "Internal_Node_%llu", (unsigned long long)b->name_counter);
             }
