@@ -37,7 +37,7 @@ UNIT = "reads/s"
 K_MER, FPR, LARGEST, THETA = 20, 0.001, 1_000_000, 1.0
 N_FAMILIES, FAMILY_SIZE, READ_LEN = 10, 10, 150
 SEED_GENOMES, SEED_READS = 1001, 2001
-CPU_SAMPLE_READS = 200_000
+CPU_SAMPLE_READS = 1_000_000
 
 
 def workload_name(n_reads: int) -> str:

@@ -338,7 +338,7 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, uint
 // pair records and per-read / per-node metadata are fetched by PROBE_CHUNK lanes in parallel (two dependent
 // memory round trips per chunk instead of per pair) and broadcast with shuffles.
 template <int G, bool SMALL_M>
-__global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : 4)) probe_kernel(const ProbeArgs a) {
+__global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 4 : 3))) probe_kernel(const ProbeArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t probes = 0;
     unsigned long long probes_total = 0;

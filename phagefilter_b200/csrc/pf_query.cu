@@ -664,7 +664,7 @@ static uint32_t group_rounds_for(uint64_t max_kmers, bool small_m) {
     return (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (max_kmers + 31) / 32));
 }
 static void launch_probe(const ProbeArgs &a, uint32_t G, int sm_count, cudaStream_t s) {
-    const int g4 = sm_count * 4, g6 = sm_count * 6;
+    const int g3 = sm_count * 3, g4 = sm_count * 4, g6 = sm_count * 6;
     if (!a.hp.small_m) {
         probe_kernel<1, false><<<g6, PROBE_THREADS, 0, s>>>(a);
         return;
@@ -675,9 +675,9 @@ static void launch_probe(const ProbeArgs &a, uint32_t G, int sm_count, cudaStrea
         case 3: probe_kernel<3, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
         case 4: probe_kernel<4, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
         case 5: probe_kernel<5, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
-        case 6: probe_kernel<6, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
-        case 7: probe_kernel<7, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
-        default: probe_kernel<8, true><<<g4, PROBE_THREADS, 0, s>>>(a); break;
+        case 6: probe_kernel<6, true><<<g3, PROBE_THREADS, 0, s>>>(a); break;
+        case 7: probe_kernel<7, true><<<g3, PROBE_THREADS, 0, s>>>(a); break;
+        default: probe_kernel<8, true><<<g3, PROBE_THREADS, 0, s>>>(a); break;
     }
 }
 
