@@ -191,6 +191,48 @@ int pf_comm_init(pf_db *db, int nranks, int rank, const void *id128);
 int pf_allreduce_counts(pf_db *db);
 
 /* ------------------------------------------------------------------------------------------
+ * Subtree shards: trees larger than one GPU's HBM (BASELINE config 5 at the default geometry).
+ * The tree is cut at one level: the levels above it are replicated, every subtree rooted at the cut level
+ * is owned by one rank, and a rank keeps only the top's and its own subtrees' filters resident.  Queries
+ * are collective: the ranks' reads are gathered, every rank descends the top with its own reads, the
+ * surviving (read, node) pairs cross NVLink to the subtrees' owners in one all-to-all, and the (read, leaf)
+ * hits return to the reads' owners in a second one.  Leaf counters stay partial per rank until
+ * pf_allreduce_counts.  Results equal those of the replicated tree (same nodes see the same reads,
+ * query.rs:99-158).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pf_shard_info_t {
+    int32_t sharded, rank, nranks;
+    uint32_t cut_level;        /* levels < cut_level are replicated */
+    uint64_t top_nodes;        /* replicated nodes */
+    uint64_t owned_nodes;      /* nodes of this rank's subtrees */
+    uint64_t resident_filters; /* distinct .bf held in this rank's HBM */
+    uint64_t resident_bytes;
+} pf_shard_info_t;
+typedef struct pf_shard_stats_t {
+    uint64_t queries, collectives;
+    uint64_t reads_gathered;   /* reads of all ranks seen by this rank */
+    uint64_t pairs_top;        /* (read,node) pairs evaluated above the cut (own reads) */
+    uint64_t pairs_subtrees;   /* pairs evaluated in this rank's subtrees (reads of every rank) */
+    uint64_t pairs_sent, pairs_received; /* frontier exchange, excluding the rank's own slice */
+    uint64_t hits_sent;
+    uint64_t bytes_sent, bytes_received;
+} pf_shard_stats_t;
+/* Collective over `nranks` processes (one GPU each); id128 comes from pf_nccl_unique_id on rank 0.
+ * cut_level < 0: chosen to minimise the filters one rank holds. */
+int pf_db_open_sharded(const char *db_path, int device, int64_t search_depth, int nranks, int rank, const void *id128,
+                       int64_t cut_level, pf_db **out);
+int pf_shard_info(const pf_db *db, pf_shard_info_t *out);
+int pf_shard_stats(pf_db *db, pf_shard_stats_t *out);
+/* The partition alone, from tree.bin (host only, no GPU needed): owner_out[u] = -1 for replicated nodes, else
+ * the owning rank, nodes in level order. */
+int pf_shard_plan(const char *db_path, int64_t search_depth, int nranks, int64_t cut_level, uint32_t *cut_level_out,
+                  int32_t *owner_out, uint64_t owner_cap, uint64_t *n_nodes_out);
+/* query_batch (query.rs:66-82) on a sharded handle; every rank calls it with its own block of reads (possibly
+ * empty) and gets the hit lists of its own reads.  pf_query_block / pf_query_device refuse sharded handles. */
+int pf_query_sharded(pf_db *db, const pf_read_batch *in, float threshold, int want_hits, pf_hits *out);
+int pf_query_sharded_device(pf_db *db, pf_dev_batch *batch, float threshold, int want_hits, pf_hits *out);
+
+/* ------------------------------------------------------------------------------------------
  * Database builder on the GPU (the `build`/`add` side the query consumes):
  * BloomTree::new (bloom_tree.rs:100-119), ::insert (:128-145), ::save (:339-355).
  * Writes the reference's on-disk format (tree.bin + one .bf per node).

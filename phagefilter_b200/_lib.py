@@ -58,6 +58,17 @@ class Stats(C.Structure):
     ]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("sharded", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("cut_level", C.c_uint32),
+                ("top_nodes", C.c_uint64), ("owned_nodes", C.c_uint64), ("resident_filters", C.c_uint64),
+                ("resident_bytes", C.c_uint64)]
+
+
+class ShardStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("queries", "collectives", "reads_gathered", "pairs_top", "pairs_subtrees",
+                                          "pairs_sent", "pairs_received", "hits_sent", "bytes_sent", "bytes_received")]
+
+
 # every symbol include/pfgpu.h declares: (restype, argtypes)
 _VP = C.c_void_p
 SYMBOLS = {
@@ -93,6 +104,13 @@ SYMBOLS = {
     "pf_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "pf_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, C.c_char_p]),
     "pf_allreduce_counts": (C.c_int, [_VP]),
+    "pf_db_open_sharded": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_char_p, C.c_int64, C.POINTER(_VP)]),
+    "pf_shard_info": (C.c_int, [_VP, C.POINTER(ShardInfo)]),
+    "pf_shard_stats": (C.c_int, [_VP, C.POINTER(ShardStats)]),
+    "pf_shard_plan": (C.c_int, [C.c_char_p, C.c_int64, C.c_int, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32),
+                                C.c_uint64, C.POINTER(C.c_uint64)]),
+    "pf_query_sharded": (C.c_int, [_VP, C.POINTER(ReadBatch), C.c_float, C.c_int, C.POINTER(Hits)]),
+    "pf_query_sharded_device": (C.c_int, [_VP, _VP, C.c_float, C.c_int, C.POINTER(Hits)]),
     "pf_builder_create": (C.c_int, [C.c_uint64, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                     C.c_uint64, C.POINTER(_VP)]),
     "pf_builder_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_VP)]),

@@ -29,6 +29,35 @@ class BloomTree:
         """bloom_tree.rs:364-386"""
         return cls(directory, device)
 
+    @classmethod
+    def open_sharded(cls, directory: str, device: int, rank: int, nranks: int, nccl_id: bytes,
+                     search_depth: Optional[int] = None, cut_level: Optional[int] = None) -> "BloomTree":
+        """Subtree-sharded tree for databases larger than one GPU's HBM (pf_db_open_sharded): collective over
+        `nranks` processes; levels above the cut are replicated, each subtree below it lives on one rank."""
+        self = cls.__new__(cls)
+        self.directory, self.device = directory, device
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().pf_db_open_sharded(directory.encode(), device, -1 if search_depth is None else search_depth,
+                                                 nranks, rank, nccl_id, -1 if cut_level is None else cut_level,
+                                                 C.byref(self._h)))
+        self._info = _lib.DbInfo()
+        _lib.check(_lib.lib().pf_db_info(self._h, C.byref(self._info)))
+        return self
+
+    def shard_info(self) -> _lib.ShardInfo:
+        o = _lib.ShardInfo()
+        _lib.check(_lib.lib().pf_shard_info(self._h, C.byref(o)))
+        return o
+
+    def shard_stats(self) -> _lib.ShardStats:
+        o = _lib.ShardStats()
+        _lib.check(_lib.lib().pf_shard_stats(self._h, C.byref(o)))
+        return o
+
+    def allreduce_counts(self) -> None:
+        """ONE ncclAllReduce(sum) of the per-leaf counters over the handle's communicator."""
+        _lib.check(_lib.lib().pf_allreduce_counts(self._h))
+
     def prune_tree(self, search_depth: int) -> None:
         """bloom_tree.rs:302-330: nodes at depth >= search_depth become leaves.  Counters restart,
         as in the reference where pruning happens before the first query (main.rs:293-299)."""

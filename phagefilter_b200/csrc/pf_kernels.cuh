@@ -45,6 +45,7 @@ struct HashArgs {
     uint32_t read0, n_reads;    // reads [read0, read0 + n_reads) of the batch
     uint32_t k;
     unsigned int *work_ctr;
+    const uint8_t *flags;       // optional [batch reads]: only reads with a non-zero flag are hashed
 };
 
 struct ByteSrc {
@@ -61,7 +62,7 @@ PF_D uint8_t src_byte(const ByteSrc &s, uint32_t j) {
 // KM in 17..32: 2-bit register path for reads of pure upper-case ACGT; KM == 0: byte path for every read.
 // Exception reads (any other byte) always take the byte path, which is what the reference hashes.
 template <int KM>
-__global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArgs a) {
+static __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t M0 = (uint32_t)a.hp.M, M1 = (uint32_t)(a.hp.M >> 32), m32 = (uint32_t)a.hp.m;
     for (;;) {
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArgs a) {
         const uint32_t i1 = min(i0 + 4u, a.n_reads);
         for (uint32_t i = i0; i < i1; ++i) {
             const uint32_t r = a.read0 + i;
+            if (a.flags && !a.flags[r]) continue;
             const uint32_t n_k = kmers_of(ldg32(a.lengths + r), a.k);
             if (n_k == 0) continue;
             const uint64_t kofs = __ldg(a.kmer_off + r) - a.kmer_base;
@@ -338,7 +340,7 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, uint
 // pair records and per-read / per-node metadata are fetched by PROBE_CHUNK lanes in parallel (two dependent
 // memory round trips per chunk instead of per pair) and broadcast with shuffles.
 template <int G, bool SMALL_M>
-__global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 4 : 3))) probe_kernel(const ProbeArgs a) {
+static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 4 : 3))) probe_kernel(const ProbeArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t probes = 0;
     unsigned long long probes_total = 0;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 4 : 3))
 // Appends (read, entry node) pairs for every read of the chunk and every entry node of this level, node-major.
 // Entry nodes are the first nodes below the root that are actually tested (the root itself unless the plan
 // skips it): the skipped region above them never enters the frontier.
-__global__ void inject_frontier_kernel(uint32_t *fr_read, uint32_t *fr_node, uint32_t read0, uint32_t n_reads,
+static __global__ void inject_frontier_kernel(uint32_t *fr_read, uint32_t *fr_node, uint32_t read0, uint32_t n_reads,
                                        const uint32_t *__restrict__ entry, uint32_t n_entry) {
     const uint64_t total = (uint64_t)n_reads * n_entry;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -404,7 +406,7 @@ struct LevelTotals {
 // gives every child its slice of the next frontier (children are numbered level-order, left before
 // right, so the slices are node-major) and every leaf its slice of the hit list; leaf counts are added
 // to the block histogram.
-__global__ void level_scan_kernel(uint32_t lo, uint32_t hi, const uint32_t *__restrict__ node_pass,
+static __global__ void level_scan_kernel(uint32_t lo, uint32_t hi, const uint32_t *__restrict__ node_pass,
                                   const uint32_t *__restrict__ left, const uint32_t *__restrict__ right,
                                   const int32_t *__restrict__ leaf, unsigned long long *next_base,
                                   unsigned long long *hit_base, unsigned long long *blk_counts, LevelTotals *totals,
@@ -453,7 +455,7 @@ __global__ void level_scan_kernel(uint32_t lo, uint32_t hi, const uint32_t *__re
 
 // Thread per pair: survivors take a rank inside their node (warp-aggregated atomic) and are written
 // to both children's slices, or to the hit list when the node is a leaf.
-__global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, const uint32_t *__restrict__ fr_node,
+static __global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, const uint32_t *__restrict__ fr_node,
                                const uint8_t *__restrict__ pass, uint32_t n, const uint32_t *__restrict__ node_pass,
                                uint32_t *cursor, const uint32_t *__restrict__ left, const uint32_t *__restrict__ right,
                                const int32_t *__restrict__ leaf, const unsigned long long *__restrict__ next_base,
@@ -477,7 +479,9 @@ __global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, const uint3
             const unsigned long long p = hit_base[u] + rank;
             hit_read[p] = r;
             hit_leaf[p] = (uint32_t)lf;
-            atomicAdd(read_hits + r, 1u);  // per-read hit count for the CSR built at the end of the block
+            // per-read hit count for the CSR built at the end of the block; mode 2 (subtree shards: the hit is
+            // still to be routed to the rank that owns the read) leaves the counting to the receiver
+            if (want_hits == 1) atomicAdd(read_hits + r, 1u);
         }
     } else {
         unsigned long long p = next_base[u] + rank;
@@ -497,7 +501,7 @@ __global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, const uint3
 
 // ---- load-time analysis of the tree --------------------------------------------------------------
 // pop[slot] += popcount(filter[slot]); grid = (blocks, n_slots_in_chunk)
-__global__ void fill_kernel(const uint64_t *__restrict__ filters, uint64_t wpf, uint32_t slot0, unsigned long long *pop) {
+static __global__ void fill_kernel(const uint64_t *__restrict__ filters, uint64_t wpf, uint32_t slot0, unsigned long long *pop) {
     const uint32_t slot = slot0 + blockIdx.y;
     const uint64_t *f = filters + (uint64_t)slot * wpf;
     unsigned long long c = 0;
@@ -507,7 +511,7 @@ __global__ void fill_kernel(const uint64_t *__restrict__ filters, uint64_t wpf, 
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(pop + slot, c);
 }
 // viol[u] += popcount(filter(child) & ~filter(u)) over both children; grid = (blocks, nodes_in_chunk)
-__global__ void subset_kernel(const uint64_t *__restrict__ filters, uint64_t wpf, const uint32_t *__restrict__ slot,
+static __global__ void subset_kernel(const uint64_t *__restrict__ filters, uint64_t wpf, const uint32_t *__restrict__ slot,
                               const uint32_t *__restrict__ left, const uint32_t *__restrict__ right, uint32_t node0,
                               unsigned long long *viol) {
     const uint32_t u = node0 + blockIdx.y;
@@ -527,7 +531,7 @@ __global__ void subset_kernel(const uint64_t *__restrict__ filters, uint64_t wpf
 }
 
 // k-mer count per read (file_parser.rs:136-139); its exclusive scan (csr_* kernels below) is kmer_off
-__global__ void kmer_counts_kernel(const uint32_t *__restrict__ lengths, uint32_t n, uint32_t k, uint32_t *cnt) {
+static __global__ void kmer_counts_kernel(const uint32_t *__restrict__ lengths, uint32_t n, uint32_t k, uint32_t *cnt) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) cnt[i] = kmers_of(lengths[i], k);
 }
@@ -535,7 +539,7 @@ __global__ void kmer_counts_kernel(const uint32_t *__restrict__ lengths, uint32_
 // ---- per-read hit lists (ResultMap, result_map.rs:9-46) as CSR, built on the device ------------------
 // exclusive scan of cnt[0..n) into off[0..n] (u64), 1024 elements per block: block sums, scan of the sums,
 // then the in-block scan with the block's base.
-__global__ void csr_block_sums_kernel(const uint32_t *__restrict__ cnt, uint32_t n, unsigned long long *bsum) {
+static __global__ void csr_block_sums_kernel(const uint32_t *__restrict__ cnt, uint32_t n, unsigned long long *bsum) {
     __shared__ unsigned long long s[32];
     const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
     unsigned long long v = i < n ? cnt[i] : 0;
@@ -548,7 +552,7 @@ __global__ void csr_block_sums_kernel(const uint32_t *__restrict__ cnt, uint32_t
         if (threadIdx.x == 0) bsum[blockIdx.x] = v;
     }
 }
-__global__ void csr_scan_sums_kernel(unsigned long long *bsum, uint32_t nb) {  // one block, in place, exclusive
+static __global__ void csr_scan_sums_kernel(unsigned long long *bsum, uint32_t nb) {  // one block, in place, exclusive
     __shared__ unsigned long long s[1024];
     const uint32_t t = threadIdx.x, per = (nb + 1023u) / 1024u;
     const uint32_t b = min(nb, t * per), e = min(nb, (t + 1) * per);
@@ -572,7 +576,7 @@ __global__ void csr_scan_sums_kernel(unsigned long long *bsum, uint32_t nb) {  /
         a += x;
     }
 }
-__global__ void csr_offsets_kernel(const uint32_t *__restrict__ cnt, uint32_t n, const unsigned long long *__restrict__ bsum,
+static __global__ void csr_offsets_kernel(const uint32_t *__restrict__ cnt, uint32_t n, const unsigned long long *__restrict__ bsum,
                                    unsigned long long *off) {
     __shared__ unsigned long long s[32];
     const uint32_t i = blockIdx.x * 1024u + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -598,7 +602,7 @@ __global__ void csr_offsets_kernel(const uint32_t *__restrict__ cnt, uint32_t n,
     if (i == n - 1) off[n] = excl + c;
 }
 // place every hit in its read's segment (any order), then sort each segment ascending by DFS leaf index
-__global__ void csr_fill_kernel(const uint32_t *__restrict__ hit_read, const uint32_t *__restrict__ hit_leaf,
+static __global__ void csr_fill_kernel(const uint32_t *__restrict__ hit_read, const uint32_t *__restrict__ hit_leaf,
                                 unsigned long long n_hits, const unsigned long long *__restrict__ off, uint32_t *cnt,
                                 uint32_t *out_leaf) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -607,7 +611,7 @@ __global__ void csr_fill_kernel(const uint32_t *__restrict__ hit_read, const uin
     const uint32_t k = atomicSub(cnt + r, 1u) - 1u;
     out_leaf[off[r] + k] = hit_leaf[i];
 }
-__global__ void csr_sort_kernel(const unsigned long long *__restrict__ off, uint32_t n, uint32_t *out_leaf) {
+static __global__ void csr_sort_kernel(const unsigned long long *__restrict__ off, uint32_t n, uint32_t *out_leaf) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const unsigned long long b = off[r], e = off[r + 1];
@@ -622,7 +626,7 @@ __global__ void csr_sort_kernel(const unsigned long long *__restrict__ off, uint
     }
 }
 
-__global__ void add_counts_kernel(unsigned long long *dst, const unsigned long long *src, uint32_t n) {
+static __global__ void add_counts_kernel(unsigned long long *dst, const unsigned long long *src, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] += src[i];
 }

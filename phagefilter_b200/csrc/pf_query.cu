@@ -6,17 +6,11 @@
 //   query::query_batch / _query_batch   query.rs:66-158
 //   query::save_leaf_counts             query.rs:173-218
 #include <dlfcn.h>
-#include <nccl.h>
 
-#include <algorithm>
 #include <cstring>
 #include <map>
-#include <string>
-#include <vector>
 
-#include "pf_common.h"
-#include "pf_format.h"
-#include "pf_kernels.cuh"
+#include "pf_db.h"
 
 namespace pf {
 
@@ -30,84 +24,6 @@ void set_error(const char *fmt, ...) {
     g_error = buf;
 }
 
-template <class T>
-struct DevBuf {  // grow-only device array
-    T *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t n) {
-        if (n <= cap) return PF_OK;
-        size_t want = std::max(n, cap + cap / 2);
-        T *q = nullptr;
-        cudaError_t e = cudaMalloc(&q, want * sizeof(T));
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            // retry with the exact size before giving up
-            want = n;
-            e = cudaMalloc(&q, want * sizeof(T));
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                set_error("device allocation of %zu bytes failed (frontier too large: use smaller read blocks)",
-                          want * sizeof(T));
-                return PF_ERR_NOMEM;
-            }
-        }
-        if (p) cudaFree(p);
-        p = q;
-        cap = want;
-        return PF_OK;
-    }
-    // grow while preserving the first `keep` elements (hit lists accumulate across levels)
-    int grow_keep(size_t n, size_t keep, cudaStream_t s) {
-        if (n <= cap) return PF_OK;
-        T *old = p;
-        p = nullptr;
-        size_t old_cap = cap;
-        cap = 0;
-        int rc = ensure(std::max(n, old_cap + old_cap / 2));
-        if (rc != PF_OK) {
-            p = old;
-            cap = old_cap;
-            return rc;
-        }
-        if (old && keep) cudaMemcpyAsync(p, old, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
-        if (old) {
-            cudaStreamSynchronize(s);
-            cudaFree(old);
-        }
-        return PF_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-template <class T>
-struct PinnedBuf {  // grow-only pinned host array
-    T *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t n) {
-        if (n <= cap) return PF_OK;
-        const size_t want = std::max(n, cap + cap / 2);
-        T *q = nullptr;
-        if (cudaMallocHost(&q, want * sizeof(T)) != cudaSuccess) {
-            cudaGetLastError();
-            set_error("pinned host allocation of %zu bytes failed", want * sizeof(T));
-            return PF_ERR_NOMEM;
-        }
-        if (p) cudaFreeHost(p);
-        p = q;
-        cap = want;
-        return PF_OK;
-    }
-    void release() {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
 // pf_build.cu
 int build_leaf_filter(const uint8_t *h_seq, uint64_t len, const HashParams &hp, uint64_t *d_filter, uint64_t wpf,
                       cudaStream_t s);
@@ -117,45 +33,10 @@ int filters_equal(const uint64_t *a, const uint64_t *b, uint64_t n_words, cudaSt
 
 using namespace pf;
 
-struct pf_dev_batch {
-    uint32_t n_reads = 0, n_exc = 0;
-    uint64_t n_words = 0, exc_nbytes = 0;
-    DevBuf<uint32_t> lengths, packed, exc_index;
-    DevBuf<uint64_t> word_off, exc_off, kmer_off;
-    DevBuf<uint32_t> kcnt;                 // scratch of the device-side k-mer prefix sum
-    DevBuf<unsigned long long> kbsum;
-    DevBuf<uint8_t> exc_bytes;
-    std::vector<uint64_t> h_kmer_off;  // [n_reads + 1] prefix sum of k-mer counts (host copy for chunking)
-    cudaEvent_t ready = nullptr;       // recorded after the H2D copies of an asynchronous upload
-    uint64_t kmer_size = 0, max_kmers = 0;
-    uint64_t total_bases_bound = 0;  // upper bound on the batch's k-mers when the prefix sum is device-only
-    uint64_t nominal_kmers = 1;      // k-mers of a read of mean length: what the step plan is made for
-    uint64_t bytes = 0;
-    void release() {
-        lengths.release();
-        packed.release();
-        exc_index.release();
-        word_off.release();
-        kmer_off.release();
-        kcnt.release();
-        kbsum.release();
-        exc_off.release();
-        exc_bytes.release();
-        if (ready) cudaEventDestroy(ready);
-        ready = nullptr;
-    }
-};
-
-struct NcclApi {
-    void *h = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    const char *(*GetErrorString)(ncclResult_t) = nullptr;
-};
-static NcclApi g_nccl;
-static int load_nccl() {
+namespace pf {
+NcclApi g_nccl;
+}
+int pf::load_nccl() {
     if (g_nccl.h) return PF_OK;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     void *h = nullptr;
@@ -171,8 +52,15 @@ static int load_nccl() {
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
+    g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(h, "ncclBroadcast");
+    g_nccl.Send = (decltype(g_nccl.Send))dlsym(h, "ncclSend");
+    g_nccl.Recv = (decltype(g_nccl.Recv))dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.AllGather ||
+        !g_nccl.Broadcast || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
         set_error("NCCL symbols missing");
         return PF_ERR_NCCL;
     }
@@ -180,67 +68,10 @@ static int load_nccl() {
     return PF_OK;
 }
 
-struct pf_db {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // H2D of the next batch overlaps the query of the current one
-    int sm_count = 148;
-    // host copy of the flattened tree (level order)
-    HostTree tree;
-    std::vector<uint32_t> h_left, h_right, h_slot;
-    std::vector<int32_t> h_leaf;
-    std::vector<int32_t> h_pre;         // level-order id -> index into tree.nodes
-    std::vector<uint32_t> level_start;  // n_levels + 1
-    std::vector<std::string> leaf_ids;  // DFS leaf order
-    uint64_t n_nodes = 0, n_leaves = 0, n_slots = 0, wpf = 0;
-    BfHeader geom;
-    HashParams hp{};
-    int exhaustive = 0;
-    int lazy = 1;                      // step-limited pre-test at verified-monotone interior nodes
-    std::vector<uint64_t> h_pop;       // set bits of each node's filter
-    std::vector<uint8_t> h_mono;       // interior node whose filter contains both children's filters
-    std::vector<uint32_t> h_steps;     // probe steps per node for the current (threshold, mode)
-    uint32_t *d_steps = nullptr;
-    std::vector<uint32_t> h_entry;        // entry nodes of the current plan, ordered by level
-    std::vector<uint32_t> entry_start;    // [n_levels + 1] offsets into h_entry per level
-    uint32_t *d_entry = nullptr;
-    float steps_theta = -1.f;
-    uint64_t steps_n = 0;  // nominal k-mers per read the plan was made for
-    int steps_mode = -1;
-    uint64_t n_internal = 0, n_monotone = 0;
-    // device tree
-    uint32_t *d_left = nullptr, *d_right = nullptr, *d_slot = nullptr;
-    int32_t *d_leaf = nullptr;
-    uint64_t *d_filters = nullptr;
-    // accumulators and per-block scratch
-    unsigned long long *d_counts = nullptr, *d_blk_counts = nullptr;
-    uint32_t *d_node_pass = nullptr, *d_cursor = nullptr;  // contiguous [2 * n_nodes]
-    unsigned long long *d_next_base = nullptr, *d_hit_base = nullptr;
-    unsigned int *d_work = nullptr;  // one counter per level
-    unsigned long long *d_probes = nullptr;
-    LevelTotals *d_totals = nullptr, *h_totals = nullptr;
-    DevBuf<uint32_t> fr_read[2], fr_node[2], hit_read, hit_leaf;
-    DevBuf<uint8_t> pass;
-    DevBuf<uint64_t> hb;                       // cached hash_bytes per k-mer of the current chunk
-    DevBuf<uint32_t> idx0;                     // cached step-0 bit index per k-mer (m < 2^31)
-    uint64_t hash_cache_bytes = 16ULL << 30;   // chunk reads so the cache stays below this
-    pf_dev_batch own_batch;  // device copy used by pf_query_block
-    // outputs: per-read hit lists as CSR, built on the device, returned through pinned host arrays
-    DevBuf<uint32_t> read_hits, csr_leaf;
-    DevBuf<unsigned long long> csr_off, csr_bsum;
-    PinnedBuf<uint64_t> pin_off;
-    PinnedBuf<uint32_t> pin_leaf;
-    std::vector<uint64_t> out_off;
-    // timing
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    std::vector<cudaEvent_t> ev_probe;  // 2 per level
-    pf_stats_t stats{};
-    ncclComm_t comm = nullptr;
-};
-
-static void db_free(pf_db *db) {
+void pf::db_free(pf_db *db) {
     if (!db) return;
     cudaSetDevice(db->device);
+    shard_free(db);
     if (db->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(db->comm);
     cudaFree(db->d_left);
     cudaFree(db->d_right);
@@ -283,7 +114,7 @@ static void db_free(pf_db *db) {
 }
 
 // prune_tree (bloom_tree.rs:302-330) + level-order flattening + DFS leaf numbering.
-static void flatten(pf_db *db, int64_t search_depth) {
+void pf::flatten(pf_db *db, int64_t search_depth) {
     const HostTree &t = db->tree;
     db->h_left.clear();
     db->h_right.clear();
@@ -366,7 +197,7 @@ static int upload(T **dst, const std::vector<T> &v, cudaStream_t s) {
 
 static int analyse_tree(pf_db *db);
 
-static int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
+int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -381,6 +212,10 @@ static int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     PF_CUDA_OK(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
     PF_CUDA_OK(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
     PF_CUDA_OK(cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, db->device));
+    if (db->sharded) {  // the load-time analysis of a sharded tree ends in an all-reduce
+        int crc = comm_init_impl(db, db->nranks, db->rank, db->nccl_id.data());
+        if (crc != PF_OK) return crc;
+    }
     std::string err;
     std::string dir(db_path);
     if (!read_tree_bin(join_path(dir, "tree.bin"), db->tree, err)) {
@@ -392,9 +227,15 @@ static int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
         set_error("database has no root node (reference panics in save_leaf_counts, main.rs:374)");
         return PF_ERR_FORMAT;
     }
+    db->h_owner.assign(db->n_nodes, -1);
+    if (db->sharded) {  // subtree shards: choose the cut, the owners, and keep only top + owned filters resident
+        int prc = shard_plan(db, db->cut_level_req);
+        if (prc != PF_OK) return prc;
+    }
     // decode every distinct filter once; geometry must be uniform
     std::vector<std::string> slot_path(db->n_slots);
-    for (size_t q = 0; q < db->n_nodes; ++q) slot_path[db->h_slot[q]] = db->tree.nodes[db->h_pre[q]].bf_path;
+    for (size_t q = 0; q < db->n_nodes; ++q)
+        if (db->h_slot[q] != NONE32) slot_path[db->h_slot[q]] = db->tree.nodes[db->h_pre[q]].bf_path;
     uint64_t *stage[2] = {nullptr, nullptr};
     cudaEvent_t staged[2] = {nullptr, nullptr};
     BfHeader first{};
@@ -480,11 +321,28 @@ static int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
 // the superset property, and such nodes stay exact.
 static int analyse_tree(pf_db *db) {
     const size_t nn = db->n_nodes;
-    unsigned long long *d_pop = nullptr, *d_viol = nullptr;
+    // Who measures what.  Replicated tree: this rank measures everything.  Subtree shards: a node's fill is
+    // measured by its owner (rank 0 for the replicated top), a (node, child) superset check by the child's owner
+    // (which also holds the parent); one all-reduce(sum) then gives every rank the same global tables, so every
+    // rank derives the same step plan.
+    auto mine = [&](uint32_t u) {
+        const int32_t o = db->h_owner[u];
+        return o == db->rank || (o < 0 && db->rank == 0);
+    };
+    std::vector<uint32_t> chk_left(nn, NONE32), chk_right(nn, NONE32);
+    for (size_t u = 0; u < nn; ++u) {
+        if (db->h_left[u] != NONE32 && mine(db->h_left[u])) chk_left[u] = db->h_left[u];
+        if (db->h_right[u] != NONE32 && mine(db->h_right[u])) chk_right[u] = db->h_right[u];
+    }
+    unsigned long long *d_pop = nullptr, *d_nodeinfo = nullptr;  // d_nodeinfo: [0,nn) violations, [nn,2nn) fill
+    uint32_t *d_chk = nullptr;
     PF_CUDA_OK(cudaMalloc(&d_pop, std::max<size_t>(db->n_slots, 1) * 8));
-    PF_CUDA_OK(cudaMalloc(&d_viol, nn * 8));
+    PF_CUDA_OK(cudaMalloc(&d_nodeinfo, 2 * nn * 8));
+    PF_CUDA_OK(cudaMalloc(&d_chk, 2 * nn * 4));
     PF_CUDA_OK(cudaMemsetAsync(d_pop, 0, std::max<size_t>(db->n_slots, 1) * 8, db->stream));
-    PF_CUDA_OK(cudaMemsetAsync(d_viol, 0, nn * 8, db->stream));
+    PF_CUDA_OK(cudaMemsetAsync(d_nodeinfo, 0, 2 * nn * 8, db->stream));
+    PF_CUDA_OK(cudaMemcpyAsync(d_chk, chk_left.data(), nn * 4, cudaMemcpyHostToDevice, db->stream));
+    PF_CUDA_OK(cudaMemcpyAsync(d_chk + nn, chk_right.data(), nn * 4, cudaMemcpyHostToDevice, db->stream));
     const uint32_t bx = (uint32_t)std::min<uint64_t>((db->wpf + 1023) / 1024, 64);
     for (uint64_t s0 = 0; s0 < db->n_slots; s0 += 65535) {
         const uint32_t ny = (uint32_t)std::min<uint64_t>(65535, db->n_slots - s0);
@@ -492,25 +350,41 @@ static int analyse_tree(pf_db *db) {
     }
     for (uint64_t u0 = 0; u0 < nn; u0 += 65535) {
         const uint32_t ny = (uint32_t)std::min<uint64_t>(65535, nn - u0);
-        subset_kernel<<<dim3(bx, ny), 256, 0, db->stream>>>(db->d_filters, db->wpf, db->d_slot, db->d_left, db->d_right,
-                                                           (uint32_t)u0, d_viol);
+        subset_kernel<<<dim3(bx, ny), 256, 0, db->stream>>>(db->d_filters, db->wpf, db->d_slot, d_chk, d_chk + nn,
+                                                           (uint32_t)u0, d_nodeinfo);
     }
-    std::vector<unsigned long long> pop(std::max<size_t>(db->n_slots, 1)), viol(nn);
+    std::vector<unsigned long long> pop(std::max<size_t>(db->n_slots, 1)), info(2 * nn, 0);
     cudaMemcpyAsync(pop.data(), d_pop, db->n_slots * 8, cudaMemcpyDeviceToHost, db->stream);
-    cudaMemcpyAsync(viol.data(), d_viol, nn * 8, cudaMemcpyDeviceToHost, db->stream);
     cudaError_t e = cudaStreamSynchronize(db->stream);
+    if (e == cudaSuccess && db->sharded) {
+        for (size_t u = 0; u < nn; ++u) info[nn + u] = mine((uint32_t)u) ? pop[db->h_slot[u]] : 0;
+        cudaMemcpyAsync(d_nodeinfo + nn, info.data() + nn, nn * 8, cudaMemcpyHostToDevice, db->stream);
+        ncclResult_t r = g_nccl.AllReduce(d_nodeinfo, d_nodeinfo, 2 * nn, ncclUint64, ncclSum, db->comm, db->stream);
+        if (r != ncclSuccess) {
+            cudaFree(d_pop);
+            cudaFree(d_nodeinfo);
+            cudaFree(d_chk);
+            set_error("ncclAllReduce (tree analysis): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+            return PF_ERR_NCCL;
+        }
+    }
+    if (e == cudaSuccess) {
+        cudaMemcpyAsync(info.data(), d_nodeinfo, 2 * nn * 8, cudaMemcpyDeviceToHost, db->stream);
+        e = cudaStreamSynchronize(db->stream);
+    }
     cudaFree(d_pop);
-    cudaFree(d_viol);
+    cudaFree(d_nodeinfo);
+    cudaFree(d_chk);
     PF_CUDA_OK(e);
     PF_CUDA_OK(cudaGetLastError());
     db->h_pop.resize(nn);
     db->h_mono.assign(nn, 0);
     db->n_internal = db->n_monotone = 0;
     for (size_t u = 0; u < nn; ++u) {
-        db->h_pop[u] = pop[db->h_slot[u]];
+        db->h_pop[u] = db->sharded ? info[nn + u] : pop[db->h_slot[u]];
         if (db->h_leaf[u] >= 0) continue;
         db->n_internal++;
-        db->h_mono[u] = viol[u] == 0;
+        db->h_mono[u] = info[u] == 0;
         db->n_monotone += db->h_mono[u];
     }
     return PF_OK;
@@ -601,7 +475,7 @@ static void plan_steps(pf_db *db, float threshold, uint64_t n_nominal, std::vect
         }
     }
 }
-static int update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
+int pf::update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
     const int mode = db->exhaustive ? 2 : (db->lazy ? 1 : 0);
     if (mode == db->steps_mode && (mode != 1 || (threshold == db->steps_theta && n_nominal == db->steps_n))) return PF_OK;
     const uint32_t K = db->geom.num_hashes;
@@ -621,6 +495,14 @@ static int update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
             } else {
                 db->h_entry.push_back(u);
             }
+        }
+        // subtree shards: below the cut only the owner of a subtree injects at its entry nodes (for the reads of
+        // every rank); above the cut each rank injects its own reads
+        if (db->sharded) {
+            size_t w = 0;
+            for (uint32_t u : db->h_entry)
+                if (db->h_owner[u] < 0 || db->h_owner[u] == db->rank) db->h_entry[w++] = u;
+            db->h_entry.resize(w);
         }
         std::sort(db->h_entry.begin(), db->h_entry.end());
     }
@@ -645,7 +527,7 @@ template <int KM>
 static void launch_hash_k(const HashArgs &a, int grid, cudaStream_t s) {
     hash_kernel<KM><<<grid, HASH_THREADS, 0, s>>>(a);
 }
-static void launch_hash(const HashArgs &a, int grid, cudaStream_t s) {
+void pf::launch_hash(const HashArgs &a, int grid, cudaStream_t s) {
     switch (a.k) {
 #define PF_CASE(K) \
     case K:        \
@@ -659,7 +541,7 @@ static void launch_hash(const HashArgs &a, int grid, cudaStream_t s) {
     }
 }
 // Rounds of 32 k-mers a lane owns at once: enough to cover the longest read of the batch, at most 8.
-static uint32_t group_rounds_for(uint64_t max_kmers, bool small_m) {
+uint32_t pf::group_rounds_for(uint64_t max_kmers, bool small_m) {
     if (!small_m) return 1;  // 64-bit remainder path (m >= 2^31): kept simple
     return (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (max_kmers + 31) / 32));
 }
@@ -690,6 +572,152 @@ static int ensure_events(pf_db *db, size_t n) {
     return PF_OK;
 }
 
+// Event times and work counters of one finished query call (after the final stream synchronize).
+void pf::account_stats(pf_db *db, const Descent &st, uint64_t n_reads, uint64_t d2h) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, db->ev_begin, db->ev_end);
+    db->stats.device_ms += ms;
+    for (size_t e = 0; e + 1 < st.n_ev; e += 2) {
+        float pm = 0.f;
+        cudaEventElapsedTime(&pm, db->ev_probe[e], db->ev_probe[e + 1]);
+        db->stats.probe_kernel_ms += pm;
+    }
+    db->stats.blocks++;
+    db->stats.reads += n_reads;
+    db->stats.pairs += st.pairs;
+    db->stats.probes_issued += st.probes;
+    db->stats.levels += st.levels;
+    db->stats.probe_launches += st.probe_launches;
+    db->stats.other_launches += st.other_launches;
+    db->stats.d2h_bytes += d2h;
+}
+
+// Levels [l_begin, l_end) of the level-synchronous descent over the frontier held in `st` (query.rs:99-158):
+// per level  [inject entry nodes] -> probe -> scan -> 32-byte D2H of the totals -> scatter.
+int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint32_t G, uint64_t kmer_base,
+                   size_t l_begin, size_t l_end, uint32_t inj_r0, uint32_t inj_n, Descent &st) {
+    cudaStream_t s = db->stream;
+    int rc;
+    const size_t last_entry_level = [&] {
+        size_t l = l_begin;
+        for (size_t i = l_begin; i < l_end; ++i)
+            if (db->entry_start[i + 1] > db->entry_start[i]) l = i;
+        return l;
+    }();
+    for (size_t l = l_begin; l < l_end && (st.n > 0 || l <= last_entry_level); ++l) {
+        const int cur = st.cur;
+        uint64_t n = st.n;
+        // entry nodes of this level: append (read, node) pairs for every read of the injected range
+        const uint32_t e0 = db->entry_start[l], n_entry = db->entry_start[l + 1] - e0;
+        if (n_entry && inj_n) {
+            const uint64_t add = (uint64_t)inj_n * n_entry;
+            if (n + add > 0xFFFFFFF0ULL) {
+                set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
+                          (unsigned long long)(n + add));
+                return PF_ERR_NOMEM;
+            }
+            if ((rc = db->fr_read[cur].grow_keep(n + add, n, s)) || (rc = db->fr_node[cur].grow_keep(n + add, n, s)))
+                return rc;
+            inject_frontier_kernel<<<(uint32_t)std::min<uint64_t>((add + 255) / 256, 8192), 256, 0, s>>>(
+                db->fr_read[cur].p + n, db->fr_node[cur].p + n, inj_r0, inj_n, db->d_entry + e0, n_entry);
+            st.other_launches++;
+            n += add;
+            st.n = n;
+        }
+        if (n == 0) continue;
+        if ((rc = db->pass.ensure(n))) return rc;
+        ProbeArgs a{};
+        a.fr_read = db->fr_read[cur].p;
+        a.fr_node = db->fr_node[cur].p;
+        a.n_pairs = (uint32_t)n;
+        a.lengths = bt->lengths.p;
+        a.kmer_off = bt->kmer_off.p;
+        a.hb = db->hb.p;
+        a.idx0 = db->idx0.p;
+        a.kmer_base = kmer_base;
+        a.node_slot = db->d_slot;
+        a.node_steps = db->d_steps;
+        a.filters = db->d_filters;
+        a.words_per_filter = db->wpf;
+        a.pass = db->pass.p;
+        a.node_pass = db->d_node_pass;
+        a.work_ctr = db->d_work + l;
+        a.probes = db->d_probes;
+        a.hp = db->hp;
+        a.threshold = threshold;
+        a.exhaustive = db->exhaustive;
+        if ((rc = ensure_events(db, st.n_ev + 2))) return rc;
+        PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev], s));
+        launch_probe(a, G, db->sm_count, s);
+        PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev + 1], s));
+        st.n_ev += 2;
+        st.probe_launches++;
+        st.pairs += n;
+        st.levels++;
+        level_scan_kernel<<<1, 1024, 0, s>>>(db->level_start[l], db->level_start[l + 1], db->d_node_pass, db->d_left,
+                                             db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base,
+                                             db->d_blk_counts, db->d_totals, db->d_probes);
+        st.other_launches++;
+        PF_CUDA_OK(cudaMemcpyAsync(db->h_totals, db->d_totals, sizeof(LevelTotals), cudaMemcpyDeviceToHost, s));
+        PF_CUDA_OK(cudaStreamSynchronize(s));
+        const uint64_t next_n = db->h_totals->next_pairs;
+        st.hits_total = db->h_totals->hits_total;
+        st.probes = db->h_totals->probes;
+        if (next_n > 0xFFFFFFF0ULL) {
+            set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
+                      (unsigned long long)next_n);
+            return PF_ERR_NOMEM;
+        }
+        const int nxt = cur ^ 1;
+        if (next_n && ((rc = db->fr_read[nxt].ensure(next_n)) || (rc = db->fr_node[nxt].ensure(next_n)))) return rc;
+        // hits of earlier levels and chunks live in the same arrays: grow with copy
+        if (want_hits && st.hits_total &&
+            ((rc = db->hit_read.grow_keep(st.hits_total, st.hits_before, s)) ||
+             (rc = db->hit_leaf.grow_keep(st.hits_total, st.hits_before, s))))
+            return rc;
+        st.hits_before = st.hits_total;
+        scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(
+            db->fr_read[cur].p, db->fr_node[cur].p, db->pass.p, (uint32_t)n, db->d_node_pass, db->d_cursor,
+            db->d_left, db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base, db->fr_read[nxt].p,
+            db->fr_node[nxt].p, db->hit_read.p, db->hit_leaf.p, db->read_hits.p, want_hits);
+        st.other_launches++;
+        st.n = next_n;
+        st.cur = nxt;
+    }
+    return PF_OK;
+}
+
+// Per-read hit lists (ResultMap, result_map.rs:9-46) as CSR over reads [0, n_reads), leaves ascending within a
+// read, built on the device from (hit_read, hit_leaf)[0, hits_total) and the per-read counts in read_hits; the
+// offsets of reads [out_r0, out_r0 + out_n] and the leaf array go back through pinned host memory.
+int pf::finish_csr(pf_db *db, uint32_t n_reads, uint64_t hits_total, int want_hits, uint32_t out_r0, uint32_t out_n,
+                   pf_hits *out, uint64_t *other_launches, uint64_t *d2h) {
+    cudaStream_t s = db->stream;
+    int rc;
+    if (!want_hits) return PF_OK;
+    const uint32_t nb = (n_reads + 1023u) / 1024u;
+    if ((rc = db->csr_off.ensure((size_t)n_reads + 1)) || (rc = db->csr_bsum.ensure(nb)) ||
+        (rc = db->csr_leaf.ensure(std::max<uint64_t>(hits_total, 1))))
+        return rc;
+    csr_block_sums_kernel<<<nb, 1024, 0, s>>>(db->read_hits.p, n_reads, db->csr_bsum.p);
+    csr_scan_sums_kernel<<<1, 1024, 0, s>>>(db->csr_bsum.p, nb);
+    csr_offsets_kernel<<<nb, 1024, 0, s>>>(db->read_hits.p, n_reads, db->csr_bsum.p, db->csr_off.p);
+    *other_launches += 3;
+    if (hits_total) {
+        csr_fill_kernel<<<(uint32_t)((hits_total + 255) / 256), 256, 0, s>>>(db->hit_read.p, db->hit_leaf.p, hits_total,
+                                                                            db->csr_off.p, db->read_hits.p, db->csr_leaf.p);
+        csr_sort_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(db->csr_off.p, n_reads, db->csr_leaf.p);
+        *other_launches += 2;
+    }
+    if ((rc = db->pin_off.ensure((size_t)out_n + 1)) || (rc = db->pin_leaf.ensure(std::max<uint64_t>(hits_total, 1))))
+        return rc;
+    PF_CUDA_OK(cudaMemcpyAsync(db->pin_off.p, db->csr_off.p + out_r0, ((size_t)out_n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (hits_total) PF_CUDA_OK(cudaMemcpyAsync(db->pin_leaf.p, db->csr_leaf.p, hits_total * 4, cudaMemcpyDeviceToHost, s));
+    *d2h += ((uint64_t)out_n + 1) * 8 + hits_total * 4;
+    (void)out;
+    return PF_OK;
+}
+
 // The level-synchronous descent for one resident batch.  Reads are processed in chunks whose cached k-mer
 // hashes (8 B per k-mer) fit the hash-cache budget; hits and counters accumulate over the chunks.
 static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, pf_hits *out) {
@@ -698,6 +726,10 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     const uint32_t n_reads = bt->n_reads;
     const size_t n_levels = db->level_start.size() - 1;
     int rc;
+    if (db->sharded) {
+        set_error("this handle holds a subtree shard: use pf_query_sharded / pf_query_sharded_device");
+        return PF_ERR_STATE;
+    }
     if (out) *out = pf_hits{};
     if (n_reads == 0) {
         db->out_off.assign(1, 0);
@@ -718,8 +750,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         if ((rc = db->read_hits.ensure(n_reads))) return rc;
         PF_CUDA_OK(cudaMemsetAsync(db->read_hits.p, 0, (size_t)n_reads * 4, s));
     }
-    uint64_t other_launches = 0, probe_launches = 0, pairs = 0, levels = 0, hits_total = 0, probes = 0, hits_before = 0;
-    size_t n_ev = 0;
+    Descent st;
     const uint32_t G = group_rounds_for(bt->max_kmers, db->hp.small_m != 0);
     db->stats.group_rounds = G;
     const uint64_t budget_kmers = std::max<uint64_t>(db->hash_cache_bytes / 12, 1);  // 8 B hash + 4 B index
@@ -758,129 +789,24 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         h.work_ctr = db->d_work + n_levels;
         if (chunk_kmers) {
             launch_hash(h, db->sm_count * 8, s);
-            other_launches++;
+            st.other_launches++;
         }
-        uint64_t n = 0;
-        int cur = 0;
-        const size_t last_entry_level = [&] {
-            size_t l = 0;
-            for (size_t i = 0; i < n_levels; ++i)
-                if (db->entry_start[i + 1] > db->entry_start[i]) l = i;
-            return l;
-        }();
-        for (size_t l = 0; l < n_levels && (n > 0 || l <= last_entry_level); ++l) {
-            // entry nodes of this level: append (read, node) pairs for every read of the chunk
-            const uint32_t e0 = db->entry_start[l], n_entry = db->entry_start[l + 1] - e0;
-            if (n_entry) {
-                const uint64_t add = (uint64_t)n_chunk * n_entry;
-                if (n + add > 0xFFFFFFF0ULL) {
-                    set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
-                              (unsigned long long)(n + add));
-                    return PF_ERR_NOMEM;
-                }
-                if ((rc = db->fr_read[cur].grow_keep(n + add, n, s)) || (rc = db->fr_node[cur].grow_keep(n + add, n, s)))
-                    return rc;
-                inject_frontier_kernel<<<(uint32_t)std::min<uint64_t>((add + 255) / 256, 8192), 256, 0, s>>>(
-                    db->fr_read[cur].p + n, db->fr_node[cur].p + n, r0, n_chunk, db->d_entry + e0, n_entry);
-                other_launches++;
-                n += add;
-            }
-            if (n == 0) continue;
-            if ((rc = db->pass.ensure(n))) return rc;
-            ProbeArgs a{};
-            a.fr_read = db->fr_read[cur].p;
-            a.fr_node = db->fr_node[cur].p;
-            a.n_pairs = (uint32_t)n;
-            a.lengths = bt->lengths.p;
-            a.kmer_off = bt->kmer_off.p;
-            a.hb = db->hb.p;
-            a.idx0 = db->idx0.p;
-            a.kmer_base = kmer_base;
-            a.node_slot = db->d_slot;
-            a.node_steps = db->d_steps;
-            a.filters = db->d_filters;
-            a.words_per_filter = db->wpf;
-            a.pass = db->pass.p;
-            a.node_pass = db->d_node_pass;
-            a.work_ctr = db->d_work + l;
-            a.probes = db->d_probes;
-            a.hp = db->hp;
-            a.threshold = threshold;
-            a.exhaustive = db->exhaustive;
-            if ((rc = ensure_events(db, n_ev + 2))) return rc;
-            PF_CUDA_OK(cudaEventRecord(db->ev_probe[n_ev], s));
-            launch_probe(a, G, db->sm_count, s);
-            PF_CUDA_OK(cudaEventRecord(db->ev_probe[n_ev + 1], s));
-            n_ev += 2;
-            probe_launches++;
-            pairs += n;
-            levels++;
-            level_scan_kernel<<<1, 1024, 0, s>>>(db->level_start[l], db->level_start[l + 1], db->d_node_pass, db->d_left,
-                                                 db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base,
-                                                 db->d_blk_counts, db->d_totals, db->d_probes);
-            other_launches++;
-            PF_CUDA_OK(cudaMemcpyAsync(db->h_totals, db->d_totals, sizeof(LevelTotals), cudaMemcpyDeviceToHost, s));
-            PF_CUDA_OK(cudaStreamSynchronize(s));
-            const uint64_t next_n = db->h_totals->next_pairs;
-            hits_total = db->h_totals->hits_total;
-            probes = db->h_totals->probes;
-            if (next_n > 0xFFFFFFF0ULL) {
-                set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
-                          (unsigned long long)next_n);
-                return PF_ERR_NOMEM;
-            }
-            const int nxt = cur ^ 1;
-            if (next_n && ((rc = db->fr_read[nxt].ensure(next_n)) || (rc = db->fr_node[nxt].ensure(next_n)))) return rc;
-            // hits of earlier levels and chunks live in the same arrays: grow with copy
-            if (want_hits && hits_total &&
-                ((rc = db->hit_read.grow_keep(hits_total, hits_before, s)) ||
-                 (rc = db->hit_leaf.grow_keep(hits_total, hits_before, s))))
-                return rc;
-            hits_before = hits_total;
-            scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(
-                db->fr_read[cur].p, db->fr_node[cur].p, db->pass.p, (uint32_t)n, db->d_node_pass, db->d_cursor,
-                db->d_left, db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base, db->fr_read[nxt].p,
-                db->fr_node[nxt].p, db->hit_read.p, db->hit_leaf.p, db->read_hits.p, want_hits);
-            other_launches++;
-            n = next_n;
-            cur = nxt;
-        }
+        st.n = 0;
+        st.cur = 0;
+        if ((rc = run_levels(db, bt, threshold, want_hits, G, kmer_base, 0, n_levels, r0, n_chunk, st))) return rc;
         r0 = r1;
     }
     add_counts_kernel<<<(uint32_t)((db->n_leaves + 255) / 256), 256, 0, s>>>(db->d_counts, db->d_blk_counts,
                                                                             (uint32_t)db->n_leaves);
-    other_launches++;
-    uint64_t d2h = levels * sizeof(LevelTotals);
-    if (want_hits) {
-        // CSR by read, leaves ascending within a read (ResultMap holds a set per read id), built on the device
-        const uint32_t nb = (n_reads + 1023u) / 1024u;
-        if ((rc = db->csr_off.ensure((size_t)n_reads + 1)) || (rc = db->csr_bsum.ensure(nb)) ||
-            (rc = db->csr_leaf.ensure(std::max<uint64_t>(hits_total, 1))))
-            return rc;
-        csr_block_sums_kernel<<<nb, 1024, 0, s>>>(db->read_hits.p, n_reads, db->csr_bsum.p);
-        csr_scan_sums_kernel<<<1, 1024, 0, s>>>(db->csr_bsum.p, nb);
-        csr_offsets_kernel<<<nb, 1024, 0, s>>>(db->read_hits.p, n_reads, db->csr_bsum.p, db->csr_off.p);
-        other_launches += 3;
-        if (hits_total) {
-            csr_fill_kernel<<<(uint32_t)((hits_total + 255) / 256), 256, 0, s>>>(db->hit_read.p, db->hit_leaf.p, hits_total,
-                                                                                db->csr_off.p, db->read_hits.p,
-                                                                                db->csr_leaf.p);
-            csr_sort_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(db->csr_off.p, n_reads, db->csr_leaf.p);
-            other_launches += 2;
-        }
-        if ((rc = db->pin_off.ensure((size_t)n_reads + 1)) || (rc = db->pin_leaf.ensure(std::max<uint64_t>(hits_total, 1))))
-            return rc;
-        PF_CUDA_OK(cudaMemcpyAsync(db->pin_off.p, db->csr_off.p, ((size_t)n_reads + 1) * 8, cudaMemcpyDeviceToHost, s));
-        if (hits_total)
-            PF_CUDA_OK(cudaMemcpyAsync(db->pin_leaf.p, db->csr_leaf.p, hits_total * 4, cudaMemcpyDeviceToHost, s));
-        d2h += ((uint64_t)n_reads + 1) * 8 + hits_total * 4;
-    }
+    st.other_launches++;
+    uint64_t d2h = st.levels * sizeof(LevelTotals);
+    if ((rc = finish_csr(db, n_reads, st.hits_total, want_hits, 0, n_reads, out, &st.other_launches, &d2h))) return rc;
     PF_CUDA_OK(cudaEventRecord(db->ev_end, s));
     PF_CUDA_OK(cudaStreamSynchronize(s));
     PF_CUDA_OK(cudaGetLastError());
     if (out) {
         if (want_hits) {
-            out->n_hits = hits_total;
+            out->n_hits = st.hits_total;
             out->read_off = db->pin_off.p;
             out->leaf = db->pin_leaf.p;
         } else {
@@ -888,26 +814,12 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
             out->read_off = db->out_off.data();
         }
     }
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, db->ev_begin, db->ev_end);
-    db->stats.device_ms += ms;
-    for (size_t e = 0; e + 1 < n_ev; e += 2) {
-        float pm = 0.f;
-        cudaEventElapsedTime(&pm, db->ev_probe[e], db->ev_probe[e + 1]);
-        db->stats.probe_kernel_ms += pm;
-    }
-    db->stats.blocks++;
-    db->stats.reads += n_reads;
-    db->stats.pairs += pairs;
-    db->stats.probes_issued += probes;
-    db->stats.levels += levels;
-    db->stats.probe_launches += probe_launches;
-    db->stats.other_launches += other_launches;
-    db->stats.d2h_bytes += d2h;
+    account_stats(db, st, n_reads, d2h);
     return PF_OK;
 }
 
-static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b, cudaStream_t s) {
+
+int pf::batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b, cudaStream_t s) {
     if (!in || (in->n_reads && (!in->lengths || !in->word_off || !in->packed))) {
         set_error("pf_read_batch: null array");
         return PF_ERR_ARG;
@@ -941,8 +853,16 @@ static int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b
     b->total_bases_bound = in->total_bases;
     {
         uint64_t tb = in->total_bases;
-        if (tb == 0)
-            for (uint32_t r = 0; r < in->n_reads; ++r) tb += in->lengths[r];
+        uint32_t ml = in->max_length;
+        if (tb == 0 || ml == 0) {
+            tb = 0;
+            for (uint32_t r = 0; r < in->n_reads; ++r) {
+                tb += in->lengths[r];
+                ml = std::max(ml, in->lengths[r]);
+            }
+        }
+        b->total_bases = tb;
+        b->max_length = ml;
         const uint64_t mean_len = tb / in->n_reads;
         b->nominal_kmers = std::max<uint64_t>(1, kmers_of((uint32_t)std::min<uint64_t>(mean_len, 0xFFFFFFFFu), k));
     }
@@ -1245,6 +1165,16 @@ int pf_comm_init(pf_db *db, int nranks, int rank, const void *id128) {
         set_error("pf_comm_init: bad argument");
         return PF_ERR_ARG;
     }
+    if (db->comm) {
+        set_error("pf_comm_init: the handle already has a communicator");
+        return PF_ERR_STATE;
+    }
+    return comm_init_impl(db, nranks, rank, id128);
+}
+
+}  // extern "C"
+
+int pf::comm_init_impl(pf_db *db, int nranks, int rank, const void *id128) {
     int rc = load_nccl();
     if (rc != PF_OK) return rc;
     PF_CUDA_OK(cudaSetDevice(db->device));
@@ -1258,6 +1188,8 @@ int pf_comm_init(pf_db *db, int nranks, int rank, const void *id128) {
     }
     return PF_OK;
 }
+
+extern "C" {
 
 int pf_allreduce_counts(pf_db *db) {
     if (!db) return PF_ERR_ARG;

@@ -71,6 +71,15 @@ def query_packed(tree: BloomTree, packed: PackedReads, threshold: float, want_hi
     return _hits_to_numpy(h, packed.n_reads)
 
 
+def query_sharded(tree: BloomTree, packed: PackedReads, threshold: float, want_hits: bool = True
+                  ) -> Tuple[np.ndarray, np.ndarray]:
+    """pf_query_sharded: collective over the ranks of a subtree-sharded tree; every rank passes its own block
+    (possibly empty) and gets the CSR of its own reads."""
+    h = _lib.Hits()
+    _lib.check(_lib.lib().pf_query_sharded(tree._h, packed.batch, C.c_float(threshold), int(want_hits), C.byref(h)))
+    return _hits_to_numpy(h, packed.n_reads)
+
+
 def query_batch(bloom_tree: BloomTree, read_set: Sequence[DNASequence], threshold: float,
                 result_map: Optional[ResultMap]) -> BloomTree:
     """query.rs:66-82.  Leaf counters accumulate inside the tree across calls; result_map receives
