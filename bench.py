@@ -181,16 +181,19 @@ def run_ours(args):
         build_s = time.perf_counter() - t0
     if world > 1:
         dist.barrier()
-    tree = BloomTree(db_dir, local_rank)
+    # one NCCL communicator owned by the library: id made on rank 0, handed over by the host
+    from phagefilter_b200.shard import exchange_nccl_id
+    nccl_id = exchange_nccl_id(rank) if (world > 1 or args.shard_tree) else None
+    if args.shard_tree:
+        # subtree shards (trees larger than HBM): top replicated, subtrees owned by ranks, frontier all-to-all
+        tree = BloomTree.open_sharded(db_dir, local_rank, rank, world, nccl_id,
+                                      cut_level=None if args.cut_level < 0 else args.cut_level)
+    else:
+        tree = BloomTree(db_dir, local_rank)
+        if world > 1:
+            _lib.check(L.pf_comm_init(tree._h, world, rank, nccl_id))
     info = tree.info
-    if world > 1:
-        # one NCCL communicator owned by the library: id made on rank 0, handed over by the host
-        idbuf = C.create_string_buffer(128)
-        if rank == 0:
-            _lib.check(L.pf_nccl_unique_id(idbuf))
-        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
-        dist.broadcast(t, 0)
-        _lib.check(L.pf_comm_init(tree._h, world, rank, bytes(t.cpu().numpy().tobytes())))
+    query_device = L.pf_query_sharded_device if args.shard_tree else L.pf_query_device
 
     packed = PackedReads.from_concat(blob, offs)
     dev_batch = C.c_void_p()
@@ -205,7 +208,7 @@ def run_ours(args):
     hits = _lib.Hits()
 
     def step_device():
-        _lib.check(L.pf_query_device(tree._h, dev_batch, C.c_float(THETA), 1, C.byref(hits)))
+        _lib.check(query_device(tree._h, dev_batch, C.c_float(THETA), 1, C.byref(hits)))
 
     def combine():
         # per-genome counts are combined with ONE NCCL reduce at the end of the run (north_star)
@@ -219,7 +222,7 @@ def run_ours(args):
         for i in range(n_steps):
             if i + 1 < n_steps:
                 _lib.check(L.pf_batch_upload_async(tree._h, packed.batch, C.byref(pipe[(i + 1) % 2])))
-            _lib.check(L.pf_query_device(tree._h, pipe[i % 2], C.c_float(THETA), 1, C.byref(hits)))
+            _lib.check(query_device(tree._h, pipe[i % 2], C.c_float(THETA), 1, C.byref(hits)))
         combine()
 
     sampler = ClockSampler(local_rank)
@@ -276,6 +279,14 @@ def run_ours(args):
     # correctness guard on the timed work: every error-free read must hit its source genome's leaf
     counts = tree.leaf_counts()
     assert int(counts.sum()) > 0
+    shard = None
+    if args.shard_tree:
+        si, ss = tree.shard_info(), tree.shard_stats()
+        shard = {"cut_level": int(si.cut_level), "top_nodes": int(si.top_nodes), "owned_nodes_rank0": int(si.owned_nodes),
+                 "resident_filter_bytes_rank0": int(si.resident_bytes),
+                 "pairs_sent_per_query_rank0": int(ss.pairs_sent) // max(int(ss.queries), 1),
+                 "bytes_sent_per_query_rank0": int(ss.bytes_sent) // max(int(ss.queries), 1),
+                 "bytes_received_per_query_rank0": int(ss.bytes_received) // max(int(ss.queries), 1)}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -323,7 +334,9 @@ def run_ours(args):
                        "nodes": int(info.n_nodes), "leaves": int(info.n_leaves), "levels": int(info.n_levels),
                        "filter_bytes": int(info.filter_bytes), "want_hits": True,
                        "l2": "filters (358 MB) + reads exceed the 126 MB L2; a 256 MB buffer is also written "
-                             "between timed steps", "parallelism": f"reads sharded x{world}, tree replicated"},
+                             "between timed steps", "parallelism": (f"reads sharded x{world}, tree cut into a replicated top and subtrees owned by ranks; "
+                                       "frontier + hit all-to-all over NCCL") if args.shard_tree else
+                       f"reads sharded x{world}, tree replicated"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st2.h2d_bytes) // steps,
                     "d2h_bytes_per_step": int(st2.d2h_bytes) // steps, "ms_per_step": e2e_ms_all / steps,
@@ -337,6 +350,8 @@ def run_ours(args):
             "work": {"pairs_per_step": pairs // steps, "probes_issued_per_step": probes // steps,
                      "hits_per_step": n_hits, "db_build_s": round(build_s, 2)},
         }
+        if shard:
+            line["shard"] = shard
         print(json.dumps(line))
     L.pf_batch_free(tree._h, dev_batch)
     packed.close()
@@ -354,6 +369,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
+    ap.add_argument("--shard-tree", action="store_true",
+                    help="subtree-sharded tree (pf_db_open_sharded) instead of one replica per GPU")
+    ap.add_argument("--cut-level", type=int, default=-1, help="cut level of the sharded tree (-1: automatic)")
     ap.add_argument("--profile", action="store_true",
                     help="for runs under ncu: shrink the CPU-baseline sample (numbers printed under a profiler are not bench values)")
     args = ap.parse_args()
