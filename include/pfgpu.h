@@ -180,6 +180,9 @@ int pf_db_set_hash_cache_bytes(pf_db *db, uint64_t bytes);
 /* Probe steps per node (level order, n_nodes entries) a query with `threshold` uses for a batch whose reads
  * of mean length have `nominal_kmers` k-mers (K = exact, 0 = skipped). */
 int pf_db_node_steps(pf_db *db, float threshold, uint64_t nominal_kmers, uint32_t *steps);
+/* Same, plus the k-mer sampling stride per node (1 = every k-mer; t > 1 only at verified interior nodes: every t-th
+ * k-mer, centred in the read, is probed -- a sound cannot-pass test on a sample).  Either array may be NULL. */
+int pf_db_node_plan(pf_db *db, float threshold, uint64_t nominal_kmers, uint32_t *steps, uint32_t *strides);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU: reads are sharded by rank, every rank holds a replica of the tree, and the

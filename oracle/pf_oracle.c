@@ -355,7 +355,8 @@ typedef struct pfo_node {
     /* cache for the kernel-schedule restatement (invalidated whenever the tree changes) */
     int analysed, mono;
     uint64_t pop;
-    uint32_t steps; /* plan of the current pfo_query_batch_sched call */
+    uint32_t steps;  /* plan of the current pfo_query_batch_sched call */
+    uint32_t stride; /* k-mer sampling stride of the plan (1 = every k-mer) */
 } pfo_node;
 
 struct pfo_tree {
@@ -785,8 +786,8 @@ typedef struct {
  * the pair fails as soon as total misses > n_k - need; after every group it passes as soon as hits >= need.
  * With n_steps < K a surviving k-mer counts as a hit (sound pre-test of interior nodes).  The outcome at
  * exact nodes (n_steps == K) is identical to query_passes; only the amount of work differs. */
-static uint64_t pair_sched(const pfo_filter *f, uint32_t n_steps, uint32_t G, const oread *r, size_t k, int rot,
-                           int *pass_out) {
+static uint64_t pair_sched(const pfo_filter *f, uint32_t n_steps, uint32_t stride, uint32_t G, const oread *r, size_t k,
+                           int rot, int *pass_out) {
     uint64_t probes = 0;
     if (n_steps == 0 || r->need == 0) { /* skipped interior node, or nothing to reach */
         *pass_out = 1;
@@ -796,15 +797,22 @@ static uint64_t pair_sched(const pfo_filter *f, uint32_t n_steps, uint32_t G, co
         *pass_out = 0;
         return 0;
     }
-    uint64_t allowed = r->n_k - r->need, misses = 0, hits = 0;
+    /* sampled pre-test (stride > 1, verified interior nodes only): slots q = 0..n_s-1 stand for the k-mers
+     * off + q*stride, centred in the read; the k-mers that are not probed count as not proven absent */
+    uint64_t n_s = r->n_k, off = 0;
+    if (stride > 1) {
+        n_s = r->n_k / stride ? r->n_k / stride : 1;
+        off = (r->n_k - 1 - (n_s - 1) * stride) / 2;
+    }
+    uint64_t allowed = r->n_k - r->need, misses = 0, hits = r->n_k - n_s;
     const uint64_t gsz = 32ull * G;
     uint64_t *h1 = (uint64_t *)malloc(gsz * 8), *h2 = (uint64_t *)malloc(gsz * 8);
     uint8_t *alive = (uint8_t *)malloc(gsz);
     int decided = 0, result = 0;
-    for (uint64_t base = 0; base < r->n_k && !decided; base += gsz) {
-        uint64_t cnt = r->n_k - base < gsz ? r->n_k - base : gsz;
+    for (uint64_t base = 0; base < n_s && !decided; base += gsz) {
+        uint64_t cnt = n_s - base < gsz ? n_s - base : gsz;
         for (uint64_t j = 0; j < cnt; j++) {
-            const uint8_t *km = r->kmers + (base + j) * k;
+            const uint8_t *km = r->kmers + (off + (base + j) * (stride > 1 ? stride : 1)) * k;
             h1[j] = pfo_fx_hash(f->seed1, km, k, rot);
             h2[j] = pfo_fx_hash(f->seed2, km, k, rot);
             alive[j] = 1;
@@ -947,8 +955,9 @@ static int filter_contains_filter(const pfo_filter *parent, const pfo_filter *ch
  * Model: a read unrelated to the subtree has n absent k-mers; at a node with fill f probed for s steps each
  * k-mer is proven absent with probability p = 1 - f^s after (1-f^s)/(1-f) expected probes; the read is pruned
  * when more than `allowed` k-mers are proven absent: P = Phi((n p - allowed - 0.5) / sqrt(n p (1-p))).
- * Bottom-up, a verified interior node picks s in {0 (skip), 1..K} minimising
- *     probes(f,s) + PAIR_OVERHEAD + (1 - P) * (cost(left) + cost(right))            [s = 0: just the children]
+ * Bottom-up, a verified interior node picks s in {0 (skip), 1..K} and a k-mer sampling stride t in {1,2,4,8} minimising
+ *     probes(f,s) * n_s/n + PAIR_OVERHEAD + (1 - P) * (cost(left) + cost(right))    [s = 0: just the children]
+ * with n_s = floor(n/t) sampled k-mers and P the prune probability of n_s trials.
  * Leaves and unverified nodes are exact (s = K). */
 #define PF_PLAN_PAIR_OVERHEAD 0.25
 static double plan_phi(double z) { /* standard normal CDF: 33-point table on [-4,4], linear interpolation */
@@ -974,17 +983,31 @@ static double plan_prune_prob(double n, double allowed, double f, uint32_t s) {
     if (var < 1e-9) return mean > allowed ? 1.0 : 0.0;
     return plan_phi((mean - allowed - 0.5) / sqrt(var));
 }
-/* best steps for one verified interior node; *cost_out = its expected cost */
-static uint32_t plan_choose(double f, uint32_t K, double n, double allowed, double below, double *cost_out) {
-    uint32_t best_s = 0;
+/* best (steps, stride) for one verified interior node; *cost_out = its expected cost.  Stride t > 1 probes only
+ * floor(n / t) k-mers, every t-th one centred in the read: an unprobed k-mer is not proven absent, so the test stays
+ * sound; its probes shrink by n_s / n and its pruning power is that of n_s trials.  t is a power of two <= 8 (a
+ * substitution spoils k >= 17 consecutive k-mers, so reads with errors are still caught) and never leaves fewer
+ * than 32 k-mers (one full warp round).  A sample is only ever probed for ONE step: with few k-mers per pair, further
+ * steps are dependent round trips with ever fewer probes in flight (measured: 66 G probes/s instead of 250). */
+static uint32_t plan_choose(double f, uint32_t K, uint64_t n_nominal, double allowed, double below, uint32_t *stride_out,
+                            double *cost_out) {
+    uint32_t best_s = 0, best_t = 1;
     double best = below;
-    for (uint32_t s = 1; s <= K; ++s) {
-        const double c = plan_probe_cost(f, s) + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(n, allowed, f, s)) * below;
-        if (c < best) {
-            best = c;
-            best_s = s;
+    const double n = (double)n_nominal;
+    for (uint32_t t = 1; t <= 8; t *= 2) {
+        const uint64_t n_s = n_nominal / t;
+        if (t > 1 && n_s < 32) break;
+        const double ns = (double)(n_s ? n_s : 1), frac = ns / n;
+        for (uint32_t s = 1; s <= (t > 1 ? 1u : K); ++s) { /* a sample is probed for one step only, see above */
+            const double c = plan_probe_cost(f, s) * frac + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(ns, allowed, f, s)) * below;
+            if (c < best) {
+                best = c;
+                best_s = s;
+                best_t = t;
+            }
         }
     }
+    *stride_out = best_s ? best_t : 1;
     *cost_out = best;
     return best_s;
 }
@@ -992,7 +1015,9 @@ static double plan_exact_cost(double f, uint32_t K, double n, double allowed, do
     return plan_probe_cost(f, K) + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(n, allowed, f, K)) * below;
 }
 
-static double plan_rec(const pfo_tree *t, pfo_node *n, double nn, double allowed, int lazy) {
+static double plan_rec(const pfo_tree *t, pfo_node *n, uint64_t n_nominal, double allowed, int lazy) {
+    const double nn = (double)n_nominal;
+    n->stride = 1;
     const pfo_filter *f = t->filters[n->filter];
     const uint32_t K = f->K;
     if (!n->analysed) {
@@ -1006,21 +1031,21 @@ static double plan_rec(const pfo_tree *t, pfo_node *n, double nn, double allowed
         n->steps = K;
         return plan_probe_cost(fill, K) + PF_PLAN_PAIR_OVERHEAD;
     }
-    const double cl = n->left ? plan_rec(t, n->left, nn, allowed, lazy) : 0.0;
-    const double cr = n->right ? plan_rec(t, n->right, nn, allowed, lazy) : 0.0;
+    const double cl = n->left ? plan_rec(t, n->left, n_nominal, allowed, lazy) : 0.0;
+    const double cr = n->right ? plan_rec(t, n->right, n_nominal, allowed, lazy) : 0.0;
     const double below = cl + cr;
     if (!lazy || !n->mono) {
         n->steps = K;
         return plan_exact_cost(fill, K, nn, allowed, below);
     }
     double c = 0.0;
-    n->steps = plan_choose(fill, K, nn, allowed, below, &c);
+    n->steps = plan_choose(fill, K, n_nominal, allowed, below, &n->stride, &c);
     return c;
 }
 static void plan_steps(pfo_tree *t, float threshold, uint64_t n_nominal, int lazy) {
     const uint64_t need = pfo_need(threshold, n_nominal);
     const double allowed = need > n_nominal ? 0.0 : (double)(n_nominal - need);
-    if (t->root) plan_rec(t, t->root, (double)n_nominal, allowed, lazy);
+    if (t->root) plan_rec(t, t->root, n_nominal, allowed, lazy);
 }
 static uint32_t pfo_node_steps(const pfo_tree *t, pfo_node *n, float threshold, int lazy) {
     (void)t;
@@ -1057,7 +1082,7 @@ static void sched_rec(sctx *c, pfo_node *node, const uint32_t *set, uint64_t n_s
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : pr)
     for (uint64_t i = 0; i < n_set; i++) {
         int pass = 0;
-        pr += pair_sched(f, n_steps, c->group_rounds, &c->reads[set[i]], k, rot, &pass);
+        pr += pair_sched(f, n_steps, node->stride ? node->stride : 1, c->group_rounds, &c->reads[set[i]], k, rot, &pass);
         flag[i] = (uint8_t)pass;
     }
     c->out->probes_sched += pr;

@@ -101,6 +101,7 @@ SYMBOLS = {
     "pf_db_set_lazy": (C.c_int, [_VP, C.c_int]),
     "pf_db_set_hash_cache_bytes": (C.c_int, [_VP, C.c_uint64]),
     "pf_db_node_steps": (C.c_int, [_VP, C.c_float, C.c_uint64, C.POINTER(C.c_uint32)]),
+    "pf_db_node_plan": (C.c_int, [_VP, C.c_float, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pf_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "pf_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, C.c_char_p]),
     "pf_allreduce_counts": (C.c_int, [_VP]),

@@ -109,6 +109,15 @@ class BloomTree:
                                                out.ctypes.data_as(C.POINTER(C.c_uint32))))
         return out
 
+    def node_plan(self, threshold: float, nominal_kmers: int = 131) -> Tuple[np.ndarray, np.ndarray]:
+        """(probe steps, k-mer sampling stride) per node in level order."""
+        steps = np.zeros(int(self._info.n_nodes), dtype=np.uint32)
+        strides = np.zeros(int(self._info.n_nodes), dtype=np.uint32)
+        _lib.check(_lib.lib().pf_db_node_plan(self._h, C.c_float(threshold), nominal_kmers,
+                                              steps.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                              strides.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return steps, strides
+
     def stats(self) -> _lib.Stats:
         s = _lib.Stats()
         _lib.check(_lib.lib().pf_get_stats(self._h, C.byref(s)))

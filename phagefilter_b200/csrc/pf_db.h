@@ -177,6 +177,7 @@ struct pf_db {
     std::vector<uint64_t> h_pop;       // set bits of each node's filter
     std::vector<uint8_t> h_mono;       // interior node whose filter contains both children's filters
     std::vector<uint32_t> h_steps;     // probe steps per node for the current (threshold, mode)
+    std::vector<uint32_t> h_stride;    // k-mer sampling stride per node (1 = every k-mer)
     uint32_t *d_steps = nullptr;
     std::vector<uint32_t> h_entry;        // entry nodes of the current plan, ordered by level
     std::vector<uint32_t> entry_start;    // [n_levels + 1] offsets into h_entry per level
@@ -191,7 +192,8 @@ struct pf_db {
     uint64_t *d_filters = nullptr;
     // accumulators and per-block scratch
     unsigned long long *d_counts = nullptr, *d_blk_counts = nullptr;
-    uint32_t *d_node_pass = nullptr, *d_cursor = nullptr;  // contiguous [2 * n_nodes]
+    uint32_t *d_node_pass = nullptr, *d_cursor = nullptr;  // contiguous [2 * n_nodes], then:
+    uint32_t *d_node_pass_copies = nullptr;                // [NODE_PASS_COPIES * n_nodes] counters the probe kernel adds to
     unsigned long long *d_next_base = nullptr, *d_hit_base = nullptr;
     unsigned int *d_work = nullptr;  // one counter per level
     unsigned long long *d_probes = nullptr;

@@ -20,6 +20,7 @@
 namespace pf {
 
 constexpr uint32_t NONE32_D = 0xFFFFFFFFu;  // "no child" / "not an exception read"
+constexpr int NODE_PASS_COPIES = 16;  // copies of the per-node survivor counters (spreads same-address atomics)
 constexpr int PROBE_THREADS = 256;
 constexpr int PROBE_CHUNK = 8;  // pairs fetched per warp per work-counter atomic
 constexpr int HASH_THREADS = 256;
@@ -128,7 +129,8 @@ struct ProbeArgs {
     uint64_t words_per_filter;
     // outputs
     uint8_t *pass;
-    uint32_t *node_pass;
+    uint32_t *node_pass;  // [NODE_PASS_COPIES][n_nodes]
+    uint32_t n_nodes;
     unsigned int *work_ctr;
     unsigned long long *probes;
     HashParams hp;
@@ -211,11 +213,16 @@ PF_D uint32_t probe_idx_phase(const uint32_t *__restrict__ filt, const uint32_t 
 // Returns true when the pair's outcome is decided (`pass` set); hits/misses updated otherwise.
 // SMALL_M: step 0 uses the cached bit indices (no hashing, no modulo); the cached hash_bytes values are only
 // fetched when the node needs more than one step -- speculatively, together with the step-0 gathers.
+// The group's k-mer slots q = gbase + j*32 + lane map to the read's k-mers off + q*stride (stride 1, off 0 unless the
+// node samples: see probe_pair); n_k is the number of slots.
 template <int G, bool SMALL_M>
 PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, uint32_t n_steps,
                       const uint64_t *__restrict__ hbp, const uint32_t *__restrict__ i0p, uint32_t gbase, uint32_t n_k,
-                      uint32_t lane, uint32_t need, uint32_t allowed, bool exhaustive, uint32_t &hits,
-                      uint32_t &misses, uint32_t &probes, bool &pass) {
+                      uint32_t lane, uint32_t need, uint32_t allowed, bool exhaustive, uint32_t stride, uint32_t off,
+                      int pre, uint32_t &hits, uint32_t &misses, uint32_t &probes, bool &pass) {
+    // pre >= 0: step 0 of the first round was already done for the whole chunk of pairs (probe_kernel); pre is this
+    // lane's result (1 = its k-mer's bit was clear)
+    const uint32_t kidx = off + (gbase + lane) * stride, kstep = 32u * stride;  // k-mer of slot j: kidx + j*kstep
     GroupState<G, SMALL_M> st;
     st.alive = 0;
     const uint32_t cnt = min(32u * G, n_k - gbase);
@@ -231,15 +238,20 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
         uint32_t idx[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) idx[j] = 0;
-        if (st.alive & 1u) idx[0] = ldg32(i0p + gbase + lane);
+        if (pre < 0 && (st.alive & 1u)) idx[0] = ldg32(i0p + kidx);
         if (n_steps > 1u) {
 #pragma unroll
             for (int j = 0; j < G; ++j)
-                if ((st.alive >> j) & 1u) hb[j] = __ldg(hbp + gbase + (uint32_t)j * 32u + lane);
+                if ((st.alive >> j) & 1u) hb[j] = __ldg(hbp + kidx + (uint32_t)j * kstep);
         }
         // step 0, first round
         probes += min(32u, cnt);
-        dead += __reduce_add_sync(0xFFFFFFFFu, probe_idx_phase<G, 0, 1>(filt, idx, st.alive));
+        if (pre >= 0) {
+            if (pre) st.alive &= ~1u;
+            dead += __popc(__ballot_sync(0xFFFFFFFFu, pre != 0));
+        } else {
+            dead += __reduce_add_sync(0xFFFFFFFFu, probe_idx_phase<G, 0, 1>(filt, idx, st.alive));
+        }
         if (!exhaustive && dead > limit) {
             pass = false;
             return true;
@@ -248,7 +260,7 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
         if (G > 1 && cnt > 32u) {
 #pragma unroll
             for (int j = 1; j < G; ++j)
-                if ((st.alive >> j) & 1u) idx[j] = ldg32(i0p + gbase + (uint32_t)j * 32u + lane);
+                if ((st.alive >> j) & 1u) idx[j] = ldg32(i0p + kidx + (uint32_t)j * kstep);
             probes += cnt - 32u;
             dead += __reduce_add_sync(0xFFFFFFFFu, probe_idx_phase<G, (G > 1 ? 1 : 0), G>(filt, idx, st.alive));
             if (!exhaustive && dead > limit) {
@@ -259,7 +271,7 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
     } else {
 #pragma unroll
         for (int j = 0; j < G; ++j)
-            if ((st.alive >> j) & 1u) hb[j] = __ldg(hbp + gbase + (uint32_t)j * 32u + lane);
+            if ((st.alive >> j) & 1u) hb[j] = __ldg(hbp + kidx + (uint32_t)j * kstep);
 #pragma unroll
         for (int j = 0; j < G; ++j) st.g[j] = fx_finish(hp.c1, hb[j], hp.rot);
         probes += min(32u, cnt);
@@ -313,25 +325,33 @@ struct PairMeta {
 
 // Evaluate one (read,node) pair; warp-uniform control flow.  Returns pass/fail (query_passes).
 template <int G, bool SMALL_M>
-PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, uint32_t &probes) {
+PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int pre, uint32_t &probes) {
     const HashParams &hp = a.hp;
     const uint32_t n_k = kmers_of(pm.len, hp.k);
     const uint32_t need = need_of(a.threshold, n_k);
     const bool exhaustive = a.exhaustive != 0;
+    const uint32_t n_steps = pm.steps & 0xFFu, stride = pm.steps >> 8;  // node plan: steps | stride << 8
     if (!exhaustive) {
-        if (pm.steps == 0u) return true;  // skipped interior node: its children decide (verified superset)
-        if (need == 0u) return true;      // hits >= 0 always
-        if (need > n_k) return false;     // hits <= n_k < need
+        if (n_steps == 0u) return true;  // skipped interior node: its children decide (verified superset)
+        if (need == 0u) return true;     // hits >= 0 always
+        if (need > n_k) return false;    // hits <= n_k < need
     }
     const uint32_t allowed = need > n_k ? 0u : n_k - need;
+    // Sampled pre-test (verified-monotone interior nodes only): every stride-th k-mer, centred in the read.  A
+    // k-mer that is not probed is not proven absent, so the test stays sound; it just prunes a little less.
+    uint32_t n_s = n_k, off = 0;
+    if (stride > 1u) {
+        n_s = max(1u, n_k / stride);
+        off = (n_k - 1u - (n_s - 1u) * stride) >> 1;
+    }
     const uint32_t *filt = reinterpret_cast<const uint32_t *>(a.filters + (uint64_t)pm.slot * a.words_per_filter);
     const uint64_t *hbp = a.hb + (pm.koff - a.kmer_base);
     const uint32_t *i0p = a.idx0 + (pm.koff - a.kmer_base);
-    uint32_t hits = 0, misses = 0;
+    uint32_t hits = n_k - n_s, misses = 0;
     bool pass = false;
-    for (uint32_t gbase = 0; gbase < n_k; gbase += 32u * G)
-        if (probe_group<G, SMALL_M>(filt, hp, pm.steps, hbp, i0p, gbase, n_k, lane, need, allowed, exhaustive, hits,
-                                    misses, probes, pass))
+    for (uint32_t gbase = 0; gbase < n_s; gbase += 32u * G)
+        if (probe_group<G, SMALL_M>(filt, hp, n_steps, hbp, i0p, gbase, n_s, lane, need, allowed, exhaustive, stride, off,
+                                    gbase == 0u ? pre : -1, hits, misses, probes, pass))
             return pass;
     return hits >= need;
 }
@@ -342,7 +362,9 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, uint
 template <int G, bool SMALL_M>
 static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 4 : 3))) probe_kernel(const ProbeArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t probes = 0;
+    uint32_t *const np_mine = a.node_pass + (size_t)(blockIdx.x % NODE_PASS_COPIES) * a.n_nodes;
+    uint32_t probes = 0;      // warp-uniform: probes of the per-pair path
+    uint32_t my_probes = 0;   // per lane: probes of the pairs this lane settled after the batched first round
     unsigned long long probes_total = 0;
     for (;;) {
         uint32_t i0 = 0;
@@ -359,8 +381,76 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
             mine.slot = ldg32(a.node_slot + mine.u);
             mine.steps = ldg32(a.node_steps + mine.u);
         }
+        // Step 0 of the first round (up to 32 k-mers) of EVERY pair of the chunk, batched: PROBE_CHUNK index loads,
+        // then PROBE_CHUNK gathers in flight per lane, instead of two dependent round trips per pair.  That round
+        // alone decides most pairs that fail and all of a sampled single-round pre-test; those pairs are settled
+        // here by the lane that holds their metadata and never enter the per-pair path below.
+        uint32_t undecided = n_here >= 32u ? 0xFFFFFFFFu : (1u << n_here) - 1u;
+        uint32_t miss_bits = 0;  // bit p: this lane's k-mer of pair p had its step-0 bit clear
+        bool my_pass = false;
+        if (SMALL_M) {
+            // per pair: first-round slot count | stride << 8, or 0 when the pair needs no probe at all; and the k-mer
+            // index of slot 0
+            uint32_t my_r0 = 0, my_nk = 0, my_need = 0, my_ns = 0;
+            uint64_t my_k0 = 0;
+            bool my_decided = false;
+            if (lane < n_here) {
+                my_nk = kmers_of(mine.len, a.hp.k);
+                my_need = need_of(a.threshold, my_nk);
+                const uint32_t n_steps = mine.steps & 0xFFu, stride = mine.steps >> 8;
+                if (!a.exhaustive && (n_steps == 0u || my_need == 0u || my_need > my_nk)) {  // as probe_pair
+                    my_decided = true;
+                    my_pass = n_steps == 0u || my_need == 0u;
+                }
+                uint32_t off = 0;
+                my_ns = my_nk;
+                if (stride > 1u) {
+                    my_ns = max(1u, my_nk / stride);
+                    off = (my_nk - 1u - (my_ns - 1u) * stride) >> 1;
+                }
+                if (!my_decided && my_nk) my_r0 = min(32u, my_ns) | (stride << 8);
+                my_k0 = mine.koff - a.kmer_base + off;
+            }
+            uint32_t idxv[PROBE_CHUNK], wv[PROBE_CHUNK];
+#pragma unroll
+            for (int p = 0; p < PROBE_CHUNK; ++p) {
+                const uint32_t r0 = __shfl_sync(0xFFFFFFFFu, my_r0, p);
+                const uint64_t k0 = __shfl_sync(0xFFFFFFFFu, my_k0, p);
+                idxv[p] = 0xFFFFFFFFu;
+                if (lane < (r0 & 0xFFu)) idxv[p] = ldg32(a.idx0 + k0 + lane * (r0 >> 8));
+            }
+#pragma unroll
+            for (int p = 0; p < PROBE_CHUNK; ++p) {
+                const uint32_t slot = __shfl_sync(0xFFFFFFFFu, mine.slot, p);
+                wv[p] = 0xFFFFFFFFu;
+                if (idxv[p] != 0xFFFFFFFFu)
+                    wv[p] = ldg32(reinterpret_cast<const uint32_t *>(a.filters + (uint64_t)slot * a.words_per_filter) + (idxv[p] >> 5));
+            }
+            uint32_t my_dead0 = 0;
+#pragma unroll
+            for (int p = 0; p < PROBE_CHUNK; ++p) {
+                const bool miss = !((wv[p] >> (idxv[p] & 31u)) & 1u);
+                if (miss) miss_bits |= 1u << p;
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, miss);
+                if (lane == (uint32_t)p) my_dead0 = __popc(b);
+            }
+            if ((my_r0 & 0xFFu) != 0u) {  // this lane's pair was probed: can its first round settle it?
+                const uint32_t cnt0 = my_r0 & 0xFFu, allowed = my_need > my_nk ? 0u : my_nk - my_need;
+                if (!a.exhaustive && my_dead0 > allowed) {
+                    my_decided = true;
+                    my_pass = false;
+                    my_probes += cnt0;
+                } else if (my_ns <= 32u && (mine.steps & 0xFFu) == 1u) {
+                    my_decided = true;
+                    my_pass = (my_nk - my_ns) + (cnt0 - my_dead0) >= my_need;
+                    my_probes += cnt0;
+                }
+            }
+            undecided = __ballot_sync(0xFFFFFFFFu, lane < n_here && !my_decided);
+        }
         uint32_t pass_bits = 0;
-        for (uint32_t p = 0; p < n_here; ++p) {
+        for (uint32_t rest = undecided; rest; rest &= rest - 1u) {
+            const uint32_t p = __ffs(rest) - 1u;
             PairMeta pm;
             pm.r = __shfl_sync(0xFFFFFFFFu, mine.r, p);
             pm.u = __shfl_sync(0xFFFFFFFFu, mine.u, p);
@@ -368,15 +458,17 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
             pm.slot = __shfl_sync(0xFFFFFFFFu, mine.slot, p);
             pm.steps = __shfl_sync(0xFFFFFFFFu, mine.steps, p);
             pm.koff = __shfl_sync(0xFFFFFFFFu, mine.koff, p);
-            if (probe_pair<G, SMALL_M>(a, pm, lane, probes)) pass_bits |= 1u << p;
+            if (probe_pair<G, SMALL_M>(a, pm, lane, SMALL_M ? (int)((miss_bits >> p) & 1u) : -1, probes)) pass_bits |= 1u << p;
         }
-        if (lane < n_here) {
-            const bool pass = (pass_bits >> lane) & 1u;
-            a.pass[i0 + lane] = pass ? 1 : 0;
-            if (pass) atomicAdd(a.node_pass + mine.u, 1u);
-        }
-        probes_total += probes;
+        // survivors per node: the frontier is node-major, so at any moment most warps of the GPU count into the same
+        // node; same-address atomics serialise in L2 (measured: 1 M of them cost ~0.5 ms), so the counter is kept in
+        // NODE_PASS_COPIES copies, one per group of CTAs, summed by level_scan_kernel
+        const bool pass = lane < n_here && (((undecided >> lane) & 1u) ? ((pass_bits >> lane) & 1u) != 0u : my_pass);
+        if (lane < n_here) a.pass[i0 + lane] = pass ? 1 : 0;
+        if (pass) atomicAdd(np_mine + mine.u, 1u);
+        probes_total += probes + __reduce_add_sync(0xFFFFFFFFu, my_probes);
         probes = 0;
+        my_probes = 0;
     }
     if (lane == 0 && probes_total) atomicAdd(a.probes, probes_total);
 }
@@ -406,7 +498,8 @@ struct LevelTotals {
 // gives every child its slice of the next frontier (children are numbered level-order, left before
 // right, so the slices are node-major) and every leaf its slice of the hit list; leaf counts are added
 // to the block histogram.
-static __global__ void level_scan_kernel(uint32_t lo, uint32_t hi, const uint32_t *__restrict__ node_pass,
+static __global__ void level_scan_kernel(uint32_t lo, uint32_t hi, const uint32_t *__restrict__ node_pass_copies,
+                                  uint32_t n_nodes, uint32_t *node_pass,
                                   const uint32_t *__restrict__ left, const uint32_t *__restrict__ right,
                                   const int32_t *__restrict__ leaf, unsigned long long *next_base,
                                   unsigned long long *hit_base, unsigned long long *blk_counts, LevelTotals *totals,
@@ -418,7 +511,11 @@ static __global__ void level_scan_kernel(uint32_t lo, uint32_t hi, const uint32_
     const uint32_t b = lo + min(n, t * per), e = lo + min(n, (t + 1) * per);
     unsigned long long sn = 0, sh = 0;
     for (uint32_t u = b; u < e; ++u) {
-        const unsigned long long c = node_pass[u];
+        uint32_t tot = 0;
+#pragma unroll
+        for (int cpy = 0; cpy < NODE_PASS_COPIES; ++cpy) tot += node_pass_copies[(size_t)cpy * n_nodes + u];
+        node_pass[u] = tot;  // the survivors of node u: read again below and by scatter_kernel
+        const unsigned long long c = tot;
         if (leaf[u] >= 0) sh += c;
         else sn += c * ((left[u] != NONE32_D) + (right[u] != NONE32_D));
     }

@@ -296,8 +296,10 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     size_t nn = db->n_nodes, nl = std::max<uint64_t>(db->n_leaves, 1), nlev = db->level_start.size();
     PF_CUDA_OK(cudaMalloc(&db->d_counts, nl * 8));
     PF_CUDA_OK(cudaMalloc(&db->d_blk_counts, nl * 8));
-    PF_CUDA_OK(cudaMalloc(&db->d_node_pass, 2 * nn * 4));
+    // [node totals | cursors | NODE_PASS_COPIES x per-node counters], zeroed together per chunk of reads
+    PF_CUDA_OK(cudaMalloc(&db->d_node_pass, (2 + NODE_PASS_COPIES) * nn * 4));
     db->d_cursor = db->d_node_pass + nn;
+    db->d_node_pass_copies = db->d_node_pass + 2 * nn;
     PF_CUDA_OK(cudaMalloc(&db->d_next_base, nn * 8));
     PF_CUDA_OK(cudaMalloc(&db->d_hit_base, nn * 8));
     PF_CUDA_OK(cudaMalloc(&db->d_work, nlev * 4));
@@ -399,8 +401,9 @@ static int analyse_tree(pf_db *db) {
  * Model: a read unrelated to the subtree has n absent k-mers; at a node with fill f probed for s steps each
  * k-mer is proven absent with probability p = 1 - f^s after (1-f^s)/(1-f) expected probes; the read is pruned
  * when more than `allowed` k-mers are proven absent: P = Phi((n p - allowed - 0.5) / sqrt(n p (1-p))).
- * Bottom-up, a verified interior node picks s in {0 (skip), 1..K} minimising
- *     probes(f,s) + PAIR_OVERHEAD + (1 - P) * (cost(left) + cost(right))            [s = 0: just the children]
+ * Bottom-up, a verified interior node picks s in {0 (skip), 1..K} and a k-mer sampling stride t in {1,2,4,8} minimising
+ *     probes(f,s) * n_s/n + PAIR_OVERHEAD + (1 - P) * (cost(left) + cost(right))    [s = 0: just the children]
+ * with n_s = floor(n/t) sampled k-mers and P the prune probability of n_s trials.
  * Leaves and unverified nodes are exact (s = K). */
 #define PF_PLAN_PAIR_OVERHEAD 0.25
 static double plan_phi(double z) { /* standard normal CDF: 33-point table on [-4,4], linear interpolation */
@@ -426,17 +429,31 @@ static double plan_prune_prob(double n, double allowed, double f, uint32_t s) {
     if (var < 1e-9) return mean > allowed ? 1.0 : 0.0;
     return plan_phi((mean - allowed - 0.5) / sqrt(var));
 }
-/* best steps for one verified interior node; *cost_out = its expected cost */
-static uint32_t plan_choose(double f, uint32_t K, double n, double allowed, double below, double *cost_out) {
-    uint32_t best_s = 0;
+/* best (steps, stride) for one verified interior node; *cost_out = its expected cost.  Stride t > 1 probes only
+ * floor(n / t) k-mers, every t-th one centred in the read: an unprobed k-mer is not proven absent, so the test stays
+ * sound; its probes shrink by n_s / n and its pruning power is that of n_s trials.  t is a power of two <= 8 (a
+ * substitution spoils k >= 17 consecutive k-mers, so reads with errors are still caught) and never leaves fewer
+ * than 32 k-mers (one full warp round).  A sample is only ever probed for ONE step: with few k-mers per pair, further
+ * steps are dependent round trips with ever fewer probes in flight (measured: 66 G probes/s instead of 250). */
+static uint32_t plan_choose(double f, uint32_t K, uint64_t n_nominal, double allowed, double below, uint32_t *stride_out,
+                            double *cost_out) {
+    uint32_t best_s = 0, best_t = 1;
     double best = below;
-    for (uint32_t s = 1; s <= K; ++s) {
-        const double c = plan_probe_cost(f, s) + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(n, allowed, f, s)) * below;
-        if (c < best) {
-            best = c;
-            best_s = s;
+    const double n = (double)n_nominal;
+    for (uint32_t t = 1; t <= 8; t *= 2) {
+        const uint64_t n_s = n_nominal / t;
+        if (t > 1 && n_s < 32) break;
+        const double ns = (double)(n_s ? n_s : 1), frac = ns / n;
+        for (uint32_t s = 1; s <= (t > 1 ? 1u : K); ++s) { /* a sample is probed for one step only, see above */
+            const double c = plan_probe_cost(f, s) * frac + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(ns, allowed, f, s)) * below;
+            if (c < best) {
+                best = c;
+                best_s = s;
+                best_t = t;
+            }
         }
     }
+    *stride_out = best_s ? best_t : 1;
     *cost_out = best;
     return best_s;
 }
@@ -452,13 +469,15 @@ static uint64_t host_need(float threshold, uint64_t n) {
     if (c >= 18446744073709551616.0f) return ~0ULL;
     return (uint64_t)c;
 }
-static void plan_steps(pf_db *db, float threshold, uint64_t n_nominal, std::vector<uint32_t> &steps) {
+static void plan_steps(pf_db *db, float threshold, uint64_t n_nominal, std::vector<uint32_t> &steps,
+                       std::vector<uint32_t> &strides) {
     const uint32_t K = db->geom.num_hashes;
     const size_t nn = db->n_nodes;
     const uint64_t need = host_need(threshold, n_nominal);
     const double n = (double)n_nominal, allowed = need > n_nominal ? 0.0 : (double)(n_nominal - need);
     std::vector<double> cost(nn, 0.0);
     steps.assign(nn, K);
+    strides.assign(nn, 1);
     for (size_t u = nn; u-- > 0;) {  // children have larger level-order ids than their parent
         const double f = (double)db->h_pop[u] / (double)db->geom.num_bits;
         const uint32_t l = db->h_left[u], r = db->h_right[u];
@@ -471,7 +490,7 @@ static void plan_steps(pf_db *db, float threshold, uint64_t n_nominal, std::vect
             steps[u] = K;
             cost[u] = plan_exact_cost(f, K, n, allowed, below);
         } else {
-            steps[u] = plan_choose(f, K, n, allowed, below, &cost[u]);
+            steps[u] = plan_choose(f, K, n_nominal, allowed, below, &strides[u], &cost[u]);
         }
     }
 }
@@ -480,7 +499,8 @@ int pf::update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
     if (mode == db->steps_mode && (mode != 1 || (threshold == db->steps_theta && n_nominal == db->steps_n))) return PF_OK;
     const uint32_t K = db->geom.num_hashes;
     db->h_steps.assign(db->n_nodes, K);
-    if (mode == 1) plan_steps(db, threshold, n_nominal, db->h_steps);
+    db->h_stride.assign(db->n_nodes, 1);
+    if (mode == 1) plan_steps(db, threshold, n_nominal, db->h_steps, db->h_stride);
     // entry nodes: descend from the root through skipped (0-step) interior nodes; level-order ids are already
     // sorted by level, so a sorted list is grouped by level
     db->h_entry.clear();
@@ -512,7 +532,10 @@ int pf::update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
         while (e < db->h_entry.size() && db->h_entry[e] < db->level_start[l + 1]) ++e;
         db->entry_start[l + 1] = (uint32_t)e;
     }
-    PF_CUDA_OK(cudaMemcpyAsync(db->d_steps, db->h_steps.data(), db->n_nodes * 4, cudaMemcpyHostToDevice, db->stream));
+    // device plan: steps | stride << 8 (stride 1 = every k-mer)
+    std::vector<uint32_t> enc(db->n_nodes);
+    for (size_t u = 0; u < db->n_nodes; ++u) enc[u] = db->h_steps[u] | (db->h_stride[u] << 8);
+    PF_CUDA_OK(cudaMemcpyAsync(db->d_steps, enc.data(), db->n_nodes * 4, cudaMemcpyHostToDevice, db->stream));
     PF_CUDA_OK(cudaMemcpyAsync(db->d_entry, db->h_entry.data(), db->h_entry.size() * 4, cudaMemcpyHostToDevice, db->stream));
     PF_CUDA_OK(cudaStreamSynchronize(db->stream));
     db->steps_mode = mode;
@@ -640,7 +663,8 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         a.filters = db->d_filters;
         a.words_per_filter = db->wpf;
         a.pass = db->pass.p;
-        a.node_pass = db->d_node_pass;
+        a.node_pass = db->d_node_pass_copies;
+        a.n_nodes = (uint32_t)db->n_nodes;
         a.work_ctr = db->d_work + l;
         a.probes = db->d_probes;
         a.hp = db->hp;
@@ -654,7 +678,8 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         st.probe_launches++;
         st.pairs += n;
         st.levels++;
-        level_scan_kernel<<<1, 1024, 0, s>>>(db->level_start[l], db->level_start[l + 1], db->d_node_pass, db->d_left,
+        level_scan_kernel<<<1, 1024, 0, s>>>(db->level_start[l], db->level_start[l + 1], db->d_node_pass_copies,
+                                             (uint32_t)db->n_nodes, db->d_node_pass, db->d_left,
                                              db->d_right, db->d_leaf, db->d_next_base, db->d_hit_base,
                                              db->d_blk_counts, db->d_totals, db->d_probes);
         st.other_launches++;
@@ -769,7 +794,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         const uint64_t kmer_base = one_chunk ? 0 : ko[r0];
         if ((rc = db->hb.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
         if (db->hp.small_m && (rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
-        PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, 2 * db->n_nodes * 4, s));
+        PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, (2 + NODE_PASS_COPIES) * db->n_nodes * 4, s));
         PF_CUDA_OK(cudaMemsetAsync(db->d_work, 0, db->level_start.size() * 4, s));
         HashArgs h{};
         h.lengths = bt->lengths.p;
@@ -987,11 +1012,15 @@ int pf_db_set_lazy(pf_db *db, int on) {
     return PF_OK;
 }
 int pf_db_node_steps(pf_db *db, float threshold, uint64_t nominal_kmers, uint32_t *steps) {
-    if (!db || !steps) return PF_ERR_ARG;
+    return pf_db_node_plan(db, threshold, nominal_kmers, steps, nullptr);
+}
+int pf_db_node_plan(pf_db *db, float threshold, uint64_t nominal_kmers, uint32_t *steps, uint32_t *strides) {
+    if (!db || (!steps && !strides)) return PF_ERR_ARG;
     PF_CUDA_OK(cudaSetDevice(db->device));
     int rc = update_steps(db, threshold, nominal_kmers ? nominal_kmers : 1);
     if (rc != PF_OK) return rc;
-    memcpy(steps, db->h_steps.data(), db->n_nodes * 4);
+    if (steps) memcpy(steps, db->h_steps.data(), db->n_nodes * 4);
+    if (strides) memcpy(strides, db->h_stride.data(), db->n_nodes * 4);
     return PF_OK;
 }
 
