@@ -160,6 +160,8 @@ typedef struct pf_stats_t {
     double probe_kernel_ms;   /* CUDA-event time summed over probe launches */
     double device_ms;         /* CUDA-event time of the query calls, first launch to last */
     uint64_t group_rounds;    /* rounds of 32 k-mers each lane owned at once in the last call (1..8) */
+    uint64_t memo_hits;       /* k-mers answered by the k-mer memo instead of K - 1 probes (pf_db_set_memo) */
+    uint64_t memo_lookups;    /* k-mers looked up in the memo (one 8-byte read each) */
 } pf_stats_t;
 int pf_get_stats(pf_db *db, pf_stats_t *out);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can
@@ -174,6 +176,13 @@ int pf_db_set_exhaustive(pf_db *db, int on);
  * instead of the exact one; leaves and unverified nodes stay exact, so results are identical.
  * 0: every node is evaluated exactly (the frontier then equals the reference's, query.rs:113-141). */
 int pf_db_set_lazy(pf_db *db, int on);
+/* 1 (default): k-mer memo at exact nodes.  BloomFilter::contains depends on a k-mer only through its 64-bit
+ * hash_bytes value, so once a k-mer has passed all K probes at a node, every later occurrence of the same value at that
+ * node within the block (sequencing depth: 30x in BASELINE config 2) is a hit after ONE table look-up instead of K - 1
+ * further probes.  Exact (a table entry is the full 64-bit value, tables are per node and zeroed per level and block),
+ * so results do not change; the number of probes issued then depends on timing, which is why the work-count parity
+ * tests switch it off.  budget_bytes = 0 keeps the current budget (default 256 MiB). */
+int pf_db_set_memo(pf_db *db, int on, uint64_t budget_bytes);
 /* hash_bytes of every k-mer is computed once per batch and cached in HBM (8 B per k-mer); a batch whose
  * cache would exceed `bytes` (default 16 GiB) is processed in several chunks of reads. */
 int pf_db_set_hash_cache_bytes(pf_db *db, uint64_t bytes);

@@ -55,6 +55,7 @@ class Stats(C.Structure):
         ("levels", C.c_uint64), ("probe_launches", C.c_uint64), ("other_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("probe_kernel_ms", C.c_double), ("device_ms", C.c_double), ("group_rounds", C.c_uint64),
+        ("memo_hits", C.c_uint64), ("memo_lookups", C.c_uint64),
     ]
 
 
@@ -99,6 +100,7 @@ SYMBOLS = {
     "pf_db_stream": (_VP, [_VP]),
     "pf_db_set_exhaustive": (C.c_int, [_VP, C.c_int]),
     "pf_db_set_lazy": (C.c_int, [_VP, C.c_int]),
+    "pf_db_set_memo": (C.c_int, [_VP, C.c_int, C.c_uint64]),
     "pf_db_set_hash_cache_bytes": (C.c_int, [_VP, C.c_uint64]),
     "pf_db_node_steps": (C.c_int, [_VP, C.c_float, C.c_uint64, C.POINTER(C.c_uint32)]),
     "pf_db_node_plan": (C.c_int, [_VP, C.c_float, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

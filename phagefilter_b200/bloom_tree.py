@@ -100,6 +100,10 @@ class BloomTree:
     def set_hash_cache_bytes(self, nbytes: int) -> None:
         _lib.check(_lib.lib().pf_db_set_hash_cache_bytes(self._h, nbytes))
 
+    def set_memo(self, on: bool, budget_bytes: int = 0) -> None:
+        """k-mer memo at exact nodes (pf_db_set_memo): same results, fewer probes on deep-coverage batches."""
+        _lib.check(_lib.lib().pf_db_set_memo(self._h, int(on), budget_bytes))
+
     def set_lazy(self, on: bool) -> None:
         _lib.check(_lib.lib().pf_db_set_lazy(self._h, int(on)))
 

@@ -186,6 +186,15 @@ struct pf_db {
     uint64_t steps_n = 0;  // nominal k-mers per read the plan was made for
     int steps_mode = -1;
     uint64_t n_internal = 0, n_monotone = 0;
+    // k-mer memo of exact nodes (see ProbeArgs::memo): regions are handed out per level, zeroed before the level runs
+    int memo = 1;
+    uint64_t memo_budget_bytes = 256ULL << 20;
+    std::vector<uint32_t> h_node_memo;          // per node: region index inside its level, or NONE32
+    std::vector<uint32_t> level_memo_regions;   // per level: regions in use
+    std::vector<uint32_t> level_memo_entries;   // per level: entries of all its regions / 4096, 0 = memo off
+    std::vector<uint64_t> level_memo_kmers;     // per level: k-mers held by the filters of its memo nodes (set bits / K)
+    uint32_t *d_node_memo = nullptr;
+    DevBuf<unsigned long long> memo_table;
     // device tree
     uint32_t *d_left = nullptr, *d_right = nullptr, *d_slot = nullptr;
     int32_t *d_leaf = nullptr;
@@ -233,6 +242,7 @@ struct Descent {
     uint64_t n = 0;  // pairs in the current frontier
     int cur = 0;     // ping-pong buffer holding it
     uint64_t hits_total = 0, hits_before = 0, probes = 0, pairs = 0, levels = 0, probe_launches = 0, other_launches = 0;
+    uint64_t memo_hits = 0, memo_lookups = 0;
     size_t n_ev = 0;
 };
 int run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint32_t G, uint64_t kmer_base,

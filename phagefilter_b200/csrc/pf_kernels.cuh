@@ -136,6 +136,12 @@ struct ProbeArgs {
     HashParams hp;
     float threshold;
     int exhaustive;
+    // k-mer memo of the exact nodes of this level (null = off): one power-of-two region of entries per exact node,
+    // node_memo[u] = (first entry / 4096) << 5 | log2(entries), or NONE32.  An entry holds hash_bytes(k-mer) of a k-mer that passed all K probes at
+    // that node; contains() depends on the k-mer only through that value, so a match is exact, never probabilistic.
+    unsigned long long *memo;
+    const uint32_t *node_memo;
+    uint32_t order_streams, order_span;  // chunk order: ticket c -> chunk (c % streams) * span + c / streams
 };
 
 // (threshold * n_k as f32).ceil() as usize   (query.rs:48): f32 product, ceil, saturating cast.
@@ -219,7 +225,8 @@ template <int G, bool SMALL_M>
 PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, uint32_t n_steps,
                       const uint64_t *__restrict__ hbp, const uint32_t *__restrict__ i0p, uint32_t gbase, uint32_t n_k,
                       uint32_t lane, uint32_t need, uint32_t allowed, bool exhaustive, uint32_t stride, uint32_t off,
-                      int pre, uint32_t &hits, uint32_t &misses, uint32_t &probes, bool &pass) {
+                      int pre, unsigned long long *memo, uint32_t memo_mask, uint32_t &hits, uint32_t &misses,
+                      uint32_t &probes, uint32_t &memo_hits, uint32_t &memo_lookups, bool &pass) {
     // pre >= 0: step 0 of the first round was already done for the whole chunk of pairs (probe_kernel); pre is this
     // lane's result (1 = its k-mer's bit was clear)
     const uint32_t kidx = off + (gbase + lane) * stride, kstep = 32u * stride;  // k-mer of slot j: kidx + j*kstep
@@ -290,13 +297,35 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
         }
     }
     if (n_steps > 1u && cnt - dead != 0u) {
+        // Exact node with a memo: a k-mer that survived step 0 and whose hash_bytes value is in the node's memo has
+        // already passed all K probes here for another read of the batch (sequencing depth) -- it is a hit without
+        // further probes.  It leaves `alive` without being counted dead.
+        uint32_t known = 0;
+        if (memo) {
+            uint32_t found = 0;
+            unsigned long long e[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                e[j] = 0;
+                if ((st.alive >> j) & 1u) e[j] = __ldcg(memo + ((uint32_t)(hb[j] >> 20) & memo_mask));
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (e[j] == hb[j] && hb[j] != 0ULL && ((st.alive >> j) & 1u)) {
+                    st.alive &= ~(1u << j);
+                    ++found;
+                }
+            known = __reduce_add_sync(0xFFFFFFFFu, found);
+            memo_hits += known;
+            memo_lookups += cnt - dead;
+        }
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             st.h1[j] = fx_finish(hp.c1, hb[j], hp.rot);
             st.h2[j] = fx_finish(hp.c2, hb[j], hp.rot);
         }
         for (uint32_t i = 1; i < n_steps; ++i) {
-            const uint32_t n_alive = cnt - dead;
+            const uint32_t n_alive = cnt - dead - known;
             if (n_alive == 0u) break;
             probes += n_alive;
 #pragma unroll
@@ -307,6 +336,15 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
                 pass = false;
                 return true;
             }
+        }
+        if (memo) {  // what is still alive passed all K probes: remember it (the value is fetched again rather than
+                     // kept in registers across the step loop)
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if ((st.alive >> j) & 1u) {
+                    const unsigned long long v = __ldg(hbp + kidx + (uint32_t)j * kstep);
+                    if (v != 0ULL) __stcg(memo + ((uint32_t)(v >> 20) & memo_mask), v);
+                }
         }
     }
     misses += dead;
@@ -319,13 +357,14 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
 }
 
 struct PairMeta {
-    uint32_t r, u, len, slot, steps;
+    uint32_t r, u, len, slot, steps, memo;
     uint64_t koff;
 };
 
 // Evaluate one (read,node) pair; warp-uniform control flow.  Returns pass/fail (query_passes).
 template <int G, bool SMALL_M>
-PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int pre, uint32_t &probes) {
+PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int pre, uint32_t &probes, uint32_t &memo_hits,
+                     uint32_t &memo_lookups) {
     const HashParams &hp = a.hp;
     const uint32_t n_k = kmers_of(pm.len, hp.k);
     const uint32_t need = need_of(a.threshold, n_k);
@@ -349,9 +388,12 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int 
     const uint32_t *i0p = a.idx0 + (pm.koff - a.kmer_base);
     uint32_t hits = n_k - n_s, misses = 0;
     bool pass = false;
+    // node_memo: (first entry / 4096) << 5 | log2(entries) of the node's region
+    unsigned long long *memo = (a.memo && pm.memo != NONE32_D) ? a.memo + ((size_t)(pm.memo >> 5) << 12) : nullptr;
+    const uint32_t memo_mask = (1u << (pm.memo & 31u)) - 1u;
     for (uint32_t gbase = 0; gbase < n_s; gbase += 32u * G)
         if (probe_group<G, SMALL_M>(filt, hp, n_steps, hbp, i0p, gbase, n_s, lane, need, allowed, exhaustive, stride, off,
-                                    gbase == 0u ? pre : -1, hits, misses, probes, pass))
+                                    gbase == 0u ? pre : -1, memo, memo_mask, hits, misses, probes, memo_hits, memo_lookups, pass))
             return pass;
     return hits >= need;
 }
@@ -365,12 +407,21 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
     uint32_t *const np_mine = a.node_pass + (size_t)(blockIdx.x % NODE_PASS_COPIES) * a.n_nodes;
     uint32_t probes = 0;      // warp-uniform: probes of the per-pair path
     uint32_t my_probes = 0;   // per lane: probes of the pairs this lane settled after the batched first round
-    unsigned long long probes_total = 0;
+    uint32_t memo_hits = 0, memo_lookups = 0;  // warp-uniform: k-mers answered by / looked up in the memo
+    unsigned long long probes_total = 0, memo_total = 0, lookup_total = 0;
     for (;;) {
         uint32_t i0 = 0;
         if (lane == 0) i0 = atomicAdd(a.work_ctr, (unsigned)PROBE_CHUNK);
         i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
-        if (i0 >= a.n_pairs) break;
+        if (a.order_streams > 1u) {
+            // memo levels: consecutive tickets go to chunks far apart in the node-major frontier, so the pairs of one
+            // node are spread over time instead of all being in flight at once (the memo can only answer what an
+            // EARLIER pair of the node has stored); order_streams bounds how many nodes are then live in L2 together
+            const uint32_t c = i0 / PROBE_CHUNK;
+            if (c >= a.order_streams * a.order_span) break;
+            i0 = ((c % a.order_streams) * a.order_span + c / a.order_streams) * PROBE_CHUNK;
+            if (i0 >= a.n_pairs) continue;
+        } else if (i0 >= a.n_pairs) break;
         const uint32_t n_here = min((uint32_t)PROBE_CHUNK, a.n_pairs - i0);
         PairMeta mine{};
         if (lane < n_here) {
@@ -380,6 +431,7 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
             mine.koff = __ldg(a.kmer_off + mine.r);
             mine.slot = ldg32(a.node_slot + mine.u);
             mine.steps = ldg32(a.node_steps + mine.u);
+            mine.memo = a.memo ? ldg32(a.node_memo + mine.u) : NONE32_D;
         }
         // Step 0 of the first round (up to 32 k-mers) of EVERY pair of the chunk, batched: PROBE_CHUNK index loads,
         // then PROBE_CHUNK gathers in flight per lane, instead of two dependent round trips per pair.  That round
@@ -458,7 +510,9 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
             pm.slot = __shfl_sync(0xFFFFFFFFu, mine.slot, p);
             pm.steps = __shfl_sync(0xFFFFFFFFu, mine.steps, p);
             pm.koff = __shfl_sync(0xFFFFFFFFu, mine.koff, p);
-            if (probe_pair<G, SMALL_M>(a, pm, lane, SMALL_M ? (int)((miss_bits >> p) & 1u) : -1, probes)) pass_bits |= 1u << p;
+            pm.memo = __shfl_sync(0xFFFFFFFFu, mine.memo, p);
+            if (probe_pair<G, SMALL_M>(a, pm, lane, SMALL_M ? (int)((miss_bits >> p) & 1u) : -1, probes, memo_hits, memo_lookups))
+                pass_bits |= 1u << p;
         }
         // survivors per node: the frontier is node-major, so at any moment most warps of the GPU count into the same
         // node; same-address atomics serialise in L2 (measured: 1 M of them cost ~0.5 ms), so the counter is kept in
@@ -467,10 +521,15 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
         if (lane < n_here) a.pass[i0 + lane] = pass ? 1 : 0;
         if (pass) atomicAdd(np_mine + mine.u, 1u);
         probes_total += probes + __reduce_add_sync(0xFFFFFFFFu, my_probes);
+        memo_total += memo_hits;
+        lookup_total += memo_lookups;
         probes = 0;
         my_probes = 0;
+        memo_hits = memo_lookups = 0;
     }
     if (lane == 0 && probes_total) atomicAdd(a.probes, probes_total);
+    if (lane == 0 && memo_total) atomicAdd(a.probes + 1, memo_total);
+    if (lane == 0 && lookup_total) atomicAdd(a.probes + 2, lookup_total);
 }
 
 // ---- frontier bookkeeping ------------------------------------------------------------------
@@ -488,10 +547,11 @@ static __global__ void inject_frontier_kernel(uint32_t *fr_read, uint32_t *fr_no
 }
 
 struct LevelTotals {
+    unsigned long long memo_lookups;  // k-mers looked up in the memo (one 8-byte read each)
     unsigned long long next_pairs;
     unsigned long long hits_total;  // running total of (read,leaf) hits in this block
     unsigned long long probes;
-    unsigned long long pad;
+    unsigned long long memo_hits;  // k-mers answered by the memo instead of K - 1 probes
 };
 
 // One block.  For the nodes [lo,hi) of the current level: exclusive scan of the surviving pair counts
@@ -533,7 +593,9 @@ static __global__ void level_scan_kernel(uint32_t lo, uint32_t hi, const uint32_
         }
         totals->next_pairs = an;
         totals->hits_total = ah;
-        totals->probes = *probes;
+        totals->probes = probes[0];
+        totals->memo_hits = probes[1];
+        totals->memo_lookups = probes[2];
     }
     __syncthreads();
     unsigned long long an = s_next[t], ah = s_hit[t];
@@ -721,6 +783,11 @@ static __global__ void csr_sort_kernel(const unsigned long long *__restrict__ of
         }
         out_leaf[j] = x;
     }
+}
+
+static __global__ void zero_kernel(uint4 *p, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 static __global__ void add_counts_kernel(unsigned long long *dst, const unsigned long long *src, uint32_t n) {

@@ -87,6 +87,8 @@ void pf::db_free(pf_db *db) {
     cudaFree(db->d_hit_base);
     cudaFree(db->d_work);
     cudaFree(db->d_probes);
+    cudaFree(db->d_node_memo);
+    db->memo_table.release();
     cudaFree(db->d_totals);
     if (db->h_totals) cudaFreeHost(db->h_totals);
     for (int i = 0; i < 2; i++) {
@@ -303,7 +305,8 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     PF_CUDA_OK(cudaMalloc(&db->d_next_base, nn * 8));
     PF_CUDA_OK(cudaMalloc(&db->d_hit_base, nn * 8));
     PF_CUDA_OK(cudaMalloc(&db->d_work, nlev * 4));
-    PF_CUDA_OK(cudaMalloc(&db->d_probes, 8));
+    PF_CUDA_OK(cudaMalloc(&db->d_probes, 24));  // [probes issued, k-mers answered by the memo, memo look-ups]
+    PF_CUDA_OK(cudaMalloc(&db->d_node_memo, nn * 4));
     PF_CUDA_OK(cudaMalloc(&db->d_totals, sizeof(LevelTotals)));
     PF_CUDA_OK(cudaMallocHost(&db->h_totals, sizeof(LevelTotals)));
     PF_CUDA_OK(cudaMemsetAsync(db->d_counts, 0, nl * 8, db->stream));
@@ -533,6 +536,42 @@ int pf::update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
         db->entry_start[l + 1] = (uint32_t)e;
     }
     // device plan: steps | stride << 8 (stride 1 = every k-mer)
+    // memo regions: every exact multi-step node of a level gets a power-of-two region of about twice the k-mers its
+    // filter holds (set bits / K), 2^12 .. 2^18 entries of 8 B; a level whose regions exceed the budget runs without
+    {
+        db->h_node_memo.assign(db->n_nodes, NONE32);
+        db->level_memo_regions.assign(n_levels, 0);
+        db->level_memo_entries.assign(n_levels, 0);
+        db->level_memo_kmers.assign(n_levels, 0);
+        for (size_t l = 0; l < n_levels && db->memo && mode != 2 && K > 1; ++l) {
+            uint64_t total = 0, kmers = 0;
+            uint32_t cnt = 0;
+            auto log2_entries = [&](uint32_t u) {
+                const uint64_t want = 2 * (db->h_pop[u] / K);
+                uint32_t lg = 12;
+                while (lg < 18 && (1ULL << lg) < want) ++lg;
+                return lg;
+            };
+            for (uint32_t u = db->level_start[l]; u < db->level_start[l + 1]; ++u)
+                if (db->h_steps[u] == K && db->h_slot[u] != NONE32) {
+                    total += 1ULL << log2_entries(u);
+                    kmers += db->h_pop[u] / K;
+                    ++cnt;
+                }
+            if (!cnt || total * 8 > db->memo_budget_bytes || (total >> 12) >= (1ULL << 27)) continue;
+            uint64_t off = 0;
+            for (uint32_t u = db->level_start[l]; u < db->level_start[l + 1]; ++u)
+                if (db->h_steps[u] == K && db->h_slot[u] != NONE32) {
+                    const uint32_t lg = log2_entries(u);
+                    db->h_node_memo[u] = (uint32_t)((off >> 12) << 5) | lg;
+                    off += 1ULL << lg;
+                }
+            db->level_memo_regions[l] = cnt;
+            db->level_memo_kmers[l] = kmers;
+            db->level_memo_entries[l] = (uint32_t)(total >> 12);  // in units of 4096 entries
+        }
+        PF_CUDA_OK(cudaMemcpyAsync(db->d_node_memo, db->h_node_memo.data(), db->n_nodes * 4, cudaMemcpyHostToDevice, db->stream));
+    }
     std::vector<uint32_t> enc(db->n_nodes);
     for (size_t u = 0; u < db->n_nodes; ++u) enc[u] = db->h_steps[u] | (db->h_stride[u] << 8);
     PF_CUDA_OK(cudaMemcpyAsync(db->d_steps, enc.data(), db->n_nodes * 4, cudaMemcpyHostToDevice, db->stream));
@@ -609,6 +648,8 @@ void pf::account_stats(pf_db *db, const Descent &st, uint64_t n_reads, uint64_t 
     db->stats.reads += n_reads;
     db->stats.pairs += st.pairs;
     db->stats.probes_issued += st.probes;
+    db->stats.memo_hits += st.memo_hits;
+    db->stats.memo_lookups += st.memo_lookups;
     db->stats.levels += st.levels;
     db->stats.probe_launches += st.probe_launches;
     db->stats.other_launches += st.other_launches;
@@ -670,6 +711,20 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         a.hp = db->hp;
         a.threshold = threshold;
         a.exhaustive = db->exhaustive;
+        // the memo pays when the level's pairs bring each k-mer of its exact nodes several times (sequencing depth):
+        // instances = pairs x k-mers per read against the k-mers those filters hold
+        if (db->level_memo_entries[l] && (double)n * (double)bt->nominal_kmers >= 4.0 * (double)db->level_memo_kmers[l]) {
+            const size_t words = (size_t)db->level_memo_entries[l] << 12;
+            if ((rc = db->memo_table.ensure(words))) return rc;
+            zero_kernel<<<db->sm_count * 8, 256, 0, s>>>(reinterpret_cast<uint4 *>(db->memo_table.p), words / 2);
+            st.other_launches++;
+            a.memo = db->memo_table.p;
+            a.node_memo = db->d_node_memo;
+            // chunk order: up to 8 nodes of the level are worked on at the same time
+            const uint32_t n_chunks = (uint32_t)((n + PROBE_CHUNK - 1) / PROBE_CHUNK);
+            a.order_streams = std::max(1u, std::min(8u, db->level_memo_regions[l]));
+            a.order_span = (n_chunks + a.order_streams - 1) / a.order_streams;
+        }
         if ((rc = ensure_events(db, st.n_ev + 2))) return rc;
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev], s));
         launch_probe(a, G, db->sm_count, s);
@@ -688,6 +743,8 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         const uint64_t next_n = db->h_totals->next_pairs;
         st.hits_total = db->h_totals->hits_total;
         st.probes = db->h_totals->probes;
+        st.memo_hits = db->h_totals->memo_hits;
+        st.memo_lookups = db->h_totals->memo_lookups;
         if (next_n > 0xFFFFFFF0ULL) {
             set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
                       (unsigned long long)next_n);
@@ -769,7 +826,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     if ((rc = update_steps(db, threshold, bt->nominal_kmers))) return rc;
     PF_CUDA_OK(cudaEventRecord(db->ev_begin, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_blk_counts, 0, std::max<uint64_t>(db->n_leaves, 1) * 8, s));
-    PF_CUDA_OK(cudaMemsetAsync(db->d_probes, 0, 8, s));
+    PF_CUDA_OK(cudaMemsetAsync(db->d_probes, 0, 24, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_totals, 0, sizeof(LevelTotals), s));
     if (want_hits) {
         if ((rc = db->read_hits.ensure(n_reads))) return rc;
@@ -1004,6 +1061,13 @@ int pf_db_set_exhaustive(pf_db *db, int on) {
 int pf_db_set_hash_cache_bytes(pf_db *db, uint64_t bytes) {
     if (!db || bytes < 8) return PF_ERR_ARG;
     db->hash_cache_bytes = bytes;
+    return PF_OK;
+}
+int pf_db_set_memo(pf_db *db, int on, uint64_t budget_bytes) {
+    if (!db) return PF_ERR_ARG;
+    db->memo = on ? 1 : 0;
+    if (budget_bytes) db->memo_budget_bytes = budget_bytes;
+    db->steps_mode = -1;  // regions are part of the plan
     return PF_OK;
 }
 int pf_db_set_lazy(pf_db *db, int on) {

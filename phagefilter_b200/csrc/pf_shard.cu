@@ -436,7 +436,7 @@ static int query_sharded_impl(pf_db *db, const pf_dev_batch *local, float thresh
         PF_CUDA_OK(cudaStreamSynchronize(s));  // rb32 is a pageable temporary
     }
     PF_CUDA_OK(cudaMemsetAsync(db->d_blk_counts, 0, std::max<uint64_t>(db->n_leaves, 1) * 8, s));
-    PF_CUDA_OK(cudaMemsetAsync(db->d_probes, 0, 8, s));
+    PF_CUDA_OK(cudaMemsetAsync(db->d_probes, 0, 24, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_totals, 0, sizeof(LevelTotals), s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, (2 + NODE_PASS_COPIES) * db->n_nodes * 4, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_work, 0, db->level_start.size() * 4, s));

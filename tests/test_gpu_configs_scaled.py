@@ -15,10 +15,21 @@ def _check(oracle, ot, gt, reads, theta):
     gt.reset_counts()
     gt.reset_stats()
     want = ot.query_batch(reads, theta)
+    sched = ot.query_sched(reads, theta, lazy=True)
+    # default: k-mer memo on -- same results and pairs, at most the scheduled probes (how many depends on timing)
     got = gpu_query(gt, reads, theta)
     assert got == want.hit_sets(len(reads))
     assert get_leaf_counts(gt) == ot.leaf_counts()
-    sched = ot.query_sched(reads, theta, lazy=True)
+    st = gt.stats()
+    assert st.pairs == sched.pairs and st.probes_issued <= sched.probes_sched
+    # memo off: the kernel's work is exactly its restatement's
+    gt.set_memo(False)
+    gt.reset_counts()
+    gt.reset_stats()
+    got = gpu_query(gt, reads, theta)
+    gt.set_memo(True)
+    assert got == want.hit_sets(len(reads))
+    assert get_leaf_counts(gt) == ot.leaf_counts()
     st = gt.stats()
     assert (st.pairs, st.probes_issued) == (sched.pairs, sched.probes_sched)
     return want, st

@@ -28,20 +28,26 @@ def _compare(oracle, otree, gtree, reads, theta, check_probes=True):
     ores = otree.query_batch(reads, theta)  # the reference's semantics
     want = ores.hit_sets(len(reads))
     ghits = None
-    for lazy in (True, False):
+    for lazy, memo in ((True, True), (True, False), (False, True), (False, False)):
         gtree.reset_counts()
         gtree.reset_stats()
         gtree.set_exhaustive(False)
         gtree.set_lazy(lazy)
+        gtree.set_memo(memo)
         ghits = gpu_query(gtree, reads, theta)
-        assert ghits == want, f"lazy={lazy}"
+        assert ghits == want, f"lazy={lazy} memo={memo}"
         assert get_leaf_counts(gtree) == otree.leaf_counts()
         if check_probes:
-            # the oracle's restatement of the kernel schedule predicts the kernel's work exactly
+            # the oracle's restatement of the kernel schedule predicts the kernel's work exactly (with the k-mer
+            # memo the probes actually issued depend on timing and can only be fewer)
             sched = otree.query_sched(reads, theta, lazy=lazy)
             assert sched.hit_sets(len(reads)) == want
             st = gtree.stats()
-            assert (st.pairs, st.probes_issued) == (sched.pairs, sched.probes_sched), f"lazy={lazy}"
+            if memo:
+                assert st.pairs == sched.pairs and st.probes_issued <= sched.probes_sched, f"lazy={lazy}"
+            else:
+                assert (st.pairs, st.probes_issued) == (sched.pairs, sched.probes_sched), f"lazy={lazy}"
+    gtree.set_memo(True)
     if check_probes:
         # reference-faithful probing: every k-mer of every pair until its first clear bit
         gtree.reset_counts()
@@ -295,4 +301,35 @@ def test_chunked_hash_cache(oracle, tmp_path):
     for budget in (8 * 131 * 7, 8, 1 << 30):  # ~7 reads per chunk; one read per chunk; everything at once
         gt.set_hash_cache_bytes(budget)
         _compare(oracle, ot, gt, reads, 0.8)
+    gt.close()
+
+
+def test_kmer_memo_deep_coverage(oracle, tmp_path):
+    """30x coverage of a few genomes: k-mers at the leaves are answered by the memo; results are unchanged,
+    with a tiny memo (evictions) as with the default one, at -f 1.0 and 0.8, with reads holding non-ACGT bytes."""
+    from phagefilter_b200 import BloomTree
+    from phagefilter_b200.query import get_leaf_counts
+    from phagefilter_b200.synth import make_genomes, simulate_reads
+    genomes = make_genomes(3, 4, seed=99, len_lo=4000, len_hi=6000)
+    d = str(tmp_path / "db")
+    ot = oracle_build_db(oracle, genomes, 20, d, largest=8000)
+    gt = BloomTree.load(d)
+    reads, _ = simulate_reads(genomes, 12000, 150, seed=7, error_rates=(0.0, 0.01))
+    rl = [r.tobytes() for r in reads] + [genomes[0][1][10:160].lower(), genomes[1][1][:150].replace(b"C", b"N", 2)]
+    for theta in (1.0, 0.8):
+        ot.reset_counts()
+        want = ot.query_batch(rl, theta)
+        sched = ot.query_sched(rl, theta, lazy=True)
+        for budget in (0, 12 * 4096 * 8):  # default budget, then the smallest regions
+            gt.set_memo(True, budget)
+            gt.reset_counts()
+            gt.reset_stats()
+            assert gpu_query(gt, rl, theta) == want.hit_sets(len(rl))
+            assert get_leaf_counts(gt) == ot.leaf_counts()
+            st = gt.stats()
+            assert st.pairs == sched.pairs
+            # how many k-mers the memo answers depends on timing (a pair only profits from pairs that finished
+            # before it); with 12,000 reads nearly all of them are in flight at once, so only demand some
+            assert st.memo_hits > 0.05 * 131 * len(want.hits)
+            assert st.probes_issued < sched.probes_sched
     gt.close()
