@@ -29,6 +29,14 @@ PF_D uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
 
 // number of k-mers of a read (file_parser.rs:136-139)
 PF_HD uint32_t kmers_of(uint32_t len, uint32_t k) { return (k == 0u || k > len) ? 0u : len - k + 1u; }
+// Slot of k-mer p in a read's idx0 cache: the k-mers are stored in four residue classes (p mod 4), each class
+// contiguous, so a stride-4 sample (the usual sampled pre-test) is one coalesced run -- 4 sectors per 32 lanes instead
+// of 16 -- while 32 consecutive k-mers still fall into four runs of 8 (4-8 sectors).
+// Classes c < r hold q4 k-mers, the others q4 - 1 (r = number of full classes), so the n_k slots are used exactly.
+PF_HD uint32_t idx0_slot(uint32_t p, uint32_t n_k) {
+    const uint32_t q4 = (n_k + 3u) >> 2, r = ((n_k - 1u) & 3u) + 1u, c = p & 3u;
+    return c * q4 - (c > r ? c - r : 0u) + (p >> 2);
+}
 
 // ---- hash_kernel ---------------------------------------------------------------------------------
 struct HashArgs {
@@ -92,7 +100,7 @@ static __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArg
                     const uint64_t hb = canonical_hash_2bit<(KM ? KM : 17)>(x);
                     if (base + lane < n_k) {
                         out[base + lane] = hb;
-                        if (out0) out0[base + lane] = mod_small(fx_finish(a.hp.c1, hb, a.hp.rot), M0, M1, m32);
+                        if (out0) out0[idx0_slot(base + lane, n_k)] = mod_small(fx_finish(a.hp.c1, hb, a.hp.rot), M0, M1, m32);
                     }
                     lo = hi;
                 }
@@ -103,7 +111,7 @@ static __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArg
                 for (uint32_t pos = lane; pos < n_k; pos += 32u) {
                     const uint64_t hb = canonical_hash_bytes([&](uint32_t j) { return src_byte(s, pos + j); }, a.k);
                     out[pos] = hb;
-                    if (out0) out0[pos] = mod_small(fx_finish(a.hp.c1, hb, a.hp.rot), M0, M1, m32);
+                    if (out0) out0[idx0_slot(pos, n_k)] = mod_small(fx_finish(a.hp.c1, hb, a.hp.rot), M0, M1, m32);
                 }
             }
         }
@@ -225,7 +233,7 @@ template <int G, bool SMALL_M>
 PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, uint32_t n_steps,
                       const uint64_t *__restrict__ hbp, const uint32_t *__restrict__ i0p, uint32_t gbase, uint32_t n_k,
                       uint32_t lane, uint32_t need, uint32_t allowed, bool exhaustive, uint32_t stride, uint32_t off,
-                      int pre, unsigned long long *memo, uint32_t memo_mask, uint32_t &hits, uint32_t &misses,
+                      int pre, uint32_t nk_full, unsigned long long *memo, uint32_t memo_mask, uint32_t &hits, uint32_t &misses,
                       uint32_t &probes, uint32_t &memo_hits, uint32_t &memo_lookups, bool &pass) {
     // pre >= 0: step 0 of the first round was already done for the whole chunk of pairs (probe_kernel); pre is this
     // lane's result (1 = its k-mer's bit was clear)
@@ -245,7 +253,7 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
         uint32_t idx[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) idx[j] = 0;
-        if (pre < 0 && (st.alive & 1u)) idx[0] = ldg32(i0p + kidx);
+        if (pre < 0 && (st.alive & 1u)) idx[0] = ldg32(i0p + idx0_slot(kidx, nk_full));
         if (n_steps > 1u) {
 #pragma unroll
             for (int j = 0; j < G; ++j)
@@ -267,7 +275,7 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
         if (G > 1 && cnt > 32u) {
 #pragma unroll
             for (int j = 1; j < G; ++j)
-                if ((st.alive >> j) & 1u) idx[j] = ldg32(i0p + kidx + (uint32_t)j * kstep);
+                if ((st.alive >> j) & 1u) idx[j] = ldg32(i0p + idx0_slot(kidx + (uint32_t)j * kstep, nk_full));
             probes += cnt - 32u;
             dead += __reduce_add_sync(0xFFFFFFFFu, probe_idx_phase<G, (G > 1 ? 1 : 0), G>(filt, idx, st.alive));
             if (!exhaustive && dead > limit) {
@@ -393,7 +401,8 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int 
     const uint32_t memo_mask = (1u << (pm.memo & 31u)) - 1u;
     for (uint32_t gbase = 0; gbase < n_s; gbase += 32u * G)
         if (probe_group<G, SMALL_M>(filt, hp, n_steps, hbp, i0p, gbase, n_s, lane, need, allowed, exhaustive, stride, off,
-                                    gbase == 0u ? pre : -1, memo, memo_mask, hits, misses, probes, memo_hits, memo_lookups, pass))
+                                    gbase == 0u ? pre : -1, n_k, memo, memo_mask, hits, misses, probes, memo_hits,
+                                    memo_lookups, pass))
             return pass;
     return hits >= need;
 }
@@ -443,7 +452,7 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
         if (SMALL_M) {
             // per pair: first-round slot count | stride << 8, or 0 when the pair needs no probe at all; and the k-mer
             // index of slot 0
-            uint32_t my_r0 = 0, my_nk = 0, my_need = 0, my_ns = 0;
+            uint32_t my_r0 = 0, my_nk = 0, my_need = 0, my_ns = 0, my_off = 0;
             uint64_t my_k0 = 0;
             bool my_decided = false;
             if (lane < n_here) {
@@ -461,15 +470,17 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
                     off = (my_nk - 1u - (my_ns - 1u) * stride) >> 1;
                 }
                 if (!my_decided && my_nk) my_r0 = min(32u, my_ns) | (stride << 8);
-                my_k0 = mine.koff - a.kmer_base + off;
+                my_k0 = mine.koff - a.kmer_base;
+                my_off = off | (my_nk << 8);  // first sampled k-mer (< 8) | n_k << 8
             }
             uint32_t idxv[PROBE_CHUNK], wv[PROBE_CHUNK];
 #pragma unroll
             for (int p = 0; p < PROBE_CHUNK; ++p) {
                 const uint32_t r0 = __shfl_sync(0xFFFFFFFFu, my_r0, p);
                 const uint64_t k0 = __shfl_sync(0xFFFFFFFFu, my_k0, p);
+                const uint32_t o4 = __shfl_sync(0xFFFFFFFFu, my_off, p);
                 idxv[p] = 0xFFFFFFFFu;
-                if (lane < (r0 & 0xFFu)) idxv[p] = ldg32(a.idx0 + k0 + lane * (r0 >> 8));
+                if (lane < (r0 & 0xFFu)) idxv[p] = ldg32(a.idx0 + k0 + idx0_slot((o4 & 0xFFu) + lane * (r0 >> 8), o4 >> 8));
             }
 #pragma unroll
             for (int p = 0; p < PROBE_CHUNK; ++p) {
