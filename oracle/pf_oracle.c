@@ -2,7 +2,9 @@
  * pf_oracle.c -- CPU ORACLE (test infrastructure; see pf_oracle.h header comment).
  *
  * Plain-C restatement of the reference's `query` path and of the `build` path needed to
- * create databases.  PARITY UNPINNED at the rustc-hash / bitvec-serde / bincode boundaries.
+ * create databases.  Pinning: the FxHasher restatement below is checked against a real rustc-hash 2.x
+ * build executed in this image (tests/test_hash_pin_cpu.py, via hashbrown bucket order of an
+ * FxHashMap<Vec<u8>,_>); PARITY UNPINNED at the bitvec-serde / bincode (file format) boundaries.
  * Citations are file:line relative to the reference root.
  */
 #define _GNU_SOURCE

@@ -12,9 +12,12 @@
  * (rustc-hash ^2.1, bitvec 1.0.1 + serde, bincode 1.3.3, bio 2.2.0); their published
  * algorithms are restated here.
  *
- * PARITY UNPINNED at the rustc-hash / bitvec-serde / bincode boundaries: the reference's
+ * PARITY UNPINNED at the bitvec-serde / bincode (file format) boundaries: the reference's
  * own tests hold no hash value, bit index or `.bf` byte image.
- * What IS pinned against the reference's tests: canonicalisation (file_parser.rs:396-407),
+ * The rustc-hash arithmetic IS pinned, against a real rustc-hash 2.x build executed in this
+ * image (tests/test_hash_pin_cpu.py: hashbrown bucket order of an FxHashMap<Vec<u8>,_> inside
+ * the outlines_core extension; 100 % agreement with finish() = rotate_left(26), chance level
+ * with 20).  Pinned against the reference's own tests: canonicalisation (file_parser.rs:396-407),
  * get_kmers windows (:380-393), the HashIter derivation (hash_iter.rs:75-90), filter
  * geometry (bloom_filter.rs:342-357), tree topology (bloom_tree.rs:458-734), query
  * semantics on the toy trees (query.rs:249-380) and get_ext_id strings (result_map.rs:78-103).

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package never imports this module.
-PARITY UNPINNED at the rustc-hash / bitvec-serde / bincode boundaries (see pf_oracle.h).
+PARITY UNPINNED at the bitvec-serde / bincode (file format) boundaries; the rustc-hash arithmetic is pinned against
+a real rustc-hash 2.x build by tests/test_hash_pin_cpu.py (see pf_oracle.h).
 """
 from __future__ import annotations
 
