@@ -94,6 +94,62 @@ def test_fxhasher_restatement_matches_real_rustc_hash(oracle, n_keys):
     assert agree20 < trials // 2, f"rotate 20 should be at chance level, got {agree20}/{trials}"
 
 
+def _capacity(buckets):
+    return buckets - 1 if buckets < 8 else buckets // 8 * 7
+
+
+def _buckets_for(cap):
+    if cap < 8:
+        return 4 if cap < 4 else 8
+    want, p = -(-cap * 8 // 7), 1
+    while p < want:
+        p *= 2
+    return p
+
+
+def _place_wide(slots, h):
+    """hashbrown's probe: the first free slot in the 16 control bytes starting at hash & mask, else the next window"""
+    n, pos, stride = len(slots), h & (len(slots) - 1), 0
+    while True:
+        for i in range(min(16, n)):
+            j = (pos + i) & (n - 1)
+            if slots[j] is None:
+                return j
+        stride += 16
+        pos = (pos + stride) & (n - 1)
+
+
+@pytest.mark.parametrize("n_keys,length", [(14, 20), (56, 21), (100, 31), (200, 20), (200, 33)])
+def test_fxhasher_low_byte_in_wide_tables(oracle, n_keys, length):
+    """Up to 200 keys -> 256 buckets: the iteration order now depends on the low 8 bits of every key's hash
+    (growth 4 -> 8 -> 16 -> ... re-inserts in bucket order); it must be predicted exactly."""
+    rng = random.Random(n_keys * 100 + length)
+    for _ in range(5):
+        keys = _keys(rng, n_keys, length, bytes(range(256)))
+        slots, items = [], 0
+        for k in keys:
+            if not slots or items == _capacity(len(slots)):
+                old = [x for x in slots if x is not None]
+                slots = [None] * _buckets_for(max(items + 1, _capacity(len(slots)) + 1 if slots else 1))
+                for x in old:
+                    slots[_place_wide(slots, _fx_vec_u8(oracle, x, 26))] = x
+            slots[_place_wide(slots, _fx_vec_u8(oracle, k, 26))] = k
+            items += 1
+        v = oc.Vocabulary(250, {})
+        for i, k in enumerate(keys):
+            v.insert(k, i % 200)
+        blob = v.__reduce__()[1][0]
+        p = 2
+        if blob[1] == 251:  # bincode varint: u16 follows
+            assert blob[2] | (blob[3] << 8) == n_keys
+            p = 4
+        seen = []
+        for _ in keys:
+            seen.append(bytes(blob[p + 1:p + 1 + length]))
+            p += length + 3
+        assert seen == [x for x in slots if x is not None]
+
+
 def test_pure_python_restatement_agrees(oracle):
     """the independent pure-Python hash_bytes (tests/test_oracle_cpu.py) and the C oracle agree on the same keys"""
     from tests.test_oracle_cpu import py_hash_bytes
