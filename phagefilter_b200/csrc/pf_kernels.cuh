@@ -637,26 +637,45 @@ static __global__ void level_scan_kernel(uint32_t lo, uint32_t hi, const uint32_
         if (leaf[u] >= 0) sh += c;
         else sn += c * ((left[u] != NONE32_D) + (right[u] != NONE32_D));
     }
-    s_next[t] = sn;
-    s_hit[t] = sh;
-    __syncthreads();
-    if (t == 0) {
-        unsigned long long an = 0, ah = totals->hits_total;
-        for (uint32_t i = 0; i < nt; ++i) {
-            unsigned long long x = s_next[i], y = s_hit[i];
-            s_next[i] = an;
-            s_hit[i] = ah;
-            an += x;
-            ah += y;
+    const unsigned long long hits_before = totals->hits_total;  // every thread reads it before the first barrier;
+                                                                // it is rewritten only after that barrier
+    // exclusive scan of (sn, sh) over the block's threads: warp scans, then a scan of the 32 warp totals
+    const uint32_t lane = t & 31u, wid = t >> 5;
+    unsigned long long in_n = sn, in_h = sh;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long yn = __shfl_up_sync(0xFFFFFFFFu, in_n, o), yh = __shfl_up_sync(0xFFFFFFFFu, in_h, o);
+        if (lane >= (uint32_t)o) {
+            in_n += yn;
+            in_h += yh;
         }
-        totals->next_pairs = an;
-        totals->hits_total = ah;
-        totals->probes = probes[0];
-        totals->memo_hits = probes[1];
-        totals->memo_lookups = probes[2];
+    }
+    if (lane == 31u) {
+        s_next[wid] = in_n;
+        s_hit[wid] = in_h;
     }
     __syncthreads();
-    unsigned long long an = s_next[t], ah = s_hit[t];
+    if (wid == 0) {
+        const unsigned long long xn = lane < (nt >> 5) ? s_next[lane] : 0ULL, xh = lane < (nt >> 5) ? s_hit[lane] : 0ULL;
+        unsigned long long zn = xn, zh = xh;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long yn = __shfl_up_sync(0xFFFFFFFFu, zn, o), yh = __shfl_up_sync(0xFFFFFFFFu, zh, o);
+            if (lane >= (uint32_t)o) {
+                zn += yn;
+                zh += yh;
+            }
+        }
+        s_next[lane] = zn - xn;  // exclusive warp bases
+        s_hit[lane] = zh - xh;
+        if (lane == 31u) {
+            totals->next_pairs = zn;
+            totals->hits_total = hits_before + zh;
+            totals->probes = probes[0];
+            totals->memo_hits = probes[1];
+            totals->memo_lookups = probes[2];
+        }
+    }
+    __syncthreads();
+    unsigned long long an = s_next[wid] + in_n - sn, ah = hits_before + s_hit[wid] + in_h - sh;
     for (uint32_t u = b; u < e; ++u) {
         const unsigned long long c = node_pass[u];
         if (leaf[u] >= 0) {
@@ -670,26 +689,50 @@ static __global__ void level_scan_kernel(uint32_t lo, uint32_t hi, const uint32_
     }
 }
 
-// Thread per pair: survivors take a rank inside their node (warp-aggregated atomic) and are written
-// to both children's slices, or to the hit list when the node is a leaf.
+// Thread per pair: survivors take a rank inside their node and are written to both children's slices, or to the hit
+// list when the node is a leaf.  The frontier is node-major, so a block's pairs mostly belong to the node of its
+// first pair: those survivors are ranked with ONE atomic per block (per-warp counts in shared memory); pairs of the
+// block's other nodes use a warp-aggregated atomic (`__match_any_sync`).  (Consecutive blocks hit the same cursor,
+// and same-address atomics with a return value serialise in L2.)
 static __global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, const uint32_t *__restrict__ fr_node,
                                const uint8_t *__restrict__ pass, uint32_t n, const uint32_t *__restrict__ node_pass,
                                uint32_t *cursor, const uint32_t *__restrict__ left, const uint32_t *__restrict__ right,
                                const int32_t *__restrict__ leaf, const unsigned long long *__restrict__ next_base,
                                const unsigned long long *__restrict__ hit_base, uint32_t *nx_read, uint32_t *nx_node,
                                uint32_t *hit_read, uint32_t *hit_leaf, uint32_t *read_hits, int want_hits) {
+    __shared__ uint32_t s_cnt[32], s_base;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const bool on = i < n && pass[i];
-    const uint32_t act = __ballot_sync(0xFFFFFFFFu, on);
+    const uint32_t u = on ? fr_node[i] : NONE32_D, r = on ? fr_read[i] : 0u;
+    const uint32_t u0 = fr_node[blockIdx.x * blockDim.x];  // the block's first pair exists: grid = ceil(n / block)
+    const bool is0 = on && u == u0;
+    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, is0);
+    if (lane == 0) s_cnt[wid] = __popc(b0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (uint32_t w = 0; w < n_warps; ++w) {
+            const uint32_t c = s_cnt[w];
+            s_cnt[w] = tot;
+            tot += c;
+        }
+        s_base = tot ? atomicAdd(cursor + u0, tot) : 0u;
+    }
+    __syncthreads();
+    uint32_t rank = 0;
+    if (is0) rank = s_base + s_cnt[wid] + __popc(b0 & ((1u << lane) - 1u));
+    const bool other = on && !is0;
+    const uint32_t act = __ballot_sync(0xFFFFFFFFu, other);
+    if (other) {
+        const uint32_t peers = __match_any_sync(act, u);
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(cursor + u, (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        rank = base + __popc(peers & ((1u << lane) - 1u));
+    }
     if (!on) return;
-    const uint32_t u = fr_node[i], r = fr_read[i];
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t peers = __match_any_sync(act, u);
-    const uint32_t leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(cursor + u, (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const uint32_t rank = base + __popc(peers & ((1u << lane) - 1u));
     const int32_t lf = leaf[u];
     if (lf >= 0) {
         if (want_hits) {
