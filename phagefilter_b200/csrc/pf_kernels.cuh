@@ -22,7 +22,8 @@ namespace pf {
 constexpr uint32_t NONE32_D = 0xFFFFFFFFu;  // "no child" / "not an exception read"
 constexpr int NODE_PASS_COPIES = 16;  // copies of the per-node survivor counters (spreads same-address atomics)
 constexpr int PROBE_THREADS = 256;
-constexpr int PROBE_CHUNK = 8;  // pairs fetched per warp per work-counter atomic
+constexpr int PROBE_CHUNK = 8;   // pairs whose first round is batched together
+constexpr int PROBE_GRAB = 32;   // pairs fetched per warp per work-counter atomic (one per lane)
 constexpr int HASH_THREADS = 256;
 
 PF_D uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
@@ -450,9 +451,9 @@ PF_D bool probe_pair(const ProbeArgs &a, const PairMeta &pm, uint32_t lane, int 
     return hits >= need;
 }
 
-// Persistent grid; warps pull PROBE_CHUNK consecutive pairs at a time from a global counter.  The chunk's
-// pair records and per-read / per-node metadata are fetched by PROBE_CHUNK lanes in parallel (two dependent
-// memory round trips per chunk instead of per pair) and broadcast with shuffles.
+// Persistent grid; warps pull PROBE_GRAB = 32 consecutive pairs at a time from a global counter.  The pairs' records
+// and per-read / per-node metadata are fetched by the 32 lanes in parallel (two dependent memory round trips per
+// ticket instead of per pair) and broadcast with shuffles.
 template <int G, bool SMALL_M>
 static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 4 : 3))) probe_kernel(const ProbeArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -465,43 +466,49 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
     uint32_t memo_hits = 0, memo_lookups = 0;  // warp-uniform: k-mers answered by / looked up in the memo
     unsigned long long probes_total = 0, memo_total = 0, lookup_total = 0;
     for (;;) {
-        uint32_t i0 = 0;
-        if (lane == 0) i0 = atomicAdd(a.work_ctr, (unsigned)PROBE_CHUNK);
-        i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
+        // One ticket = PROBE_GRAB consecutive pairs: every lane fetches the metadata of one pair (two dependent round
+        // trips per 32 pairs), and the ticket counter -- a same-address atomic with a return value -- is hit once per
+        // 32 pairs.  The pairs are then worked in sub-chunks of PROBE_CHUNK.
+        uint32_t g0 = 0;
+        if (lane == 0) g0 = atomicAdd(a.work_ctr, (unsigned)PROBE_GRAB);
+        g0 = __shfl_sync(0xFFFFFFFFu, g0, 0);
         if (a.order_streams > 1u) {
-            // memo levels: consecutive tickets go to chunks far apart in the node-major frontier, so the pairs of one
+            // memo levels: consecutive tickets go to pairs far apart in the node-major frontier, so the pairs of one
             // node are spread over time instead of all being in flight at once (the memo can only answer what an
             // EARLIER pair of the node has stored); order_streams bounds how many nodes are then live in L2 together
-            const uint32_t c = i0 / PROBE_CHUNK;
+            const uint32_t c = g0 / PROBE_GRAB;
             if (c >= a.order_streams * a.order_span) break;
-            i0 = ((c % a.order_streams) * a.order_span + c / a.order_streams) * PROBE_CHUNK;
-            if (i0 >= a.n_pairs) continue;
-        } else if (i0 >= a.n_pairs) break;
-        const uint32_t n_here = min((uint32_t)PROBE_CHUNK, a.n_pairs - i0);
+            g0 = ((c % a.order_streams) * a.order_span + c / a.order_streams) * PROBE_GRAB;
+            if (g0 >= a.n_pairs) continue;
+        } else if (g0 >= a.n_pairs) break;
+        const uint32_t n_grab = min((uint32_t)PROBE_GRAB, a.n_pairs - g0);
         PairMeta mine{};
-        if (lane < n_here) {
-            mine.r = ldg32(a.fr_read + i0 + lane);
-            mine.u = ldg32(a.fr_node + i0 + lane);
+        if (lane < n_grab) {
+            mine.r = ldg32(a.fr_read + g0 + lane);
+            mine.u = ldg32(a.fr_node + g0 + lane);
             mine.len = ldg32(a.lengths + mine.r);
             mine.koff = __ldg(a.kmer_off + mine.r);
             mine.slot = ldg32(a.node_slot + mine.u);
             mine.steps = ldg32(a.node_steps + mine.u);
             mine.memo = a.memo ? ldg32(a.node_memo + mine.u) : NONE32_D;
         }
-        // Step 0 of the first round (up to 32 k-mers) of EVERY pair of the chunk, batched: PROBE_CHUNK index loads,
+        bool my_pass = false;  // outcome of this lane's pair
+        for (uint32_t sb = 0; sb < n_grab; sb += PROBE_CHUNK) {  // pairs [sb, sb + n_here) of the ticket: lanes sb + p
+        const uint32_t n_here = min((uint32_t)PROBE_CHUNK, n_grab - sb);
+        const bool holder = lane >= sb && lane < sb + n_here;  // this lane holds the metadata of a pair of the sub-chunk
+        // Step 0 of the first round (up to 32 k-mers) of EVERY pair of the sub-chunk, batched: PROBE_CHUNK index loads,
         // then PROBE_CHUNK gathers in flight per lane, instead of two dependent round trips per pair.  That round
         // alone decides most pairs that fail and all of a sampled single-round pre-test; those pairs are settled
         // here by the lane that holds their metadata and never enter the per-pair path below.
-        uint32_t undecided = n_here >= 32u ? 0xFFFFFFFFu : (1u << n_here) - 1u;
-        uint32_t miss_bits = 0;  // bit p: this lane's k-mer of pair p had its step-0 bit clear
-        bool my_pass = false;
+        uint32_t undecided = (1u << n_here) - 1u;  // bit p: pair sb + p
+        uint32_t miss_bits = 0;                    // bit p: this lane's k-mer of pair sb + p had its step-0 bit clear
         if (SMALL_M) {
             // per pair: first-round slot count | stride << 8, or 0 when the pair needs no probe at all; and the k-mer
             // index of slot 0
             uint32_t my_r0 = 0, my_nk = 0, my_need = 0, my_ns = 0, my_off = 0;
             uint64_t my_k0 = 0;
             bool my_decided = false;
-            if (lane < n_here) {
+            if (holder) {
                 my_nk = kmers_of(mine.len, a.hp.k);
                 my_need = need_of(a.threshold, my_nk);
                 const uint32_t n_steps = mine.steps & 0xFFu, stride = mine.steps >> 8;
@@ -522,15 +529,15 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
             uint32_t idxv[PROBE_CHUNK], wv[PROBE_CHUNK];
 #pragma unroll
             for (int p = 0; p < PROBE_CHUNK; ++p) {
-                const uint32_t r0 = __shfl_sync(0xFFFFFFFFu, my_r0, p);
-                const uint64_t k0 = __shfl_sync(0xFFFFFFFFu, my_k0, p);
-                const uint32_t o4 = __shfl_sync(0xFFFFFFFFu, my_off, p);
+                const uint32_t r0 = __shfl_sync(0xFFFFFFFFu, my_r0, sb + p);
+                const uint64_t k0 = __shfl_sync(0xFFFFFFFFu, my_k0, sb + p);
+                const uint32_t o4 = __shfl_sync(0xFFFFFFFFu, my_off, sb + p);
                 idxv[p] = 0xFFFFFFFFu;
                 if (lane < (r0 & 0xFFu)) idxv[p] = ldg32(a.idx0 + k0 + idx0_slot((o4 & 0xFFu) + lane * (r0 >> 8), o4 >> 8));
             }
 #pragma unroll
             for (int p = 0; p < PROBE_CHUNK; ++p) {
-                const uint32_t slot = __shfl_sync(0xFFFFFFFFu, mine.slot, p);
+                const uint32_t slot = __shfl_sync(0xFFFFFFFFu, mine.slot, sb + p);
                 wv[p] = 0xFFFFFFFFu;
                 if (idxv[p] != 0xFFFFFFFFu)
                     wv[p] = ldg32(reinterpret_cast<const uint32_t *>(a.filters + (uint64_t)slot * a.words_per_filter) + (idxv[p] >> 5));
@@ -541,7 +548,7 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
                 const bool miss = !((wv[p] >> (idxv[p] & 31u)) & 1u);
                 if (miss) miss_bits |= 1u << p;
                 const uint32_t b = __ballot_sync(0xFFFFFFFFu, miss);
-                if (lane == (uint32_t)p) my_dead0 = __popc(b);
+                if (lane == sb + (uint32_t)p) my_dead0 = __popc(b);
             }
             if ((my_r0 & 0xFFu) != 0u) {  // this lane's pair was probed: can its first round settle it?
                 const uint32_t cnt0 = my_r0 & 0xFFu, allowed = my_need > my_nk ? 0u : my_nk - my_need;
@@ -555,28 +562,30 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
                     my_probes += cnt0;
                 }
             }
-            undecided = __ballot_sync(0xFFFFFFFFu, lane < n_here && !my_decided);
+            undecided = (__ballot_sync(0xFFFFFFFFu, holder && !my_decided) >> sb) & ((1u << PROBE_CHUNK) - 1u);
         }
         uint32_t pass_bits = 0;
         for (uint32_t rest = undecided; rest; rest &= rest - 1u) {
             const uint32_t p = __ffs(rest) - 1u;
             PairMeta pm;
-            pm.r = __shfl_sync(0xFFFFFFFFu, mine.r, p);
-            pm.u = __shfl_sync(0xFFFFFFFFu, mine.u, p);
-            pm.len = __shfl_sync(0xFFFFFFFFu, mine.len, p);
-            pm.slot = __shfl_sync(0xFFFFFFFFu, mine.slot, p);
-            pm.steps = __shfl_sync(0xFFFFFFFFu, mine.steps, p);
-            pm.koff = __shfl_sync(0xFFFFFFFFu, mine.koff, p);
-            pm.memo = __shfl_sync(0xFFFFFFFFu, mine.memo, p);
+            pm.r = __shfl_sync(0xFFFFFFFFu, mine.r, sb + p);
+            pm.u = __shfl_sync(0xFFFFFFFFu, mine.u, sb + p);
+            pm.len = __shfl_sync(0xFFFFFFFFu, mine.len, sb + p);
+            pm.slot = __shfl_sync(0xFFFFFFFFu, mine.slot, sb + p);
+            pm.steps = __shfl_sync(0xFFFFFFFFu, mine.steps, sb + p);
+            pm.koff = __shfl_sync(0xFFFFFFFFu, mine.koff, sb + p);
+            pm.memo = __shfl_sync(0xFFFFFFFFu, mine.memo, sb + p);
             if (probe_pair<G, SMALL_M>(a, pm, lane, SMALL_M ? (int)((miss_bits >> p) & 1u) : -1, stage, probes, my_probes,
                                        memo_hits, memo_lookups))
                 pass_bits |= 1u << p;
         }
+        if (holder && ((undecided >> (lane - sb)) & 1u)) my_pass = ((pass_bits >> (lane - sb)) & 1u) != 0u;
+        }  // sub-chunks
         // survivors per node: the frontier is node-major, so at any moment most warps of the GPU count into the same
         // node; same-address atomics serialise in L2 (measured: 1 M of them cost ~0.5 ms), so the counter is kept in
         // NODE_PASS_COPIES copies, one per group of CTAs, summed by level_scan_kernel
-        const bool pass = lane < n_here && (((undecided >> lane) & 1u) ? ((pass_bits >> lane) & 1u) != 0u : my_pass);
-        if (lane < n_here) a.pass[i0 + lane] = pass ? 1 : 0;
+        const bool pass = lane < n_grab && my_pass;
+        if (lane < n_grab) a.pass[g0 + lane] = pass ? 1 : 0;
         if (pass) atomicAdd(np_mine + mine.u, 1u);
         probes_total += probes + __reduce_add_sync(0xFFFFFFFFu, my_probes);
         memo_total += memo_hits;

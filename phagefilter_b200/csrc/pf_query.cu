@@ -721,7 +721,7 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
             a.memo = db->memo_table.p;
             a.node_memo = db->d_node_memo;
             // chunk order: up to 8 nodes of the level are worked on at the same time
-            const uint32_t n_chunks = (uint32_t)((n + PROBE_CHUNK - 1) / PROBE_CHUNK);
+            const uint32_t n_chunks = (uint32_t)((n + PROBE_GRAB - 1) / PROBE_GRAB);
             a.order_streams = std::max(1u, std::min(8u, db->level_memo_regions[l]));
             a.order_span = (n_chunks + a.order_streams - 1) / a.order_streams;
         }
