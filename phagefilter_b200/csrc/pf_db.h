@@ -251,6 +251,7 @@ int update_steps(pf_db *db, float threshold, uint64_t n_nominal);
 int batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b, cudaStream_t s);
 void launch_hash(const HashArgs &a, int grid, cudaStream_t s);
 uint32_t group_rounds_for(uint64_t max_kmers, bool small_m);
+uint32_t hash_grab(uint64_t max_kmers);
 int db_open_impl(pf_db *db, const char *db_path, int64_t search_depth);
 void db_free(pf_db *db);
 void flatten(pf_db *db, int64_t search_depth);     // prune_tree + level-order numbering (host only)

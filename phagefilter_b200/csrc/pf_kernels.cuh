@@ -56,6 +56,7 @@ struct HashArgs {
     uint32_t k;
     unsigned int *work_ctr;
     const uint8_t *flags;       // optional [batch reads]: only reads with a non-zero flag are hashed
+    uint32_t grab;              // reads per ticket of the work counter (>= 1)
 };
 
 struct ByteSrc {
@@ -77,10 +78,10 @@ static __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArg
     const uint32_t M0 = (uint32_t)a.hp.M, M1 = (uint32_t)(a.hp.M >> 32), m32 = (uint32_t)a.hp.m;
     for (;;) {
         uint32_t i0 = 0;
-        if (lane == 0) i0 = atomicAdd(a.work_ctr, 4u);
+        if (lane == 0) i0 = atomicAdd(a.work_ctr, a.grab);  // same-address atomic: as few tickets as balance allows
         i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
         if (i0 >= a.n_reads) break;
-        const uint32_t i1 = min(i0 + 4u, a.n_reads);
+        const uint32_t i1 = min(i0 + a.grab, a.n_reads);
         for (uint32_t i = i0; i < i1; ++i) {
             const uint32_t r = a.read0 + i;
             if (a.flags && !a.flags[r]) continue;

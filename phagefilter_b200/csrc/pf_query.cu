@@ -603,6 +603,8 @@ void pf::launch_hash(const HashArgs &a, int grid, cudaStream_t s) {
     }
 }
 // Rounds of 32 k-mers a lane owns at once: enough to cover the longest read of the batch, at most 8.
+// reads per ticket of the hash kernel's work counter: many short reads per ticket, long reads one by one
+uint32_t pf::hash_grab(uint64_t max_kmers) { return max_kmers <= 256 ? 16u : (max_kmers <= 2048 ? 4u : 1u); }
 uint32_t pf::group_rounds_for(uint64_t max_kmers, bool small_m) {
     if (!small_m) return 1;  // 64-bit remainder path (m >= 2^31): kept simple
     return (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (max_kmers + 31) / 32));
@@ -869,6 +871,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         h.n_reads = n_chunk;
         h.k = db->hp.k;
         h.work_ctr = db->d_work + n_levels;
+        h.grab = hash_grab(bt->max_kmers);
         if (chunk_kmers) {
             launch_hash(h, db->sm_count * 8, s);
             st.other_launches++;

@@ -389,6 +389,7 @@ static void fill_hash_args(pf_db *db, const pf_dev_batch &g, HashArgs &h, uint32
     h.k = db->hp.k;
     h.work_ctr = db->d_work + (db->level_start.size() - 1);
     h.flags = flags;
+    h.grab = hash_grab(g.max_kmers);
 }
 static int hash_range(pf_db *db, const pf_dev_batch &g, uint32_t read0, uint32_t n, const uint8_t *flags, Descent &st) {
     if (!n) return PF_OK;
