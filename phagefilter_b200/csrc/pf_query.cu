@@ -436,7 +436,7 @@ static double plan_prune_prob(double n, double allowed, double f, uint32_t s) {
  * floor(n / t) k-mers, every t-th one centred in the read: an unprobed k-mer is not proven absent, so the test stays
  * sound; its probes shrink by n_s / n and its pruning power is that of n_s trials.  t is a power of two <= 8 (a
  * substitution spoils k >= 17 consecutive k-mers, so reads with errors are still caught) and never leaves fewer
- * than 32 k-mers (one full warp round).  A sample is only ever probed for ONE step: with few k-mers per pair, further
+ * than 16 k-mers (a gather costs per sector, not per instruction, so half a warp round is still efficient).  A sample is only ever probed for ONE step: with few k-mers per pair, further
  * steps are dependent round trips with ever fewer probes in flight (measured: 66 G probes/s instead of 250). */
 static uint32_t plan_choose(double f, uint32_t K, uint64_t n_nominal, double allowed, double below, uint32_t *stride_out,
                             double *cost_out) {
@@ -445,7 +445,7 @@ static uint32_t plan_choose(double f, uint32_t K, uint64_t n_nominal, double all
     const double n = (double)n_nominal;
     for (uint32_t t = 1; t <= 8; t *= 2) {
         const uint64_t n_s = n_nominal / t;
-        if (t > 1 && n_s < 32) break;
+        if (t > 1 && n_s < 16) break;
         const double ns = (double)(n_s ? n_s : 1), frac = ns / n;
         for (uint32_t s = 1; s <= (t > 1 ? 1u : K); ++s) { /* a sample is probed for one step only, see above */
             const double c = plan_probe_cost(f, s) * frac + PF_PLAN_PAIR_OVERHEAD + (1.0 - plan_prune_prob(ns, allowed, f, s)) * below;
