@@ -178,6 +178,7 @@ struct pf_db {
     std::vector<uint8_t> h_mono;       // interior node whose filter contains both children's filters
     std::vector<uint32_t> h_steps;     // probe steps per node for the current (threshold, mode)
     std::vector<uint32_t> h_stride;    // k-mer sampling stride per node (1 = every k-mer)
+    std::vector<uint32_t> level_min_stride;  // per level: smallest stride if every tested node is a 1-step sample, else 0
     uint32_t *d_steps = nullptr;
     std::vector<uint32_t> h_entry;        // entry nodes of the current plan, ordered by level
     std::vector<uint32_t> entry_start;    // [n_levels + 1] offsets into h_entry per level

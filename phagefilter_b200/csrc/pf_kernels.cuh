@@ -23,7 +23,7 @@ constexpr uint32_t NONE32_D = 0xFFFFFFFFu;  // "no child" / "not an exception re
 constexpr int NODE_PASS_COPIES = 16;  // copies of the per-node survivor counters (spreads same-address atomics)
 constexpr int PROBE_THREADS = 256;
 constexpr int PROBE_CHUNK = 8;   // pairs whose first round is batched together
-constexpr int PROBE_GRAB = 32;   // pairs fetched per warp per work-counter atomic (one per lane)
+constexpr int PROBE_GRAB = 32;   // most pairs fetched per warp per work-counter atomic (one per lane); ProbeArgs::grab
 constexpr int HASH_THREADS = 256;
 
 PF_D uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
@@ -151,6 +151,7 @@ struct ProbeArgs {
     // that node; contains() depends on the k-mer only through that value, so a match is exact, never probabilistic.
     unsigned long long *memo;
     const uint32_t *node_memo;
+    uint32_t grab;  // pairs per ticket: PROBE_GRAB, or PROBE_CHUNK when pairs are long or few (load balance)
     uint32_t order_streams, order_span;  // chunk order: ticket c -> chunk (c % streams) * span + c / streams
 };
 
@@ -471,18 +472,18 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
         // trips per 32 pairs), and the ticket counter -- a same-address atomic with a return value -- is hit once per
         // 32 pairs.  The pairs are then worked in sub-chunks of PROBE_CHUNK.
         uint32_t g0 = 0;
-        if (lane == 0) g0 = atomicAdd(a.work_ctr, (unsigned)PROBE_GRAB);
+        if (lane == 0) g0 = atomicAdd(a.work_ctr, a.grab);
         g0 = __shfl_sync(0xFFFFFFFFu, g0, 0);
         if (a.order_streams > 1u) {
             // memo levels: consecutive tickets go to pairs far apart in the node-major frontier, so the pairs of one
             // node are spread over time instead of all being in flight at once (the memo can only answer what an
             // EARLIER pair of the node has stored); order_streams bounds how many nodes are then live in L2 together
-            const uint32_t c = g0 / PROBE_GRAB;
+            const uint32_t c = g0 / a.grab;
             if (c >= a.order_streams * a.order_span) break;
-            g0 = ((c % a.order_streams) * a.order_span + c / a.order_streams) * PROBE_GRAB;
+            g0 = ((c % a.order_streams) * a.order_span + c / a.order_streams) * a.grab;
             if (g0 >= a.n_pairs) continue;
         } else if (g0 >= a.n_pairs) break;
-        const uint32_t n_grab = min((uint32_t)PROBE_GRAB, a.n_pairs - g0);
+        const uint32_t n_grab = min(a.grab, a.n_pairs - g0);
         PairMeta mine{};
         if (lane < n_grab) {
             mine.r = ldg32(a.fr_read + g0 + lane);

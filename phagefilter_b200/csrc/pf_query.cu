@@ -536,6 +536,20 @@ int pf::update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
         db->entry_start[l + 1] = (uint32_t)e;
     }
     // device plan: steps | stride << 8 (stride 1 = every k-mer)
+    // per level: the smallest sampling stride over its tested nodes if ALL of them are single-step samples, else 0
+    db->level_min_stride.assign(n_levels, 0);
+    for (size_t l = 0; l < n_levels && mode == 1; ++l) {
+        uint32_t mn = 0xFFFFFFFFu;
+        for (uint32_t u = db->level_start[l]; u < db->level_start[l + 1]; ++u) {
+            if (db->h_steps[u] == 0 && db->h_leaf[u] < 0) continue;  // skipped: settled without probes
+            if (db->h_steps[u] != 1 || db->h_stride[u] < 2) {
+                mn = 0;
+                break;
+            }
+            mn = std::min(mn, db->h_stride[u]);
+        }
+        db->level_min_stride[l] = mn == 0xFFFFFFFFu ? 0 : mn;
+    }
     // memo regions: every exact multi-step node of a level gets a power-of-two region of about four times the k-mers its
     // filter holds (set bits / K), 2^12 .. 2^18 entries of 8 B; a level whose regions exceed the budget runs without
     {
@@ -713,6 +727,12 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         a.hp = db->hp;
         a.threshold = threshold;
         a.exhaustive = db->exhaustive;
+        // 32 pairs per ticket when pairs are cheap and plentiful; 8 when a pair is long (per-pair path, many k-mer groups)
+        // or the level has few tickets per warp, where coarse tickets leave warps idle at the end of the launch
+        // (cheap pairs = every tested node of the level is a single-step sample that fits one round: the ticket atomic
+        // and the metadata round trips are then a large share of a pair's cost)
+        const bool cheap = db->level_min_stride[l] > 1 && bt->max_kmers / db->level_min_stride[l] <= 32;
+        a.grab = (cheap && n >= (uint64_t)db->sm_count * 32u * PROBE_GRAB * 8u) ? PROBE_GRAB : PROBE_CHUNK;
         // the memo pays when the level's pairs bring each k-mer of its exact nodes several times (sequencing depth):
         // instances = pairs x k-mers per read against the k-mers those filters hold
         if (db->level_memo_entries[l] && (double)n * (double)bt->nominal_kmers >= 4.0 * (double)db->level_memo_kmers[l]) {
@@ -723,7 +743,7 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
             a.memo = db->memo_table.p;
             a.node_memo = db->d_node_memo;
             // chunk order: up to 8 nodes of the level are worked on at the same time
-            const uint32_t n_chunks = (uint32_t)((n + PROBE_GRAB - 1) / PROBE_GRAB);
+            const uint32_t n_chunks = (uint32_t)((n + a.grab - 1) / a.grab);
             a.order_streams = std::max(1u, std::min(8u, db->level_memo_regions[l]));
             a.order_span = (n_chunks + a.order_streams - 1) / a.order_streams;
         }
