@@ -115,6 +115,10 @@ const pf_read_batch *pf_packed_batch(const pf_packed *p);
 void pf_packed_free(pf_packed *p);
 void *pf_alloc_pinned(size_t bytes);
 void pf_free_pinned(void *p);
+/* Host threads other than the one that opened the handle (an ingest thread that packs the next batch while the
+ * query thread runs, main.rs:322-342 split in two) call this once so that their pinned allocations belong to the
+ * handle's GPU.  A no-op without a CUDA device. */
+int pf_thread_set_device(int device);
 
 /* Per-read matched leaves of one block: CSR over the block's reads; leaves are DFS leaf
  * indices, ascending within a read.  Replaces ResultMap (result_map.rs:9-46). */

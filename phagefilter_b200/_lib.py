@@ -87,6 +87,7 @@ SYMBOLS = {
     "pf_packed_free": (None, [_VP]),
     "pf_alloc_pinned": (_VP, [C.c_size_t]),
     "pf_free_pinned": (None, [_VP]),
+    "pf_thread_set_device": (C.c_int, [C.c_int]),
     "pf_query_block": (C.c_int, [_VP, C.POINTER(ReadBatch), C.c_float, C.c_int, C.POINTER(Hits)]),
     "pf_batch_upload": (C.c_int, [_VP, C.POINTER(ReadBatch), C.POINTER(_VP)]),
     "pf_query_device": (C.c_int, [_VP, _VP, C.c_float, C.c_int, C.POINTER(Hits)]),

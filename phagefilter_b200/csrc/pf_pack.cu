@@ -120,6 +120,18 @@ void *pf_alloc_pinned(size_t bytes) {
 void pf_free_pinned(void *p) {
     if (p) cudaFreeHost(p);
 }
+int pf_thread_set_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return PF_OK;  // no device: the packer uses pageable memory (host logic only)
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        pf::set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return PF_ERR_CUDA;
+    }
+    return PF_OK;
+}
 
 // seq(r) / len(r) accessors: contiguous (seqs + offs) or scattered (one pointer per read)
 struct ReadSrcView {

@@ -1,0 +1,93 @@
+// outputs.h -- POS_FILTERING / NEG_FILTERING writers of the query driver (src/main.rs:345-364, 394-404) on several
+// host threads.
+//
+// The reference keeps a ResultMap keyed by read id that is cleared after every block of `-b` reads
+// (main.rs:345-364, result_map.rs:20-41): a read is "mapped" when ANY record of its block carrying the same id has
+// a hit, and its header lists the union of those records' genomes.  Blocks are independent, so whole blocks are
+// formatted concurrently into per-task byte buffers, which are then written in input order.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <set>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+#include "seq_reader.h"
+
+namespace pfhost {
+
+class FilterWriter {
+  public:
+    // pos_fp / neg_fp may be null (flag not given: such records are written nowhere, main.rs:350-359).
+    FilterWriter(FILE *pos_fp, FILE *neg_fp, size_t block, const std::vector<std::string> *leaf_ids, Pool *pool)
+        : pos_fp_(pos_fp), neg_fp_(neg_fp), block_(block), leaf_ids_(leaf_ids), pool_(pool) {}
+
+    // recs[0..n): the records of whole blocks (only the last block of the input may be short);
+    // read_off[n+1], leaf[]: the per-read hit lists of pf_hits (DFS leaf indices).
+    void write(const Record *recs, size_t n, const uint64_t *read_off, const uint32_t *leaf) {
+        if (!n || (!pos_fp_ && !neg_fp_)) return;
+        const size_t n_blocks = (n + block_ - 1) / block_;
+        const size_t tasks = std::min<size_t>(n_blocks, (size_t)(pool_ ? pool_->size() : 1) * 4);
+        if (pos_.size() < tasks) pos_.resize(tasks), neg_.resize(tasks);
+        auto job = [&](int t) {
+            std::string &pos = pos_[(size_t)t], &neg = neg_[(size_t)t];
+            pos.clear();
+            neg.clear();
+            const size_t blk0 = n_blocks * (size_t)t / tasks, blk1 = n_blocks * ((size_t)t + 1) / tasks;
+            std::unordered_map<std::string_view, std::set<uint32_t>> result_map;  // keys: views into this block's records
+            for (size_t blk = blk0; blk < blk1; ++blk) {
+                const size_t b0 = blk * block_, b1 = std::min(n, b0 + block_);
+                result_map.clear();
+                for (size_t i = b0; i < b1; ++i)
+                    for (uint64_t j = read_off[i]; j < read_off[i + 1]; ++j)
+                        result_map[std::string_view(recs[i].id, recs[i].id_len)].insert(leaf[j]);
+                for (size_t i = b0; i < b1; ++i) {
+                    const Record &r = recs[i];
+                    auto it = result_map.empty() ? result_map.end() : result_map.find(std::string_view(r.id, r.id_len));
+                    const bool mapped = it != result_map.end();
+                    if ((mapped && !pos_fp_) || (!mapped && !neg_fp_)) continue;
+                    std::string &o = mapped ? pos : neg;
+                    o.push_back(r.has_qual ? '@' : '>');  // main.rs:394-404
+                    o.append(r.id, r.id_len);
+                    if (mapped) {  // get_ext_id, result_map.rs:24-37
+                        o.append(" |");
+                        bool first = true;
+                        for (uint32_t l : it->second) {
+                            if (!first) o.push_back(',');
+                            o.append((*leaf_ids_)[l]);
+                            first = false;
+                        }
+                    }
+                    o.push_back('\n');
+                    const size_t at = o.size();
+                    o.append(r.seq, r.seq_len);
+                    for (size_t c = at; c < o.size(); ++c)
+                        if (o[c] >= 'a' && o[c] <= 'z') o[c] = (char)(o[c] - 32);  // to_ascii_uppercase, main.rs:347-349
+                    if (r.has_qual) {
+                        o.append("\n+\n");
+                        o.append(r.qual, r.seq_len);
+                    }
+                    o.push_back('\n');
+                }
+            }
+        };
+        if (pool_) pool_->run((int)tasks, job);
+        else
+            for (size_t t = 0; t < tasks; ++t) job((int)t);
+        for (size_t t = 0; t < tasks; ++t) {
+            if (pos_fp_ && !pos_[t].empty() && fwrite(pos_[t].data(), 1, pos_[t].size(), pos_fp_) != pos_[t].size()) die("cannot write POS_FILTERING");
+            if (neg_fp_ && !neg_[t].empty() && fwrite(neg_[t].data(), 1, neg_[t].size(), neg_fp_) != neg_[t].size()) die("cannot write NEG_FILTERING");
+        }
+    }
+
+  private:
+    FILE *pos_fp_, *neg_fp_;
+    size_t block_;
+    const std::vector<std::string> *leaf_ids_;
+    Pool *pool_;
+    std::vector<std::string> pos_, neg_;
+};
+
+}  // namespace pfhost

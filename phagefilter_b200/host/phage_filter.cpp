@@ -7,334 +7,39 @@
 // the Rust binding).  File parsing stays on the host (file_parser.rs); everything else runs in libpfgpu.
 //
 // Differences that cannot change results: --threads and --cache-size are accepted and ignored (all filters are
-// resident in HBM; reads are packed by the host thread); reads go to the GPU in batches larger than
-// --block-size-reads, while ResultMap's per-block, id-keyed semantics (main.rs:345-364) are kept on the host.
-#include <dirent.h>
+// resident in HBM; host threads are set with --host-threads / PF_HOST_THREADS); reads go to the GPU in batches
+// larger than --block-size-reads, while ResultMap's per-block, id-keyed semantics (main.rs:345-364) are kept on the
+// host.  An ingest thread (seq_reader.h: parallel read + parse, then the 2-bit packer) runs one chunk ahead of the
+// query thread; POS/NEG records are formatted on several threads (outputs.h).
 #include <sys/stat.h>
-#include <zlib.h>
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <set>
 #include <string>
-#include <string_view>
-#include <unordered_map>
+#include <thread>
 #include <vector>
 
 #include "../../include/pfgpu.h"
+#include "outputs.h"
+#include "seq_reader.h"
 
 namespace {
 
-[[noreturn]] void die(const std::string &msg) {
-    // the reference panics (exit code 101) on every error on this path
-    fprintf(stderr, "thread 'main' panicked: %s\n", msg.c_str());
-    exit(101);
-}
+using namespace pfhost;
+
 void check(int rc, const char *what) {
     if (rc != PF_OK) die(std::string(what) + ": " + pf_last_error());
 }
-
-// ---- file_parser.rs ----------------------------------------------------------------------------------
-enum class Fmt { Auto, Fasta, Fastq };
-
-// A record as slices of the parse buffer (or of the carry arena): nothing is copied per read.
-struct Record {
-    const char *id = nullptr, *seq = nullptr, *qual = nullptr;
-    uint32_t id_len = 0, seq_len = 0;
-    bool has_qual = false;
-    std::string id_str() const { return std::string(id, id_len); }
-};
-
-std::string lower_ext(const std::string &name) {
-    size_t p = name.rfind('.');
-    return p == std::string::npos ? "" : name.substr(p + 1);
-}
-std::string stem(const std::string &name) {
-    size_t p = name.rfind('.');
-    return p == std::string::npos ? name : name.substr(0, p);
-}
-const std::set<std::string> kSeqExt = {"fa", "fasta", "fna", "fsa", "fas", "fq", "fastq"};  // file_parser.rs:303
-bool is_gz_ext(const std::string &e) { return e == "gz" || e == "gzip"; }
-
-bool has_supported_extension(const std::string &path) {  // file_parser.rs:323-344
-    std::string base = path.substr(path.find_last_of('/') + 1);
-    std::string e = lower_ext(base);
-    if (e.empty()) return false;
-    if (kSeqExt.count(e)) return true;
-    if (is_gz_ext(e)) return kSeqExt.count(lower_ext(stem(base))) > 0;
-    return false;
-}
-Fmt format_from_extension(const std::string &path) {  // file_parser.rs:69-86
-    std::string base = path.substr(path.find_last_of('/') + 1);
-    std::string e = lower_ext(base);
-    if (is_gz_ext(e)) e = lower_ext(stem(base));
-    return (e == "fq" || e == "fastq") ? Fmt::Fastq : Fmt::Fasta;
-}
-Fmt detect_format(const std::string &path, Fmt override_) {  // file_parser.rs:33-66 (gzread passes plain files through)
-    if (override_ != Fmt::Auto) return override_;
-    gzFile gz = gzopen(path.c_str(), "rb");
-    if (!gz) die("Failed to open '" + path + "'");
-    char c = 0;
-    int n = gzread(gz, &c, 1);
-    gzclose(gz);
-    if (n == 1 && c == '>') return Fmt::Fasta;
-    if (n == 1 && c == '@') return Fmt::Fastq;
-    return format_from_extension(path);
-}
-
-// One input file read in large blocks; records are parsed in place (memchr line scanning; multi-line
-// sequences are compacted inside the buffer) and handed out as slices.  open_reader: file_parser.rs:89-101.
-class SeqFile {
-  public:
-    SeqFile(const std::string &path, Fmt fmt, size_t buf_bytes) : fmt_(fmt) {
-        gz_ = gzopen(path.c_str(), "rb");
-        if (!gz_) die("Failed to open '" + path + "'");
-        gzbuffer(gz_, 1 << 20);
-        buf_.resize(buf_bytes);
-    }
-    ~SeqFile() {
-        if (gz_) gzclose(gz_);
-    }
-    // Parses up to max_records complete records into out (appending).  Slices stay valid until the next call.
-    // Returns false when the file is exhausted and nothing was appended.
-    bool next_records(std::vector<Record> &out, size_t max_records) {
-        const size_t before = out.size();
-        refill();
-        for (;;) {
-            while (out.size() - before < max_records) {
-                Record r;
-                const size_t used = fmt_ == Fmt::Fastq ? parse_fastq(r) : parse_fasta(r);
-                if (!used) break;
-                pos_ += used;
-                out.push_back(r);
-            }
-            if (out.size() > before || eof_) break;
-            // not even one complete record fits: grow the buffer and read more
-            if (len_ - pos_ >= buf_.size() / 2) buf_.resize(buf_.size() * 2);
-            if (!refill_more()) break;
-        }
-        return out.size() > before;
-    }
-
-  private:
-    void refill() {  // move the unparsed tail to the front, then fill the rest of the buffer
-        if (pos_ > 0) {
-            memmove(buf_.data(), buf_.data() + pos_, len_ - pos_);
-            len_ -= pos_;
-            pos_ = 0;
-        }
-        refill_more();
-    }
-    bool refill_more() {
-        bool got = false;
-        while (!eof_ && len_ < buf_.size()) {
-            const size_t want = std::min<size_t>(buf_.size() - len_, 1u << 30);
-            const int n = gzread(gz_, buf_.data() + len_, (unsigned)want);
-            if (n <= 0) {
-                eof_ = true;
-                break;
-            }
-            len_ += (size_t)n;
-            got = true;
-        }
-        return got;
-    }
-    // [p, end of line) ; returns pointer past the newline, or nullptr if the line is not complete in the buffer
-    const char *line_end(const char *p, const char *&eol) const {
-        const char *lim = buf_.data() + len_;
-        const char *nl = (const char *)memchr(p, '\n', (size_t)(lim - p));
-        if (!nl) {
-            if (!eof_) return nullptr;
-            eol = lim;  // last line without a newline
-            return lim;
-        }
-        eol = nl;
-        return nl + 1;
-    }
-    static void strip_cr(const char *b, const char *&e) {
-        if (e > b && e[-1] == '\r') --e;
-    }
-    static void set_id(Record &r, const char *b, const char *e) {  // bio: id = header up to the first whitespace
-        const char *q = b + 1;
-        while (q < e && *q != ' ' && *q != '\t') ++q;
-        r.id = b + 1;
-        r.id_len = (uint32_t)(q - (b + 1));
-    }
-    size_t parse_fastq(Record &r) {
-        char *base = buf_.data() + pos_, *lim = buf_.data() + len_;
-        const char *p = base;
-        while (p < lim && (*p == '\n' || *p == '\r')) ++p;  // blank lines between records
-        if (p >= lim) return eof_ ? (size_t)(p - base) * 0 : 0;
-        if (*p != '@') die("Expected @ at record start");
-        const char *eol, *nx = line_end(p, eol);
-        if (!nx) return 0;
-        const char *hb = p, *he = eol;
-        strip_cr(hb, he);
-        // sequence lines up to the '+' separator (one line in practice)
-        const char *sb = nx, *q = nx;
-        std::vector<std::pair<const char *, const char *>> extra;  // multi-line pieces beyond the first
-        const char *s0e = nullptr;
-        for (;;) {
-            if (q >= lim) {
-                if (!eof_) return 0;
-                die("Incomplete FASTQ record");
-            }
-            if (*q == '+') break;
-            const char *e2, *n2 = line_end(q, e2);
-            if (!n2) return 0;
-            strip_cr(q, e2);
-            if (!s0e) s0e = e2;
-            else extra.emplace_back(q, e2);
-            q = n2;
-        }
-        if (!s0e) s0e = sb;
-        const char *e3, *n3 = line_end(q, e3);  // '+' line
-        if (!n3) return 0;
-        size_t seq_len = (size_t)(s0e - sb);
-        for (auto &pc : extra) seq_len += (size_t)(pc.second - pc.first);
-        // quality lines until they cover the sequence
-        const char *qb = n3, *qq = n3, *q0e = nullptr;
-        std::vector<std::pair<const char *, const char *>> qextra;
-        size_t qual_len = 0;
-        while (qual_len < seq_len) {
-            if (qq >= lim) {
-                if (!eof_) return 0;
-                break;
-            }
-            const char *e4, *n4 = line_end(qq, e4);
-            if (!n4) return 0;
-            strip_cr(qq, e4);
-            if (!q0e) q0e = e4;
-            else qextra.emplace_back(qq, e4);
-            qual_len += (size_t)(e4 - qq);
-            qq = n4;
-        }
-        if (seq_len == 0 && qq < lim && *qq != '@') {  // empty sequence still has an (empty) quality line
-            const char *e4, *n4 = line_end(qq, e4);
-            if (!n4) return 0;
-            qq = n4;
-        }
-        // the record is complete: compact multi-line pieces in place (rare)
-        char *w = const_cast<char *>(s0e);
-        for (auto &pc : extra) {
-            memmove(w, pc.first, (size_t)(pc.second - pc.first));
-            w += pc.second - pc.first;
-        }
-        char *wq = const_cast<char *>(q0e ? q0e : qb);
-        for (auto &pc : qextra) {
-            memmove(wq, pc.first, (size_t)(pc.second - pc.first));
-            wq += pc.second - pc.first;
-        }
-        set_id(r, hb, he);
-        r.seq = sb;
-        r.seq_len = (uint32_t)seq_len;
-        r.qual = qb;
-        r.has_qual = true;
-        return (size_t)(qq - base);
-    }
-    size_t parse_fasta(Record &r) {
-        char *base = buf_.data() + pos_, *lim = buf_.data() + len_;
-        const char *p = base;
-        while (p < lim && (*p == '\n' || *p == '\r')) ++p;
-        if (p >= lim) return 0;
-        if (*p != '>') die("Expected > at record start.");
-        const char *eol, *nx = line_end(p, eol);
-        if (!nx) return 0;
-        const char *hb = p, *he = eol;
-        strip_cr(hb, he);
-        // find the next header ("\n>") or the end of the input
-        const char *q = nx, *rec_end = nullptr;
-        while (q < lim) {
-            const char *gt = (const char *)memchr(q, '>', (size_t)(lim - q));
-            if (!gt) break;
-            if (gt == nx || gt[-1] == '\n') {
-                rec_end = gt;
-                break;
-            }
-            q = gt + 1;
-        }
-        if (!rec_end) {
-            if (!eof_) return 0;
-            rec_end = lim;
-        }
-        // compact the sequence lines in place
-        char *w = const_cast<char *>(nx);
-        const char *rd = nx;
-        while (rd < rec_end) {
-            const char *nl = (const char *)memchr(rd, '\n', (size_t)(rec_end - rd));
-            const char *le = nl ? nl : rec_end;
-            const char *e2 = le;
-            strip_cr(rd, e2);
-            if (w != rd) memmove(w, rd, (size_t)(e2 - rd));
-            w += e2 - rd;
-            rd = nl ? nl + 1 : rec_end;
-        }
-        set_id(r, hb, he);
-        r.seq = nx;
-        r.seq_len = (uint32_t)(w - nx);
-        r.has_qual = false;
-        return (size_t)(rec_end - base);
-    }
-
-    gzFile gz_ = nullptr;
-    Fmt fmt_;
-    std::vector<char> buf_;
-    size_t pos_ = 0, len_ = 0;
-    bool eof_ = false;
-};
-
-class ReadQueue {  // file_parser.rs:227-301, block-wise
-  public:
-    ReadQueue(const std::string &path, Fmt fmt, size_t buf_bytes) : fmt_(fmt), buf_bytes_(buf_bytes) {
-        struct stat st;
-        if (stat(path.c_str(), &st) != 0) die("No such file or directory: " + path);
-        if (S_ISREG(st.st_mode)) {
-            files_.push_back(path);
-        } else {
-            DIR *d = opendir(path.c_str());
-            if (!d) die("cannot read directory " + path);
-            while (dirent *e = readdir(d)) {
-                std::string p = path + (path.back() == '/' ? "" : "/") + e->d_name;
-                struct stat s2;
-                if (stat(p.c_str(), &s2) == 0 && S_ISREG(s2.st_mode) && has_supported_extension(p)) files_.push_back(p);
-            }
-            closedir(d);
-            std::sort(files_.begin(), files_.end());  // read_dir order is unspecified in the reference
-        }
-    }
-    ~ReadQueue() { delete cur_; }
-    Fmt peek_format() const { return files_.empty() ? Fmt::Fasta : detect_format(files_.back(), fmt_); }
-    // Appends up to max_records records of the CURRENT file (slices valid until the next call).  Returns false
-    // when every file is exhausted; `file_done` tells the caller that the current file ended (so the next call
-    // moves to another buffer and anything it still needs from this one must be copied).
-    bool next_records(std::vector<Record> &out, size_t max_records, bool &file_done) {
-        file_done = false;
-        for (;;) {
-            if (!cur_) {
-                if (files_.empty()) return false;
-                const std::string f = files_.back();  // popped from the END (file_parser.rs:238)
-                files_.pop_back();
-                cur_ = new SeqFile(f, detect_format(f, fmt_), buf_bytes_);
-            }
-            if (cur_->next_records(out, max_records)) return true;
-            delete cur_;
-            cur_ = nullptr;
-            file_done = true;
-            return true;
-        }
-    }
-
-  private:
-    std::vector<std::string> files_;
-    Fmt fmt_;
-    size_t buf_bytes_;
-    SeqFile *cur_ = nullptr;
-};
 
 // ---- argument parsing (clap surface of main.rs:38-136) -------------------------------------------------
 struct Args {
@@ -401,21 +106,9 @@ void create_and_overwrite_directory(const std::string &dir) {  // main.rs:380-39
     }
     mkdir(dir.c_str(), 0777);
 }
-void write_record(FILE *fp, const std::string &id, const std::string &seq, const Record &r) {  // main.rs:394-404
-    fputc(r.has_qual ? '@' : '>', fp);
-    fwrite(id.data(), 1, id.size(), fp);
-    fputc('\n', fp);
-    fwrite(seq.data(), 1, seq.size(), fp);
-    if (r.has_qual) {
-        fwrite("\n+\n", 1, 3, fp);
-        fwrite(r.qual, 1, r.seq_len, fp);
-    }
-    fputc('\n', fp);
-}
-
 constexpr size_t kParseBufBytes = 256u << 20;
 
-struct PhaseTimer {  // --stats: where the wall time of a run goes
+struct PhaseTimer {  // --stats: where the time of a run goes (one timer per host thread; stages overlap)
     std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
     std::map<std::string, double> ms;
     void lap(const char *name) {
@@ -423,14 +116,151 @@ struct PhaseTimer {  // --stats: where the wall time of a run goes
         ms[name] += std::chrono::duration<double, std::milli>(n - t).count();
         t = n;
     }
-    void report(uint64_t reads) const {
-        double total = 0;
-        for (auto &kv : ms) total += kv.second;
-        fprintf(stderr, "[stats] reads=%llu total=%.1f ms (%.2f M reads/s)", (unsigned long long)reads, total,
-                total > 0 ? reads / total / 1e3 : 0.0);
+    void print(const char *who) const {
+        fprintf(stderr, " | %s:", who);
         for (auto &kv : ms) fprintf(stderr, " %s=%.1f", kv.first.c_str(), kv.second);
-        fputc('\n', stderr);
     }
+};
+
+// ---- ingest pipeline ---------------------------------------------------------------------------------------
+// A producer thread reads, parses (seq_reader.h) and 2-bit-packs (pf_pack_reads_ptrs) one chunk of the input
+// while the caller's thread queries and writes the outputs of the chunk before: file_parser.rs's ReadQueue with
+// the reading taken off the query thread.  A chunk is the content of one parse buffer (more if a block of
+// `block` reads does not fit in one), cut to whole blocks; the rest (< block records) is carried into the next
+// chunk, so block boundaries stay where the reference puts them (main.rs:322-364), also across files.
+struct Chunk {
+    std::vector<RawBuf> bufs;  // parse buffers the records are slices of
+    size_t used_bufs = 0;
+    std::vector<char> carry;         // bytes of the records carried over from the chunk before
+    std::vector<Record> recs;        // carried records first, then this chunk's
+    size_t n = 0;                    // recs[0, n) are processed with this chunk
+    std::vector<pf_packed *> packed;  // one per GPU batch of <= batch_reads reads; pinned buffers recycled
+    size_t n_batches = 0;
+    bool last = false;
+    ~Chunk() {
+        for (pf_packed *p : packed) pf_packed_free(p);
+    }
+};
+
+template <class T>
+class Channel {
+  public:
+    void push(T v) {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            q_.push_back(v);
+        }
+        cv_.notify_one();
+    }
+    T pop() {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [this] { return !q_.empty(); });
+        T v = q_.front();
+        q_.pop_front();
+        return v;
+    }
+
+  private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<T> q_;
+};
+
+class Ingest {
+  public:
+    // block: the reference's --block-size-reads; batch_reads: reads per GPU call (a multiple of block);
+    // pack: also build the 2-bit batches (the `parse` test hook can switch it off)
+    Ingest(const std::string &path, Fmt fmt, size_t buf_bytes, size_t block, size_t batch_reads, bool pack, int threads,
+           int device = 0, size_t min_segment = 256u << 10)
+        : pool_(threads), q_(path, fmt, &pool_), buf_bytes_(buf_bytes), block_(block), batch_reads_(batch_reads), pack_(pack), device_(device) {
+        q_.set_min_segment(min_segment);
+        for (auto &c : chunks_) free_.push(&c);
+    }
+    ~Ingest() {
+        if (thread_.joinable()) thread_.join();
+    }
+    Fmt peek_format() const { return q_.peek_format(); }
+    void start() {
+        thread_ = std::thread([this] { produce(); });
+    }
+    Chunk *next() { return ready_.pop(); }       // blocks until the producer has a chunk; the last one has ->last set
+    void release(Chunk *c) { free_.push(c); }    // hand the chunk back once its records are no longer needed
+    const PhaseTimer &timer() const { return timer_; }  // read after the last chunk was released
+
+  private:
+    void produce() {
+        if (pack_) check(pf_thread_set_device(device_), "pf_thread_set_device");  // pinned batches belong to the handle's GPU
+        std::vector<char> pend_bytes;  // records of an unfinished block, copied out of the chunk they came from
+        std::vector<Record> pend_recs;
+        std::vector<const uint8_t *> ptrs;
+        std::vector<uint32_t> lens;
+        for (bool more = true; more;) {
+            Chunk *c = free_.pop();
+            c->used_bufs = 0;
+            c->carry.swap(pend_bytes);  // swapping keeps the data pointers the records hold
+            c->recs.swap(pend_recs);
+            pend_bytes.clear();
+            pend_recs.clear();
+            timer_.lap("wait");
+            // at least one block; beyond that, about one parse buffer's worth of input (small files are gathered)
+            size_t chunk_bytes = 0;
+            do {
+                if (c->bufs.size() <= c->used_bufs) c->bufs.emplace_back();
+                const size_t before = c->recs.size();
+                more = q_.next_records(c->bufs[c->used_bufs], buf_bytes_, c->recs);
+                chunk_bytes += q_.last_bytes();
+                if (c->recs.size() > before) ++c->used_bufs;
+            } while (more && (c->recs.size() < block_ || (c->recs.size() < batch_reads_ && chunk_bytes < buf_bytes_)));
+            timer_.lap("read_parse");
+            const size_t n = more ? c->recs.size() / block_ * block_ : c->recs.size();
+            c->n = n;
+            c->last = !more;
+            // what is left (< one block) must outlive this chunk's buffers: copy it
+            size_t bytes = 0;
+            for (size_t i = n; i < c->recs.size(); ++i) bytes += c->recs[i].id_len + (size_t)c->recs[i].seq_len * (c->recs[i].has_qual ? 2 : 1);
+            pend_bytes.resize(bytes);
+            char *w = pend_bytes.data();
+            for (size_t i = n; i < c->recs.size(); ++i) {
+                const Record &r = c->recs[i];
+                Record o = r;
+                memcpy(w, r.id, r.id_len), o.id = w, w += r.id_len;
+                memcpy(w, r.seq, r.seq_len), o.seq = w, w += r.seq_len;
+                if (r.has_qual) memcpy(w, r.qual, r.seq_len), o.qual = w, w += r.seq_len;
+                pend_recs.push_back(o);
+            }
+            c->recs.resize(n);
+            c->n_batches = 0;
+            if (pack_) {
+                for (size_t lo = 0; lo < n; lo += batch_reads_) {
+                    const size_t cnt = std::min(batch_reads_, n - lo);
+                    ptrs.resize(cnt);
+                    lens.resize(cnt);
+                    pool_.run((int)std::min<size_t>((size_t)pool_.size(), cnt / 65536 + 1), [&](int t) {
+                        const size_t T = std::min<size_t>((size_t)pool_.size(), cnt / 65536 + 1);
+                        for (size_t i = cnt * (size_t)t / T; i < cnt * ((size_t)t + 1) / T; ++i) {
+                            ptrs[i] = (const uint8_t *)c->recs[lo + i].seq;  // k-mers come from the raw bytes (file_parser.rs:203-205)
+                            lens[i] = c->recs[lo + i].seq_len;
+                        }
+                    });
+                    if (c->packed.size() <= c->n_batches) c->packed.push_back(nullptr);
+                    check(pf_pack_reads_ptrs(ptrs.data(), lens.data(), (uint32_t)cnt, &c->packed[c->n_batches]), "pf_pack_reads");
+                    ++c->n_batches;
+                }
+                timer_.lap("pack");
+            }
+            ready_.push(c);
+        }
+    }
+
+    Pool pool_;
+    ReadQueue q_;
+    size_t buf_bytes_, block_, batch_reads_;
+    bool pack_;
+    int device_;
+    Chunk chunks_[3];
+    Channel<Chunk *> free_, ready_;
+    std::thread thread_;
+    PhaseTimer timer_;
 };
 
 // ---- build / add (main.rs:148-247) -----------------------------------------------------------------------
@@ -454,10 +284,11 @@ int cmd_build(const Args &a, bool add) {
                                 a.get("node-names", "u16") == "counter" ? 0 : 1, s1 ^ s2, &b),
               "BloomTree::new");
     }
-    ReadQueue q(a.get("genomes"), parse_fmt(a.get("format", "auto")), 64u << 20);
+    Pool pool(a.has("host-threads") ? std::max(1, atoi(a.get("host-threads").c_str())) : default_host_threads());
+    ReadQueue q(a.get("genomes"), parse_fmt(a.get("format", "auto")), &pool);
+    RawBuf buf;
     std::vector<Record> recs;
-    bool file_done;
-    while (q.next_records(recs, 256, file_done)) {  // one leaf per record (main.rs:173-195)
+    while (q.next_records(buf, 64u << 20, recs)) {  // one leaf per record (main.rs:173-195)
         for (const Record &r : recs)
             check(pf_builder_insert(b, r.id_str().c_str(), (const uint8_t *)r.seq, r.seq_len), "BloomTree::insert");
         recs.clear();
@@ -469,10 +300,6 @@ int cmd_build(const Args &a, bool add) {
 }
 
 // ---- query (main.rs:249-376) -------------------------------------------------------------------------------
-struct OwnedRecord {
-    std::string id, seq, qual;
-};
-
 int cmd_query(const Args &a) {
     if (!a.has("reads") || !a.has("out") || !a.has("db-path"))
         die("the following required arguments were not provided: --reads --out --db-path");
@@ -484,8 +311,10 @@ int cmd_query(const Args &a) {
     const int64_t depth = a.has("search-depth") ? strtoll(a.get("search-depth").c_str(), nullptr, 10) : -1;
     const int device = atoi(a.get("device", "0").c_str());
     const size_t gpu_batch = strtoull(a.get("gpu-batch-reads", "1000000").c_str(), nullptr, 10);
+    const int host_threads = a.has("host-threads") ? std::max(1, atoi(a.get("host-threads").c_str())) : default_host_threads();
     if (block == 0) die("block size must be positive");
 
+    const auto t_start = std::chrono::steady_clock::now();
     PhaseTimer timer;
     const bool stats = a.flags.count("stats") > 0;
     uint64_t total_reads = 0;
@@ -493,6 +322,10 @@ int cmd_query(const Args &a) {
     check(pf_db_open(a.get("db-path").c_str(), device, depth, &db), "BloomTree::load");
     timer.lap("db_open");
     if (a.has("hash-rot")) check(pf_db_set_hash_rot(db, atoi(a.get("hash-rot").c_str())), "pf_db_set_hash_rot");
+    pf_db_info_t info{};
+    check(pf_db_info(db, &info), "pf_db_info");
+    std::vector<std::string> leaf_ids(info.n_leaves);
+    for (uint64_t l = 0; l < info.n_leaves; ++l) leaf_ids[l] = pf_db_leaf_id(db, l);
 
     puts("Querying reads...");
     printf("Filtering settings: positive=%s; negative=%s\n", pos ? "true" : "false", neg ? "true" : "false");
@@ -500,118 +333,89 @@ int cmd_query(const Args &a) {
         if (!filtering) puts("If using a search depth, use a filtering flag (--pos-filter or --neg-filter, or both!)");
         printf("Search depth settings: %lld\n", (long long)depth);
     }
-    ReadQueue q(a.get("reads"), parse_fmt(a.get("format", "auto")), kParseBufBytes);
+    // GPU batches are whole multiples of the reference's block, so block boundaries stay where they were
+    const size_t batch_reads = std::max(block, gpu_batch / block * block);
+    auto ingest = std::make_unique<Ingest>(a.get("reads"), parse_fmt(a.get("format", "auto")), kParseBufBytes, block, batch_reads, true, host_threads, device);
     create_and_overwrite_directory(out);
-    const char *ext = q.peek_format() == Fmt::Fastq ? "fq" : "fa";
+    const char *ext = ingest->peek_format() == Fmt::Fastq ? "fq" : "fa";
     FILE *pos_fp = nullptr, *neg_fp = nullptr;
     if (pos && !(pos_fp = fopen((out + "/POS_FILTERING." + ext).c_str(), "wb"))) die("cannot create POS_FILTERING");
     if (neg && !(neg_fp = fopen((out + "/NEG_FILTERING." + ext).c_str(), "wb"))) die("cannot create NEG_FILTERING");
+    if (pos_fp) setvbuf(pos_fp, nullptr, _IOFBF, 4u << 20);
+    if (neg_fp) setvbuf(neg_fp, nullptr, _IOFBF, 4u << 20);
+    Pool out_pool(filtering ? host_threads : 1);
+    FilterWriter writer(pos_fp, neg_fp, block, &leaf_ids, &out_pool);
+    ingest->start();
+    timer.lap("setup");
 
-    // GPU batches are whole multiples of the reference's block, so block boundaries stay where they were
-    const size_t batch_reads = std::max(block, gpu_batch / block * block);
-    std::vector<Record> recs;
-    std::vector<OwnedRecord> carry;  // records of an unfinished block, copied out of the parse buffer
-    std::vector<const uint8_t *> ptrs;
-    std::vector<uint32_t> lens;
-    pf_packed *packed = nullptr;  // recycled: its pinned buffers are reused by every batch
-    std::string seq_up, ext_id;
-    std::unordered_map<std::string_view, std::set<uint32_t>> result_map;
-
-    auto process = [&](size_t n) {
-        ptrs.resize(n);
-        lens.resize(n);
-        for (size_t i = 0; i < n; ++i) {
-            ptrs[i] = (const uint8_t *)recs[i].seq;  // k-mers come from the raw bytes (file_parser.rs:203-205)
-            lens[i] = recs[i].seq_len;
+    for (bool last = false; !last;) {
+        Chunk *c = ingest->next();
+        timer.lap("wait_ingest");
+        for (size_t j = 0; j < c->n_batches; ++j) {
+            const size_t lo = j * batch_reads, cnt = std::min(batch_reads, c->n - lo);
+            pf_hits hits{};
+            check(pf_query_block(db, pf_packed_batch(c->packed[j]), theta, filtering ? 1 : 0, &hits), "query_batch");
+            timer.lap("gpu");
+            // ResultMap is keyed by read id and cleared after every block of `block` reads (main.rs:345-364)
+            if (filtering) writer.write(c->recs.data() + lo, cnt, hits.read_off, hits.leaf);
+            timer.lap("outputs");
         }
-        total_reads += n;
-        check(pf_pack_reads_ptrs(ptrs.data(), lens.data(), (uint32_t)n, &packed), "pf_pack_reads");
-        timer.lap("pack");
-        pf_hits hits{};
-        check(pf_query_block(db, pf_packed_batch(packed), theta, filtering ? 1 : 0, &hits), "query_batch");
-        timer.lap("gpu");
-        if (!filtering) return;
-        // ResultMap is keyed by read id and cleared after every block of `block` reads (main.rs:345-364)
-        for (size_t b0 = 0; b0 < n; b0 += block) {
-            const size_t b1 = std::min(n, b0 + block);
-            result_map.clear();  // keys are views into the records of this block
-            for (size_t i = b0; i < b1; ++i)
-                for (uint64_t j = hits.read_off[i]; j < hits.read_off[i + 1]; ++j)
-                    result_map[std::string_view(recs[i].id, recs[i].id_len)].insert(hits.leaf[j]);
-            for (size_t i = b0; i < b1; ++i) {
-                const Record &r = recs[i];
-                auto it = result_map.empty() ? result_map.end() : result_map.find(std::string_view(r.id, r.id_len));
-                const bool mapped = it != result_map.end();
-                if ((mapped && !pos_fp) || (!mapped && !neg_fp)) continue;
-                seq_up.assign(r.seq, r.seq_len);
-                for (auto &c : seq_up)
-                    if (c >= 'a' && c <= 'z') c = (char)(c - 32);  // to_ascii_uppercase, main.rs:347-349
-                if (mapped) {
-                    ext_id.assign(r.id, r.id_len);  // get_ext_id, result_map.rs:24-37
-                    ext_id += " |";
-                    bool first = true;
-                    for (uint32_t leaf : it->second) {
-                        if (!first) ext_id += ",";
-                        ext_id += pf_db_leaf_id(db, leaf);
-                        first = false;
-                    }
-                    write_record(pos_fp, ext_id, seq_up, r);
-                } else {
-                    ext_id.assign(r.id, r.id_len);
-                    write_record(neg_fp, ext_id, seq_up, r);
-                }
-            }
-        }
-    };
-
-    for (bool final = false; !final;) {
-        bool file_done = false;
-        if (!q.next_records(recs, batch_reads - recs.size(), file_done)) final = true;
-        timer.lap("read_parse");
-        const size_t n = final ? recs.size() : recs.size() / block * block;
-        if (n) process(n);
-        timer.lap("outputs");
-        // what is left (< one block) must outlive the parse buffer: copy it
-        std::vector<OwnedRecord> keep(recs.size() - n);
-        for (size_t i = n; i < recs.size(); ++i) {
-            OwnedRecord &o = keep[i - n];
-            o.id.assign(recs[i].id, recs[i].id_len);
-            o.seq.assign(recs[i].seq, recs[i].seq_len);
-            if (recs[i].has_qual) o.qual.assign(recs[i].qual, recs[i].seq_len);
-        }
-        std::vector<Record> rest(keep.size());
-        for (size_t i = 0; i < keep.size(); ++i) {
-            rest[i].id = keep[i].id.data();
-            rest[i].id_len = (uint32_t)keep[i].id.size();
-            rest[i].seq = keep[i].seq.data();
-            rest[i].seq_len = (uint32_t)keep[i].seq.size();
-            rest[i].has_qual = recs[n + i].has_qual;
-            rest[i].qual = keep[i].qual.data();
-        }
-        carry.swap(keep);
-        recs.swap(rest);
+        total_reads += c->n;
+        last = c->last;
+        ingest->release(c);
     }
-    pf_packed_free(packed);
-    if (pos_fp) fclose(pos_fp);
-    if (neg_fp) fclose(neg_fp);
+    if (pos_fp && fclose(pos_fp) != 0) die("cannot write POS_FILTERING");
+    if (neg_fp && fclose(neg_fp) != 0) die("cannot write NEG_FILTERING");
     check(pf_save_leaf_counts(db, (out + "/CLASSIFICATION.csv").c_str()), "save_leaf_counts");
+    const PhaseTimer ingest_timer = ingest->timer();
+    ingest.reset();  // joins the producer and frees the pinned batches before the handle goes
     pf_db_close(db);
     timer.lap("finish");
-    if (stats) timer.report(total_reads);
+    if (stats) {
+        const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+        fprintf(stderr, "[stats] reads=%llu total=%.1f ms (%.2f M reads/s) host_threads=%d", (unsigned long long)total_reads, total,
+                total > 0 ? total_reads / total / 1e3 : 0.0, host_threads);
+        timer.print("query thread");
+        ingest_timer.print("ingest thread");
+        fputc('\n', stderr);
+    }
     puts("Finished.");
     return 0;
 }
 
-// ---- parse: dump the records the reader sees (id<TAB>sequence<TAB>quality); used to test the parser on CPU
+// ---- parse: run the ingest pipeline alone and dump the records it hands out (id<TAB>sequence<TAB>quality);
+// tests the reader, the chunking and the packer's view of the records on a machine without a GPU
 int cmd_parse(const Args &a) {
     if (!a.has("reads")) die("the following required arguments were not provided: --reads");
     const size_t buf = strtoull(a.get("buf-bytes", "1048576").c_str(), nullptr, 10);
-    const size_t chunk = strtoull(a.get("chunk", "1000").c_str(), nullptr, 10);
-    ReadQueue q(a.get("reads"), parse_fmt(a.get("format", "auto")), buf);
-    std::vector<Record> recs;
-    bool file_done;
-    while (q.next_records(recs, chunk, file_done)) {
-        for (const Record &r : recs) {
+    const size_t block = strtoull(a.get("block-size-reads", "100").c_str(), nullptr, 10);
+    const size_t gpu_batch = strtoull(a.get("gpu-batch-reads", "1000000").c_str(), nullptr, 10);
+    const size_t min_segment = strtoull(a.get("min-segment", "262144").c_str(), nullptr, 10);
+    const int host_threads = a.has("host-threads") ? std::max(1, atoi(a.get("host-threads").c_str())) : default_host_threads();
+    const bool count_only = a.flags.count("count") > 0, pack = a.flags.count("pack") > 0;
+    if (block == 0) die("block size must be positive");
+    const size_t batch_reads = std::max(block, gpu_batch / block * block);
+    const auto t0 = std::chrono::steady_clock::now();
+    Ingest ingest(a.get("reads"), parse_fmt(a.get("format", "auto")), buf, block, batch_reads, pack, host_threads, 0, min_segment);
+    ingest.start();
+    uint64_t n_reads = 0, n_bases = 0, n_chunks = 0;
+    for (bool last = false; !last;) {
+        Chunk *c = ingest.next();
+        ++n_chunks;
+        if (!c->last && (c->n == 0 || c->n % block)) die("a chunk that is not the last must hold whole blocks");
+        if (pack) {  // the packed batches must describe exactly the records handed out
+            size_t at = 0;
+            for (size_t j = 0; j < c->n_batches; ++j) {
+                const pf_read_batch *b = pf_packed_batch(c->packed[j]);
+                for (uint32_t i = 0; i < b->n_reads; ++i, ++at)
+                    if (at >= c->n || b->lengths[i] != c->recs[at].seq_len) die("packed batch does not match the records");
+            }
+            if (at != c->n) die("packed batches do not cover the chunk");
+        }
+        for (size_t i = 0; i < c->n; ++i) {
+            const Record &r = c->recs[i];
+            n_bases += r.seq_len;
+            if (count_only) continue;
             fwrite(r.id, 1, r.id_len, stdout);
             fputc('\t', stdout);
             fwrite(r.seq, 1, r.seq_len, stdout);
@@ -620,7 +424,16 @@ int cmd_parse(const Args &a) {
             else fputc('-', stdout);
             fputc('\n', stdout);
         }
-        recs.clear();
+        n_reads += c->n;
+        last = c->last;
+        ingest.release(c);
+    }
+    if (count_only) {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        printf("reads=%llu bases=%llu chunks=%llu ms=%.1f host_threads=%d\n", (unsigned long long)n_reads, (unsigned long long)n_bases,
+               (unsigned long long)n_chunks, ms, host_threads);
+        ingest.timer().print("ingest thread");
+        fputc('\n', stderr);
     }
     return 0;
 }
@@ -644,7 +457,7 @@ int main(int argc, char **argv) {
                                {{"r", "reads"}, {"o", "out"}, {"d", "db-path"}, {"t", "threads"}, {"b", "block-size-reads"},
                                 {"f", "filter-threshold"}, {"c", "cache-size"}, {"F", "format"}},
                                {"pos-filter", "neg-filter", "stats"}));
-    if (cmd == "parse") return cmd_parse(parse(argc, argv, 2, {{"r", "reads"}, {"F", "format"}}, {}));
+    if (cmd == "parse") return cmd_parse(parse(argc, argv, 2, {{"r", "reads"}, {"F", "format"}, {"b", "block-size-reads"}}, {"count", "pack"}));
     if (cmd == "--version" || cmd == "-V") {
         printf("PhageFilter 2.0 (%s)\n", pf_version());
         return 0;
