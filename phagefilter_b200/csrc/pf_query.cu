@@ -7,8 +7,11 @@
 //   query::save_leaf_counts             query.rs:173-218
 #include <dlfcn.h>
 
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <thread>
 
 #include "pf_db.h"
 
@@ -199,7 +202,30 @@ static int upload(T **dst, const std::vector<T> &v, cudaStream_t s) {
 
 static int analyse_tree(pf_db *db);
 
+namespace {
+struct OpenTiming {  // PF_TIMING=1: where pf_db_open spends its time (stderr)
+    bool on = getenv("PF_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), t = t0;
+    std::string line;
+    void lap(const char *name) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        char b[96];
+        snprintf(b, sizeof b, " %s=%.1f", name, std::chrono::duration<double, std::milli>(n - t).count());
+        line += b;
+        t = n;
+    }
+    void report(const pf_db *db) {
+        if (!on) return;
+        fprintf(stderr, "[pf_db_open] total=%.1f ms%s (%llu filters, %.1f MB)\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), line.c_str(),
+                (unsigned long long)db->n_slots, db->n_slots * db->wpf * 8 / 1e6);
+    }
+};
+}  // namespace
+
 int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
+    OpenTiming timing;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -214,6 +240,7 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     PF_CUDA_OK(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
     PF_CUDA_OK(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
     PF_CUDA_OK(cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, db->device));
+    timing.lap("cuda_init");
     if (db->sharded) {  // the load-time analysis of a sharded tree ends in an all-reduce
         int crc = comm_init_impl(db, db->nranks, db->rank, db->nccl_id.data());
         if (crc != PF_OK) return crc;
@@ -238,8 +265,6 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     std::vector<std::string> slot_path(db->n_slots);
     for (size_t q = 0; q < db->n_nodes; ++q)
         if (db->h_slot[q] != NONE32) slot_path[db->h_slot[q]] = db->tree.nodes[db->h_pre[q]].bf_path;
-    uint64_t *stage[2] = {nullptr, nullptr};
-    cudaEvent_t staged[2] = {nullptr, nullptr};
     BfHeader first{};
     if (!read_bf_header(join_path(dir, slot_path[0]), first, err)) {
         set_error("%s", err.c_str());
@@ -258,35 +283,50 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
         set_error("cannot hold %zu filters (%.1f GB) in device memory", (size_t)db->n_slots, total_words * 8 / 1e9);
         return PF_ERR_NOMEM;
     }
-    for (int i = 0; i < 2; i++) {
-        PF_CUDA_OK(cudaMallocHost(&stage[i], db->wpf * 8));
-        PF_CUDA_OK(cudaEventCreateWithFlags(&staged[i], cudaEventDisableTiming));
-    }
+    timing.lap("tree+alloc");
+    // Filters are decoded by several host threads into two half-rings of pinned staging buffers: while the copies
+    // of one wave run, the next wave is read into the other half.
+    const unsigned hc = std::thread::hardware_concurrency();
+    const uint64_t wave = std::min<uint64_t>(std::max<uint64_t>((32u << 20) / (db->wpf * 8), 1), std::min<uint64_t>(hc ? hc : 4, 16));
+    uint64_t *stage = nullptr;
+    cudaEvent_t staged[2] = {nullptr, nullptr};
+    PF_CUDA_OK(cudaMallocHost(&stage, 2 * wave * db->wpf * 8));
+    for (int i = 0; i < 2; i++) PF_CUDA_OK(cudaEventCreateWithFlags(&staged[i], cudaEventDisableTiming));
     int rc = PF_OK;
-    for (uint64_t s = 0; s < db->n_slots && rc == PF_OK; ++s) {
-        int b = (int)(s & 1);
-        cudaEventSynchronize(staged[b]);
-        memset(stage[b], 0, db->wpf * 8);
-        BfHeader h;
-        if (!read_bf(join_path(dir, slot_path[s]), h, stage[b], db->wpf, err)) {
-            set_error("%s", err.c_str());
-            rc = err.rfind("Failed to open", 0) == 0 ? PF_ERR_IO : PF_ERR_FORMAT;
-            break;
+    std::vector<std::string> errs(wave);
+    std::vector<BfHeader> hdrs(wave);
+    for (uint64_t s0 = 0, w = 0; s0 < db->n_slots && rc == PF_OK; s0 += wave, ++w) {
+        const uint64_t cnt = std::min<uint64_t>(wave, db->n_slots - s0);
+        uint64_t *half = stage + (w & 1) * wave * db->wpf;
+        cudaEventSynchronize(staged[w & 1]);
+        auto load = [&](uint64_t i) {
+            uint64_t *dst = half + i * db->wpf;
+            errs[i].clear();
+            if (read_bf(join_path(dir, slot_path[s0 + i]), hdrs[i], dst, db->wpf, errs[i]))
+                memset(dst + hdrs[i].n_words, 0, (db->wpf - hdrs[i].n_words) * 8);  // pad words of the 128-byte slot
+        };
+        std::vector<std::thread> th;
+        for (uint64_t i = 1; i < cnt; ++i) th.emplace_back(load, i);
+        load(0);
+        for (auto &t : th) t.join();
+        for (uint64_t i = 0; i < cnt && rc == PF_OK; ++i) {
+            const BfHeader &h = hdrs[i];
+            if (!errs[i].empty()) {
+                set_error("%s", errs[i].c_str());
+                rc = errs[i].rfind("Failed to open", 0) == 0 ? PF_ERR_IO : PF_ERR_FORMAT;
+            } else if (h.num_bits != first.num_bits || h.num_hashes != first.num_hashes || h.seed1 != first.seed1 || h.seed2 != first.seed2) {
+                set_error("filter %s differs in geometry/seeds from the rest of the database", slot_path[s0 + i].c_str());
+                rc = PF_ERR_FORMAT;
+            }
         }
-        if (h.num_bits != first.num_bits || h.num_hashes != first.num_hashes || h.seed1 != first.seed1 ||
-            h.seed2 != first.seed2) {
-            set_error("filter %s differs in geometry/seeds from the rest of the database", slot_path[s].c_str());
-            rc = PF_ERR_FORMAT;
-            break;
-        }
-        cudaMemcpyAsync(db->d_filters + s * db->wpf, stage[b], db->wpf * 8, cudaMemcpyHostToDevice, db->stream);
-        cudaEventRecord(staged[b], db->stream);
+        if (rc != PF_OK) break;
+        cudaMemcpyAsync(db->d_filters + s0 * db->wpf, half, cnt * db->wpf * 8, cudaMemcpyHostToDevice, db->stream);
+        cudaEventRecord(staged[w & 1], db->stream);
     }
     cudaStreamSynchronize(db->stream);
-    for (int i = 0; i < 2; i++) {
-        cudaFreeHost(stage[i]);
-        cudaEventDestroy(staged[i]);
-    }
+    cudaFreeHost(stage);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(staged[i]);
+    timing.lap("filters");
     if (rc != PF_OK) return rc;
     PF_CUDA_OK(cudaGetLastError());
 
@@ -312,10 +352,13 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     PF_CUDA_OK(cudaMemsetAsync(db->d_counts, 0, nl * 8, db->stream));
     PF_CUDA_OK(cudaMalloc(&db->d_steps, nn * 4));
     PF_CUDA_OK(cudaMalloc(&db->d_entry, nn * 4));
+    timing.lap("tables");
     if ((rc = analyse_tree(db))) return rc;
     PF_CUDA_OK(cudaEventCreate(&db->ev_begin));
     PF_CUDA_OK(cudaEventCreate(&db->ev_end));
     PF_CUDA_OK(cudaStreamSynchronize(db->stream));
+    timing.lap("analyse");
+    timing.report(db);
     return PF_OK;
 }
 
@@ -1203,9 +1246,20 @@ int pf_query_block(pf_db *db, const pf_read_batch *in, float threshold, int want
         set_error("pf_query_block: null argument");
         return PF_ERR_ARG;
     }
+    static const bool timing = getenv("PF_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = batch_upload_impl(db, in, &db->own_batch, db->stream);
     if (rc != PF_OK) return rc;
-    return query_impl(db, &db->own_batch, threshold, want_hits, out);
+    const auto t1 = std::chrono::steady_clock::now();
+    rc = query_impl(db, &db->own_batch, threshold, want_hits, out);
+    if (timing && rc == PF_OK) {
+        float dev_ms = 0.f;
+        cudaEventElapsedTime(&dev_ms, db->ev_begin, db->ev_end);
+        fprintf(stderr, "[pf_query_block] reads=%u upload_call=%.2f ms query_call=%.2f ms (device %.2f ms)\n", in->n_reads,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), dev_ms);
+    }
+    return rc;
 }
 
 int pf_leaf_counts(pf_db *db, uint64_t *counts) {

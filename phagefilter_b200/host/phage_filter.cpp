@@ -313,11 +313,17 @@ int cmd_query(const Args &a) {
     const size_t gpu_batch = strtoull(a.get("gpu-batch-reads", "1000000").c_str(), nullptr, 10);
     const int host_threads = a.has("host-threads") ? std::max(1, atoi(a.get("host-threads").c_str())) : default_host_threads();
     if (block == 0) die("block size must be positive");
+    setenv("PF_PACK_THREADS", std::to_string(host_threads).c_str(), 0);  // the packer's threads follow --host-threads
 
     const auto t_start = std::chrono::steady_clock::now();
     PhaseTimer timer;
     const bool stats = a.flags.count("stats") > 0;
     uint64_t total_reads = 0;
+    // GPU batches are whole multiples of the reference's block, so block boundaries stay where they were
+    const size_t batch_reads = std::max(block, gpu_batch / block * block);
+    // the ingest thread starts reading and parsing right away: it overlaps CUDA start-up and the database load
+    auto ingest = std::make_unique<Ingest>(a.get("reads"), parse_fmt(a.get("format", "auto")), kParseBufBytes, block, batch_reads, true, host_threads, device);
+    ingest->start();
     pf_db *db = nullptr;
     check(pf_db_open(a.get("db-path").c_str(), device, depth, &db), "BloomTree::load");
     timer.lap("db_open");
@@ -333,9 +339,6 @@ int cmd_query(const Args &a) {
         if (!filtering) puts("If using a search depth, use a filtering flag (--pos-filter or --neg-filter, or both!)");
         printf("Search depth settings: %lld\n", (long long)depth);
     }
-    // GPU batches are whole multiples of the reference's block, so block boundaries stay where they were
-    const size_t batch_reads = std::max(block, gpu_batch / block * block);
-    auto ingest = std::make_unique<Ingest>(a.get("reads"), parse_fmt(a.get("format", "auto")), kParseBufBytes, block, batch_reads, true, host_threads, device);
     create_and_overwrite_directory(out);
     const char *ext = ingest->peek_format() == Fmt::Fastq ? "fq" : "fa";
     FILE *pos_fp = nullptr, *neg_fp = nullptr;
@@ -345,7 +348,6 @@ int cmd_query(const Args &a) {
     if (neg_fp) setvbuf(neg_fp, nullptr, _IOFBF, 4u << 20);
     Pool out_pool(filtering ? host_threads : 1);
     FilterWriter writer(pos_fp, neg_fp, block, &leaf_ids, &out_pool);
-    ingest->start();
     timer.lap("setup");
 
     for (bool last = false; !last;) {

@@ -13,6 +13,7 @@
 //    stretch is parsed serially by the full parser, which also reports errors at the place a serial pass would.
 #pragma once
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -127,8 +128,9 @@ inline int default_host_threads() {
         const int v = atoi(e);
         if (v > 0) return std::min(v, 64);
     }
+    // two cores stay free for the query thread (kernel launches, per-level syncs) and the CUDA driver's own threads
     const unsigned hc = std::thread::hardware_concurrency();
-    return (int)std::min<unsigned>(hc ? hc : 4, 16);
+    return (int)std::max(1u, std::min<unsigned>(hc ? hc : 4, 16) - (hc > 4 ? 2 : 0));
 }
 
 // ---- file_parser.rs ----------------------------------------------------------------------------------------
@@ -142,8 +144,10 @@ struct Record {
     std::string id_str() const { return std::string(id, id_len); }
 };
 
-// malloc-backed byte buffer: growing keeps the contents and never value-initialises (a 256 MB memset per buffer
-// is a measurable part of a short run)
+// mmap-backed byte buffer on transparent huge pages where the kernel allows it (madvise): a parse buffer is
+// first-touched by every parser thread at once, and 65,536 small-page faults per 256 MB contend for the process's
+// mmap lock with the CUDA driver's allocations on the query thread (measured: GPU calls stalled for 100s of ms).
+// Growing keeps the contents and never value-initialises.
 struct RawBuf {
     char *p = nullptr;
     size_t cap = 0;
@@ -151,13 +155,22 @@ struct RawBuf {
     RawBuf(const RawBuf &) = delete;
     RawBuf &operator=(const RawBuf &) = delete;
     RawBuf(RawBuf &&o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr, o.cap = 0; }
-    ~RawBuf() { free(p); }
+    ~RawBuf() {
+        if (p) munmap(p, cap);
+    }
     void reserve(size_t n) {
         if (n <= cap) return;
-        char *q = (char *)realloc(p, n);
-        if (!q) die("out of memory growing a parse buffer");
-        p = q;
-        cap = n;
+        const size_t huge = 2u << 20;
+        const size_t want = n >= huge ? (n + huge - 1) / huge * huge : (n + 4095) / 4096 * 4096;
+        void *q = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (q == MAP_FAILED) die("out of memory growing a parse buffer");
+        if (want >= huge) madvise(q, want, MADV_HUGEPAGE);  // advisory: failure only means small pages
+        if (p) {
+            memcpy(q, p, cap);
+            munmap(p, cap);
+        }
+        p = (char *)q;
+        cap = want;
     }
 };
 
