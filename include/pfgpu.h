@@ -112,6 +112,10 @@ int pf_pack_reads(const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, p
 /* Same, for reads scattered in memory (e.g. slices of a parsed FASTQ buffer): one pointer and length per read. */
 int pf_pack_reads_ptrs(const uint8_t *const *seq_ptrs, const uint32_t *lengths, uint32_t n_reads, pf_packed **out);
 const pf_read_batch *pf_packed_batch(const pf_packed *p);
+/* Gives *inout (NULL: a new pf_packed) page-locked buffers at least as large as `model` has reached, without packing
+ * anything: a host that rotates several batches (an ingest thread ahead of the query thread) locks all of them once,
+ * up front -- page-locking holds the driver's lock and would otherwise stall the first queries. */
+int pf_packed_reserve_like(pf_packed **inout, const pf_packed *model);
 void pf_packed_free(pf_packed *p);
 void *pf_alloc_pinned(size_t bytes);
 void pf_free_pinned(void *p);

@@ -85,6 +85,7 @@ SYMBOLS = {
     "pf_pack_reads_ptrs": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(_VP)]),
     "pf_packed_batch": (C.POINTER(ReadBatch), [_VP]),
     "pf_packed_free": (None, [_VP]),
+    "pf_packed_reserve_like": (C.c_int, [C.POINTER(_VP), _VP]),
     "pf_alloc_pinned": (_VP, [C.c_size_t]),
     "pf_free_pinned": (None, [_VP]),
     "pf_thread_set_device": (C.c_int, [C.c_int]),

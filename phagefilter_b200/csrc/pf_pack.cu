@@ -274,6 +274,21 @@ static int pack_impl(const ReadSrcView &src, uint32_t n_reads, pf_packed **out) 
 
 const pf_read_batch *pf_packed_batch(const pf_packed *p) { return p ? &p->b : nullptr; }
 
+int pf_packed_reserve_like(pf_packed **inout, const pf_packed *model) {
+    if (!inout || !model) {
+        pf::set_error("pf_packed_reserve_like: null argument");
+        return PF_ERR_ARG;
+    }
+    pf_packed *p = *inout ? *inout : new pf_packed();
+    if (!p->main.ensure(model->main.cap) || (model->exc.cap && !p->exc.ensure(model->exc.cap))) {
+        if (!*inout) pf_packed_free(p);
+        pf::set_error("pf_packed_reserve_like: out of host memory");
+        return PF_ERR_NOMEM;
+    }
+    *inout = p;
+    return PF_OK;
+}
+
 void pf_packed_free(pf_packed *p) {
     if (!p) return;
     p->main.release();

@@ -244,6 +244,14 @@ class Ingest {
                     });
                     if (c->packed.size() <= c->n_batches) c->packed.push_back(nullptr);
                     check(pf_pack_reads_ptrs(ptrs.data(), lens.data(), (uint32_t)cnt, &c->packed[c->n_batches]), "pf_pack_reads");
+                    if (!reserved_) {  // page-lock the other chunks' first batch now, before any query runs beside it
+                        reserved_ = true;
+                        for (auto &o : chunks_)
+                            if (&o != c) {
+                                o.packed.resize(1, nullptr);
+                                check(pf_packed_reserve_like(&o.packed[0], c->packed[0]), "pf_packed_reserve_like");
+                            }
+                    }
                     ++c->n_batches;
                 }
                 timer_.lap("pack");
@@ -255,7 +263,7 @@ class Ingest {
     Pool pool_;
     ReadQueue q_;
     size_t buf_bytes_, block_, batch_reads_;
-    bool pack_;
+    bool pack_, reserved_ = false;
     int device_;
     Chunk chunks_[3];
     Channel<Chunk *> free_, ready_;
