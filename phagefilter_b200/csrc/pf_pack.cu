@@ -15,6 +15,11 @@
 
 #include "pf_common.h"
 
+namespace pf {  // pf_pack_simd.cpp
+bool cpu_has_avx2();
+bool pack_groups_avx2(const uint8_t *s, uint64_t n32, uint32_t *dst);
+}  // namespace pf
+
 namespace {
 
 struct HostBuf {  // pinned when a CUDA device is present, pageable otherwise (packing is host logic)
@@ -68,10 +73,16 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline uint64_t words_of(uint64_t len) { return ((len + 15) / 16 + 1) & ~1ULL; }  // even: 8-byte aligned reads
 
 // packs one read into nw zero-padded words; returns false (all zeros) if it holds a byte outside {A,C,G,T}
-inline bool pack_read(const uint8_t *s, uint64_t len, uint32_t *dst, uint64_t nw) {
+inline bool pack_read(const uint8_t *s, uint64_t len, uint32_t *dst, uint64_t nw, bool avx2) {
     const uint64_t full = len / 16;
     uint32_t bad = 0;
-    for (uint64_t w = 0; w < full; ++w) {
+    uint64_t w0 = 0;
+    if (avx2 && len >= 32) {  // 32 bases (two words) per step; the table loop below finishes the read
+        const uint64_t n32 = len / 32;
+        if (!pf::pack_groups_avx2(s, n32, dst)) bad = 0x80u;
+        w0 = 2 * n32;
+    }
+    for (uint64_t w = w0; w < full; ++w) {
         const uint8_t *q = s + w * 16;
         uint32_t v = 0;
 #pragma GCC unroll 16
@@ -213,13 +224,14 @@ static int pack_impl(const ReadSrcView &src, uint32_t n_reads, pf_packed **out) 
     if (const char *e = getenv("PF_PACK_THREADS")) n_thr = (unsigned)atoi(e);
     n_thr = std::max(1u, std::min(n_thr, 32u));
     if (total_bases < (1u << 20)) n_thr = 1;
+    const bool avx2 = pf::cpu_has_avx2() && !getenv("PF_PACK_SCALAR");
     std::vector<std::vector<uint32_t>> exc_lists(n_thr);
     auto work = [&](unsigned t) {
         const uint32_t r0 = (uint32_t)((uint64_t)n_reads * t / n_thr), r1 = (uint32_t)((uint64_t)n_reads * (t + 1) / n_thr);
         for (uint32_t r = r0; r < r1; ++r) {
             const uint64_t len = src.len(r);
             exc_index[r] = pf::NONE32;
-            if (!pack_read(src.seq(r), len, packed + word_off[r], words_of(len))) exc_lists[t].push_back(r);
+            if (!pack_read(src.seq(r), len, packed + word_off[r], words_of(len), avx2)) exc_lists[t].push_back(r);
         }
     };
     if (n_thr == 1) {

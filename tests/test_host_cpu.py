@@ -117,3 +117,39 @@ def test_read_queue_and_formats(tmp_path):
     assert by["r2"].sequence == b"GGCC" and by["r2"].quality == b"!!!!"
     assert [len(b) for b in blocks] == [3, 1]
     assert by["r1"].num_kmers(3) == 2 and by["r1"].num_kmers(5) == 0 and by["r1"].num_kmers(0) == 0
+
+
+def test_packer_avx2_matches_table_loop(monkeypatch):
+    """The AVX2 body of the packer (pf_pack_simd.cpp) against the table-driven loop (PF_PACK_SCALAR=1): every length
+    around the 16/32-base steps, invalid bytes (lower case, N, bytes that differ from A/C/G/T in one bit, >= 0x80) at
+    every position class."""
+    import ctypes as C
+    from phagefilter_b200.query import PackedReads
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = []
+    for L in list(range(0, 100)) + [127, 128, 129, 150, 151, 1000, 4097]:
+        reads.append(acgt[rng.integers(0, 4, size=L)].tobytes())
+    for bad in (b"N", b"a", b"@", b"E", b"U", b"\xc1", b"\x00", b"\n"):
+        for L in (1, 31, 32, 33, 64, 150):
+            for pos in {0, L // 2, L - 1}:
+                r = bytearray(acgt[rng.integers(0, 4, size=L)].tobytes())
+                r[pos:pos + 1] = bad
+                reads.append(bytes(r))
+
+    def snapshot():
+        p = PackedReads(reads)
+        b = p.batch.contents
+        words = np.ctypeslib.as_array(b.packed, shape=(b.n_words,)).copy()
+        offs = np.ctypeslib.as_array(b.word_off, shape=(b.n_reads,)).copy()
+        exc = None if not b.n_exc else np.ctypeslib.as_array(b.exc_index, shape=(b.n_reads,)).copy()
+        n_exc = b.n_exc
+        p.close()
+        return words, offs, exc, n_exc
+
+    monkeypatch.delenv("PF_PACK_SCALAR", raising=False)
+    fast = snapshot()
+    monkeypatch.setenv("PF_PACK_SCALAR", "1")
+    slow = snapshot()
+    assert fast[3] == slow[3] == sum(1 for r in reads if any(c not in b"ACGT" for c in r))  # every poisoned read is an exception read
+    assert (fast[0] == slow[0]).all() and (fast[1] == slow[1]).all() and (fast[2] == slow[2]).all()
