@@ -67,7 +67,7 @@ class FilterWriter {
                         if (o[c] >= 'a' && o[c] <= 'z') o[c] = (char)(o[c] - 32);  // to_ascii_uppercase, main.rs:347-349
                     if (r.has_qual) {
                         o.append("\n+\n");
-                        o.append(r.qual, r.seq_len);
+                        o.append(r.qual, r.qual_len);
                     }
                     o.push_back('\n');
                 }

@@ -218,7 +218,7 @@ class Ingest {
             c->last = !more;
             // what is left (< one block) must outlive this chunk's buffers: copy it
             size_t bytes = 0;
-            for (size_t i = n; i < c->recs.size(); ++i) bytes += c->recs[i].id_len + (size_t)c->recs[i].seq_len * (c->recs[i].has_qual ? 2 : 1);
+            for (size_t i = n; i < c->recs.size(); ++i) bytes += (size_t)c->recs[i].id_len + c->recs[i].seq_len + (c->recs[i].has_qual ? c->recs[i].qual_len : 0);
             pend_bytes.resize(bytes);
             char *w = pend_bytes.data();
             for (size_t i = n; i < c->recs.size(); ++i) {
@@ -226,7 +226,7 @@ class Ingest {
                 Record o = r;
                 memcpy(w, r.id, r.id_len), o.id = w, w += r.id_len;
                 memcpy(w, r.seq, r.seq_len), o.seq = w, w += r.seq_len;
-                if (r.has_qual) memcpy(w, r.qual, r.seq_len), o.qual = w, w += r.seq_len;
+                if (r.has_qual) memcpy(w, r.qual, r.qual_len), o.qual = w, w += r.qual_len;
                 pend_recs.push_back(o);
             }
             c->recs.resize(n);
@@ -435,7 +435,7 @@ int cmd_parse(const Args &a) {
             fputc('\t', stdout);
             fwrite(r.seq, 1, r.seq_len, stdout);
             fputc('\t', stdout);
-            if (r.has_qual) fwrite(r.qual, 1, r.seq_len, stdout);
+            if (r.has_qual) fwrite(r.qual, 1, r.qual_len, stdout);
             else fputc('-', stdout);
             fputc('\n', stdout);
         }

@@ -139,7 +139,7 @@ enum class Fmt { Auto, Fasta, Fastq };
 // A record as slices of a parse buffer (or of a carry arena): nothing is copied per read.
 struct Record {
     const char *id = nullptr, *seq = nullptr, *qual = nullptr;
-    uint32_t id_len = 0, seq_len = 0;
+    uint32_t id_len = 0, seq_len = 0, qual_len = 0;  // qual_len != seq_len only in malformed records (kept as read, like bio's reader)
     bool has_qual = false;
     std::string id_str() const { return std::string(id, id_len); }
 };
@@ -324,6 +324,7 @@ inline size_t parse_fastq(const Span &s, char *p0, Record &r) {
     r.seq = sb;
     r.seq_len = (uint32_t)seq_len;
     r.qual = qb;
+    r.qual_len = (uint32_t)qual_len;
     r.has_qual = true;
     return (size_t)(qq - p0);
 }
