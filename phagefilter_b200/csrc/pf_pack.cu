@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -181,18 +182,56 @@ static int pack_impl(const ReadSrcView &src, uint32_t n_reads, pf_packed **out) 
         }
         return rc;
     };
-    // sizes from the offsets alone
+    unsigned n_thr = std::thread::hardware_concurrency();
+    if (const char *e = getenv("PF_PACK_THREADS")) n_thr = (unsigned)atoi(e);
+    n_thr = std::max(1u, std::min(n_thr, 32u));
+    // small batches are not worth the thread start-up (estimate: first read's length x reads; ranges are by read count)
+    if (n_reads < 64 || (uint64_t)src.len(0) * n_reads < (1u << 20)) n_thr = 1;
+    auto parallel = [&](const std::function<void(unsigned)> &fn) {
+        if (n_thr == 1) return fn(0);
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < n_thr; ++t) th.emplace_back(fn, t);
+        fn(0);
+        for (auto &x : th) x.join();
+    };
+    auto range = [&](unsigned t, uint32_t &r0, uint32_t &r1) {
+        r0 = (uint32_t)((uint64_t)n_reads * t / n_thr);
+        r1 = (uint32_t)((uint64_t)n_reads * (t + 1) / n_thr);
+    };
+    // sizes from the lengths alone: per-thread sums over contiguous ranges of reads, then a prefix over the threads
+    struct Part {
+        uint64_t bases = 0, words = 0;
+        uint32_t max_len = 0, too_long = pf::NONE32;
+    };
+    std::vector<Part> part(n_thr);
+    parallel([&](unsigned t) {
+        uint32_t r0, r1;
+        range(t, r0, r1);
+        Part q;
+        for (uint32_t r = r0; r < r1; ++r) {
+            const uint64_t len = src.len(r);
+            if (len > 0xFFFFFFFFull) {
+                if (q.too_long == pf::NONE32) q.too_long = r;
+                continue;
+            }
+            q.bases += len;
+            q.max_len = std::max<uint32_t>(q.max_len, (uint32_t)len);
+            q.words += words_of(len);
+        }
+        part[t] = q;
+    });
     uint64_t total_bases = 0, n_words = 0;
     uint32_t max_length = 0;
-    for (uint32_t r = 0; r < n_reads; ++r) {
-        const uint64_t len = src.len(r);
-        if (len > 0xFFFFFFFFull) {
-            pf::set_error("read %u longer than 2^32-1 bases", r);
+    std::vector<uint64_t> first_word(n_thr);
+    for (unsigned t = 0; t < n_thr; ++t) {
+        if (part[t].too_long != pf::NONE32) {
+            pf::set_error("read %u longer than 2^32-1 bases", part[t].too_long);
             return fail(PF_ERR_ARG);
         }
-        total_bases += len;
-        max_length = std::max<uint32_t>(max_length, (uint32_t)len);
-        n_words += words_of(len);
+        first_word[t] = n_words;
+        total_bases += part[t].bases;
+        max_length = std::max(max_length, part[t].max_len);
+        n_words += part[t].words;
     }
     const uint64_t pad_words = 4;
     const size_t o_len = 0;
@@ -209,38 +248,23 @@ static int pack_impl(const ReadSrcView &src, uint32_t n_reads, pf_packed **out) 
     uint64_t *word_off = reinterpret_cast<uint64_t *>(base + o_woff);
     uint32_t *packed = reinterpret_cast<uint32_t *>(base + o_packed);
     uint32_t *exc_index = reinterpret_cast<uint32_t *>(base + o_excidx);
-    {
-        uint64_t w = 0;
-        for (uint32_t r = 0; r < n_reads; ++r) {
-            const uint64_t len = src.len(r);
-            lengths[r] = (uint32_t)len;
-            word_off[r] = w;
-            w += words_of(len);
-        }
-        memset(packed + n_words, 0, pad_words * 4);
-    }
-    // one pass over the bases, in parallel over contiguous ranges of reads
-    unsigned n_thr = std::thread::hardware_concurrency();
-    if (const char *e = getenv("PF_PACK_THREADS")) n_thr = (unsigned)atoi(e);
-    n_thr = std::max(1u, std::min(n_thr, 32u));
-    if (total_bases < (1u << 20)) n_thr = 1;
+    memset(packed + n_words, 0, pad_words * 4);
+    // one pass over the bases, in parallel over the same ranges: lengths, word offsets and the 2-bit codes
     const bool avx2 = pf::cpu_has_avx2() && !getenv("PF_PACK_SCALAR");
     std::vector<std::vector<uint32_t>> exc_lists(n_thr);
-    auto work = [&](unsigned t) {
-        const uint32_t r0 = (uint32_t)((uint64_t)n_reads * t / n_thr), r1 = (uint32_t)((uint64_t)n_reads * (t + 1) / n_thr);
+    parallel([&](unsigned t) {
+        uint32_t r0, r1;
+        range(t, r0, r1);
+        uint64_t w = first_word[t];
         for (uint32_t r = r0; r < r1; ++r) {
-            const uint64_t len = src.len(r);
+            const uint64_t len = src.len(r), nw = words_of(len);
+            lengths[r] = (uint32_t)len;
+            word_off[r] = w;
             exc_index[r] = pf::NONE32;
-            if (!pack_read(src.seq(r), len, packed + word_off[r], words_of(len), avx2)) exc_lists[t].push_back(r);
+            if (!pack_read(src.seq(r), len, packed + w, nw, avx2)) exc_lists[t].push_back(r);
+            w += nw;
         }
-    };
-    if (n_thr == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < n_thr; ++t) th.emplace_back(work, t);
-        for (auto &x : th) x.join();
-    }
+    });
     // exception side channel (rare): raw bytes of the reads that could not be packed
     uint32_t n_exc = 0;
     uint64_t exc_bytes = 0;

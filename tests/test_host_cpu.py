@@ -153,3 +153,36 @@ def test_packer_avx2_matches_table_loop(monkeypatch):
     slow = snapshot()
     assert fast[3] == slow[3] == sum(1 for r in reads if any(c not in b"ACGT" for c in r))  # every poisoned read is an exception read
     assert (fast[0] == slow[0]).all() and (fast[1] == slow[1]).all() and (fast[2] == slow[2]).all()
+
+
+def test_packer_threads_give_identical_batches(monkeypatch):
+    """Ranges of reads packed by several threads (per-thread size sums + prefix) against the one-thread pass,
+    with exception reads spread over the ranges and ragged lengths."""
+    from phagefilter_b200.query import PackedReads
+    rng = np.random.default_rng(12)
+    alpha = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    lens = rng.choice([0, 1, 15, 16, 17, 100, 150, 151, 700], size=30_000)
+    lens[0] = 150  # the thread heuristic looks at the first read
+    reads = [alpha[rng.integers(0, 5 if i % 97 == 0 else 4, size=int(L))].tobytes() for i, L in enumerate(lens)]
+
+    def snapshot(threads):
+        monkeypatch.setenv("PF_PACK_THREADS", str(threads))
+        p = PackedReads(reads)
+        b = p.batch.contents
+        out = (np.ctypeslib.as_array(b.packed, shape=(b.n_words,)).copy(),
+               np.ctypeslib.as_array(b.word_off, shape=(b.n_reads,)).copy(),
+               np.ctypeslib.as_array(b.lengths, shape=(b.n_reads,)).copy(),
+               np.ctypeslib.as_array(b.exc_index, shape=(b.n_reads,)).copy(),
+               np.ctypeslib.as_array(b.exc_off, shape=(b.n_exc + 1,)).copy(),
+               bytes(bytearray(b.exc_bytes[i] for i in range(int(b.exc_off[b.n_exc])))),
+               (b.n_exc, b.max_length, b.total_bases, b.n_words))
+        p.close()
+        return out
+
+    one = snapshot(1)
+    assert one[6][0] == sum(1 for r in reads if b"N" in r) and one[6][1] == 700 and one[6][2] == int(lens.sum())
+    for threads in (2, 7, 32):
+        got = snapshot(threads)
+        assert got[6] == one[6] and got[5] == one[5]
+        for a, b in zip(got[:5], one[:5]):
+            assert (a == b).all()
