@@ -25,8 +25,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <dirent.h>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <string>
@@ -489,29 +491,145 @@ inline size_t parse_stretch(const Span &s, Fmt fmt, Pool *pool, std::vector<Reco
     return handover ? serial_from(cur) : cur;
 }
 
+// ---- gzip (and anything that is not a plain regular file): inflated by zlib on a thread of its own ------------------
+// zlib inflates one stream at 0.3-0.4 GB/s and cannot be split, so (a) the current file is inflated while the
+// stretch before it is parsed, packed and queried, and (b) ReadQueue starts the next few queued gzip files early:
+// a directory of N gzip files is inflated on up to kAheadFiles cores.  The consumer sees the same byte stream.
+inline bool is_gzip_or_special(const std::string &path) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0 || !S_ISREG(st.st_mode) || st.st_size == 0) return true;
+    unsigned char magic[2] = {0, 0};
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return true;
+    const bool gz = pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    close(fd);
+    return gz;
+}
+
+class GzAhead {
+  public:
+    static constexpr size_t kMaxBlocks = 16;  // at most 16 blocks (256 MB) inflated ahead per file
+    static size_t block_bytes() {             // inflated bytes per queue entry (PF_GZ_BLOCK: tests use tiny blocks)
+        static const size_t v = [] {
+            const char *e = getenv("PF_GZ_BLOCK");
+            const size_t x = e ? strtoull(e, nullptr, 10) : 0;
+            return x ? x : (size_t)(16u << 20);
+        }();
+        return v;
+    }
+    explicit GzAhead(const std::string &path) : path_(path) {
+        thread_ = std::thread([this] { run(); });
+    }
+    ~GzAhead() {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            cancel_ = true;
+        }
+        space_.notify_all();
+        thread_.join();
+    }
+    GzAhead(const GzAhead &) = delete;
+    GzAhead &operator=(const GzAhead &) = delete;
+    const std::string &path() const { return path_; }
+    // Copies up to want bytes of the inflated stream to dst; less than want only at the end of the file.
+    size_t read(char *dst, size_t want) {
+        size_t done = 0;
+        while (done < want) {
+            std::unique_lock<std::mutex> g(mu_);
+            data_.wait(g, [this] { return !q_.empty() || finished_; });
+            if (q_.empty()) break;  // finished and drained
+            Block &b = q_.front();
+            const size_t n = std::min(want - done, b.len - b.pos);
+            g.unlock();  // the front block is only ever touched by this (single) consumer
+            memcpy(dst + done, b.p.get() + b.pos, n);
+            done += n;
+            g.lock();
+            b.pos += n;
+            if (b.pos == b.len) {
+                spare_.push_back(std::move(b.p));  // recycled: fresh 16 MB allocations page-fault every time
+                q_.pop_front();
+                space_.notify_one();
+            }
+        }
+        return done;
+    }
+
+  private:
+    struct Block {
+        std::unique_ptr<char[]> p;
+        size_t len = 0, pos = 0;
+    };
+    void run() {
+        gzFile gz = gzopen(path_.c_str(), "rb");
+        if (!gz) die("Failed to open '" + path_ + "'");
+        gzbuffer(gz, 1 << 20);
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                space_.wait(g, [this] { return cancel_ || q_.size() < kMaxBlocks; });
+                if (cancel_) break;
+            }
+            const size_t cap = block_bytes();
+            Block b;
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (!spare_.empty()) {
+                    b.p = std::move(spare_.back());
+                    spare_.pop_back();
+                }
+            }
+            if (!b.p) b.p.reset(new char[cap]);
+            bool end = false;
+            while (b.len < cap) {
+                const int n = gzread(gz, b.p.get() + b.len, (unsigned)(cap - b.len));
+                if (n < 0) die("corrupt gzip input '" + path_ + "'");
+                if (n == 0) {
+                    end = true;
+                    break;
+                }
+                b.len += (size_t)n;
+            }
+            std::lock_guard<std::mutex> g(mu_);
+            if (b.len) q_.push_back(std::move(b));
+            if (end) finished_ = true;
+            data_.notify_one();
+            if (end) break;
+        }
+        gzclose(gz);
+        std::lock_guard<std::mutex> g(mu_);
+        finished_ = true;
+        data_.notify_one();
+    }
+    std::string path_;
+    std::mutex mu_;
+    std::condition_variable data_, space_;
+    std::deque<Block> q_;
+    std::vector<std::unique_ptr<char[]>> spare_;
+    bool finished_ = false, cancel_ = false;
+    std::thread thread_;
+};
+
 // ---- one input file, read in large stretches (open_reader: file_parser.rs:89-101) -------------------------------
 class SeqFile {
   public:
-    SeqFile(const std::string &path, Fmt fmt, Pool *pool, ParseScratch *scratch = nullptr) : fmt_(fmt), pool_(pool), scratch_(scratch) {
+    // ahead: an inflater ReadQueue already started for this file (gzip), or null
+    SeqFile(const std::string &path, Fmt fmt, Pool *pool, ParseScratch *scratch = nullptr, std::unique_ptr<GzAhead> ahead = nullptr)
+        : fmt_(fmt), pool_(pool), scratch_(scratch), gz_(std::move(ahead)) {
         // plain regular files are read with pread (several threads); gzip and everything else through zlib
+        if (gz_ || is_gzip_or_special(path)) {
+            if (!gz_) gz_.reset(new GzAhead(path));
+            // first buffer size: sequence text inflates 3-6x; a pipe or device has no size, take the full buffer
+            struct stat st;
+            gz_guess_ = stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode) ? (size_t)st.st_size * 8 : ~(size_t)0 >> 1;
+            return;
+        }
         fd_ = open(path.c_str(), O_RDONLY);
         if (fd_ < 0) die("Failed to open '" + path + "'");
         struct stat st;
-        unsigned char magic[2] = {0, 0};
-        const bool regular = fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0;
-        const bool gz = pread(fd_, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
-        if (regular && !gz) {
-            fsize_ = (size_t)st.st_size;
-        } else {
-            close(fd_);
-            fd_ = -1;
-            gz_ = gzopen(path.c_str(), "rb");
-            if (!gz_) die("Failed to open '" + path + "'");
-            gzbuffer(gz_, 1 << 20);
-        }
+        if (fstat(fd_, &st) != 0) die("Failed to open '" + path + "'");
+        fsize_ = (size_t)st.st_size;
     }
     ~SeqFile() {
-        if (gz_) gzclose(gz_);
         if (fd_ >= 0) close(fd_);
     }
     SeqFile(const SeqFile &) = delete;
@@ -524,7 +642,7 @@ class SeqFile {
         const size_t before = out.size();
         buf_bytes = std::max<size_t>(buf_bytes, 64);
         // small inputs get small buffers (a directory of many small files must not reserve 256 MB for each)
-        size_t want = gz_ ? std::min<size_t>(buf_bytes, 8u << 20) : std::min(buf_bytes, tail_.size() + (fsize_ - foff_));
+        size_t want = gz_ ? std::min<size_t>(buf_bytes, std::max<size_t>(8u << 20, gz_guess_)) : std::min(buf_bytes, tail_.size() + (fsize_ - foff_));
         buf.reserve(std::max<size_t>(std::max<size_t>(want, 64), tail_.size() * 2));
         size_t len = tail_.size();
         if (len) memcpy(buf.p, tail_.data(), len);
@@ -555,18 +673,11 @@ class SeqFile {
     bool fill(RawBuf &buf, size_t &len) {
         if (eof_ || len >= buf.cap) return false;
         if (gz_) {
-            bool got = false;
-            while (len < buf.cap) {
-                const size_t want = std::min<size_t>(buf.cap - len, 1u << 30);
-                const int n = gzread(gz_, buf.p + len, (unsigned)want);
-                if (n <= 0) {
-                    eof_ = true;
-                    break;
-                }
-                len += (size_t)n;
-                got = true;
-            }
-            return got;
+            const size_t want = buf.cap - len;
+            const size_t n = gz_->read(buf.p + len, want);
+            len += n;
+            if (n < want) eof_ = true;
+            return n > 0;
         }
         const size_t want = std::min(buf.cap - len, fsize_ - foff_);
         const int T = pool_ ? (int)std::min<size_t>((size_t)pool_->size(), want / (4u << 20) + 1) : 1;
@@ -595,8 +706,8 @@ class SeqFile {
     Pool *pool_;
     ParseScratch *scratch_;
     int fd_ = -1;
-    gzFile gz_ = nullptr;
-    size_t fsize_ = 0, foff_ = 0, min_segment_ = 256u << 10;
+    std::unique_ptr<GzAhead> gz_;
+    size_t fsize_ = 0, foff_ = 0, gz_guess_ = 0, min_segment_ = 256u << 10;
     bool eof_ = false;
     size_t last_bytes_ = 0;
     std::vector<char> tail_;  // the incomplete record at the end of the previous stretch
@@ -634,7 +745,19 @@ class ReadQueue {
             if (files_.empty()) return false;
             const std::string f = files_.back();  // popped from the END (file_parser.rs:238)
             files_.pop_back();
-            cur_ = new SeqFile(f, detect_format(f, fmt_), pool_, &scratch_);
+            std::unique_ptr<GzAhead> mine;
+            if (!ahead_.empty() && ahead_.front()->path() == f) {
+                mine = std::move(ahead_.front());
+                ahead_.pop_front();
+            }
+            // start inflating the next queued gzip files: ahead_[j] belongs to files_[size - 1 - j]
+            const size_t want_ahead = pool_ ? std::min<size_t>((size_t)std::max(pool_->size() - 1, 0), kAheadFiles) : 0;
+            for (size_t j = ahead_.size(); j < want_ahead && j < files_.size(); ++j) {
+                const std::string &next = files_[files_.size() - 1 - j];
+                if (!is_gzip_or_special(next)) break;  // plain files are read in place; the run of inflaters stays contiguous
+                ahead_.emplace_back(new GzAhead(next));
+            }
+            cur_ = new SeqFile(f, detect_format(f, fmt_), pool_, &scratch_, std::move(mine));
             cur_->set_min_segment(min_segment_);
         }
         const bool got = cur_->next_records(buf, buf_bytes, out);
@@ -651,6 +774,8 @@ class ReadQueue {
     std::vector<std::string> files_;
     Fmt fmt_;
     Pool *pool_;
+    static constexpr size_t kAheadFiles = 8;
+    std::deque<std::unique_ptr<GzAhead>> ahead_;  // inflaters of files_[size-1], files_[size-2], ... in that order
     SeqFile *cur_ = nullptr;
     ParseScratch scratch_;
     size_t min_segment_ = 256u << 10, last_bytes_ = 0;

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "phagefilter_b200", "bin", "phage_filter")
 
 
-def parse_cli(path, buf=1 << 20, chunk=None, fmt=None, threads=None, min_segment=None, block=None, pack=False):
+def parse_cli(path, buf=1 << 20, chunk=None, fmt=None, threads=None, min_segment=None, block=None, pack=False, env=None):
     """chunk (the old reader's record cap) is accepted and unused.  Unless told otherwise the run uses 1 or 5
     parser threads and small segments (derived from buf), so every call site also covers the threaded path."""
     if threads is None:
@@ -29,7 +29,7 @@ def parse_cli(path, buf=1 << 20, chunk=None, fmt=None, threads=None, min_segment
         args += ["--pack"]
     if fmt:
         args += ["-F", fmt]
-    p = subprocess.run(args, capture_output=True)
+    p = subprocess.run(args, capture_output=True, env=dict(os.environ, **(env or {})))
     assert p.returncode == 0, p.stderr.decode()
     out = []
     for line in p.stdout.split(b"\n"):
@@ -189,3 +189,30 @@ def test_blocks_carry_and_packer_view(tmp_path):
     for block, buf, batch in ((1, 1 << 20, None), (7, 300, None), (64, 5000, None), (1000, 1 << 20, None), (100, 1 << 20, None)):
         got = parse_cli(d, block=block, buf=buf, pack=True)
         assert got == order, (block, buf)
+
+
+def test_gzip_files_inflated_ahead(tmp_path):
+    """A directory of gzip files (plus plain ones in between): the next files are inflated on their own threads while
+    the current one is parsed; tiny inflate blocks force the bounded queue to fill and drain many times."""
+    rng = np.random.default_rng(21)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    d = tmp_path / "lanes"
+    d.mkdir()
+    expect = {}
+    for k in range(9):
+        recs = [(f"l{k}_{i}", acgt[rng.integers(0, 4, size=int(rng.choice([1, 50, 150])))].tobytes(),
+                 bytes(rng.integers(46, 74, size=1, dtype=np.uint8)) * 0) for i in range(int(rng.integers(1, 400)))]
+        recs = [(r, s, bytes(rng.integers(46, 74, size=len(s), dtype=np.uint8))) for r, s, _ in recs]
+        blob = b"".join(b"@" + r.encode() + b"\n" + s + b"\n+\n" + q + b"\n" for r, s, q in recs)
+        name = f"lane{k}.fastq" + ("" if k in (3, 4) else ".gz")
+        if name.endswith(".gz"):
+            with gzip.open(d / name, "wb") as f:
+                f.write(blob)
+        else:
+            (d / name).write_bytes(blob)
+        expect[name] = recs
+    (d / "empty.fq.gz").write_bytes(gzip.compress(b""))
+    order = [x for name in sorted(expect, reverse=True) for x in expect[name]]
+    for threads, blk in ((1, "100000"), (4, "512"), (12, "97"), (3, "16777216")):
+        got = parse_cli(d, threads=threads, buf=3000 if threads != 3 else 1 << 20, block=50, pack=True, env={"PF_GZ_BLOCK": blk})
+        assert got == order, (threads, blk)
