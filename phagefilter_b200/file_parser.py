@@ -48,8 +48,12 @@ def detect_format(path: str, override: str = "auto") -> str:
             return "fastq"
     except OSError:
         pass
-    name = os.path.basename(path)
-    parts = name.split(".")
+    return format_from_extension(path)
+
+
+def format_from_extension(path: str) -> str:
+    """file_parser.rs:69-86: the extension inside .gz/.gzip decides; anything that is not fq/fastq is FASTA."""
+    parts = os.path.basename(path).split(".")
     ext = parts[-1] if len(parts) > 1 else ""
     if ext.lower() in COMPRESSED_EXTENSIONS and len(parts) > 2:
         ext = parts[-2]
