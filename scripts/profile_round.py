@@ -105,6 +105,9 @@ def cmd_summarise(tag):
     probe = [r[2] / 1e6 for r in rows if "probe_kernel" in r[1]]
     print("  probe levels (ms):", ", ".join(f"{x:.2f}" for x in probe))
     # full-set summary: metrics as rows, launches as columns
+    if not os.path.exists(os.path.join(src, "full_raw.csv")):
+        print("no full_raw.csv (the full-set pass did not finish): launch list only")
+        return
     with open(os.path.join(src, "full_raw.csv"), newline="") as f:
         rd = list(csv.reader(ln for ln in f if ln.startswith('"')))
     header, units, launches = rd[0], rd[1], rd[2:]
