@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <filesystem>
 #include <set>
 #include <string>
 #include <string_view>
@@ -17,6 +18,18 @@
 #include "seq_reader.h"
 
 namespace pfhost {
+
+// main.rs:380-391: an existing output directory is removed with everything in it, then created again (the parent must
+// exist, like fs::create_dir)
+inline void create_and_overwrite_directory(const std::string &dir) {
+    std::error_code ec;
+    if (std::filesystem::is_directory(dir, ec)) {
+        std::filesystem::remove_all(dir, ec);
+        if (ec) die("cannot remove '" + dir + "': " + ec.message());
+    }
+    std::filesystem::create_directory(dir, ec);
+    if (ec) die("cannot create '" + dir + "': " + ec.message());
+}
 
 class FilterWriter {
   public:

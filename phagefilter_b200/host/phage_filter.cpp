@@ -98,14 +98,6 @@ Fmt parse_fmt(const std::string &s) {
     die("invalid value '" + s + "' for '--format'");
 }
 
-void create_and_overwrite_directory(const std::string &dir) {  // main.rs:380-391
-    struct stat st;
-    if (stat(dir.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) {
-        std::string cmd = "rm -rf -- '" + dir + "'";
-        if (system(cmd.c_str()) != 0) die("cannot remove " + dir);
-    }
-    mkdir(dir.c_str(), 0777);
-}
 constexpr size_t kParseBufBytes = 256u << 20;
 
 struct PhaseTimer {  // --stats: where the time of a run goes (one timer per host thread; stages overlap)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """One-call profiling of the bench step (cfg 2) and the summaries that go under profiles/.
 
-On the GPU box (one gpurun call; the recipe is /opt/skills/guides/B200_PROFILING.md):
+On the GPU box (one gpurun call of about 4 minutes -- the full-set pass alone replays ten launches ~40 times each and
+every ncu pass is preceded by the pool's own plain run; the recipe is /opt/skills/guides/B200_PROFILING.md):
     python scripts/profile_round.py run --tag r2a
   1. plain `python bench.py --steps 5 --warmup 3`                      -> gpurun_out/<tag>/bench.json
   2. plain `python bench.py --steps 1 --warmup 3 --profile` (must exit 0 before anything runs under ncu)

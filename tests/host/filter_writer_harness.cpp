@@ -17,6 +17,7 @@ int main(int argc, char **argv) {
     const size_t batch_reads = strtoull(argv[8], nullptr, 10);  // a multiple of block, like the driver's GPU batches
     std::vector<std::string> leaf_ids;
     for (uint32_t l = 0; l < n_leaves; ++l) leaf_ids.push_back("genome_" + std::to_string(l));
+    create_and_overwrite_directory(out);  // the driver's own helper: stale content must be gone afterwards
     Pool pool(threads);
     ReadQueue q(reads, Fmt::Auto, &pool);
     const char *ext = q.peek_format() == Fmt::Fastq ? "fq" : "fa";

@@ -64,7 +64,10 @@ def test_filter_writer_matches_reference_logic(harness, tmp_path, fastq):
     for block, threads, pos, neg, batch_blocks in ((100, 4, 1, 1, 3), (7, 8, 1, 1, 50), (1, 3, 1, 0, 1000), (1000, 1, 0, 1, 1),
                                                    (64, 16, 1, 1, 1), (5000, 2, 1, 1, 1)):
         out = tmp_path / f"out_{block}_{threads}_{pos}{neg}"
-        out.mkdir()
+        if threads % 2 == 0:  # an existing directory is emptied (main.rs:380-391); a missing one is created
+            (out / "sub").mkdir(parents=True)
+            (out / "sub" / "stale.txt").write_text("x")
+            (out / "POS_FILTERING.fa").write_text("stale")
         subprocess.run([harness, str(path), str(out), str(block), str(threads), str(pos), str(neg), "9", str(block * batch_blocks)], check=True)
         want_pos, want_neg = expected(records, block, 9, pos, neg, fastq)
         assert sorted(os.listdir(out)) == sorted((["NEG_FILTERING." + ext] if neg else []) + (["POS_FILTERING." + ext] if pos else []))
