@@ -31,16 +31,45 @@ inline void create_and_overwrite_directory(const std::string &dir) {
     if (ec) die("cannot create '" + dir + "': " + ec.message());
 }
 
+// POS_FILTERING.<ext> / NEG_FILTERING.<ext> in the output directory; only the files whose flag was given exist
+// (main.rs:311-321).  Plain file descriptors: the writer places every task's bytes with pwrite.
+class FilterFiles {
+  public:
+    FilterFiles(const std::string &out_dir, const char *ext, bool pos, bool neg) {
+        if (pos) pos_fd_ = create(out_dir + "/POS_FILTERING." + ext);
+        if (neg) neg_fd_ = create(out_dir + "/NEG_FILTERING." + ext);
+    }
+    ~FilterFiles() { close_all(); }
+    FilterFiles(const FilterFiles &) = delete;
+    FilterFiles &operator=(const FilterFiles &) = delete;
+    int pos_fd() const { return pos_fd_; }
+    int neg_fd() const { return neg_fd_; }
+    void close_all() {
+        if (pos_fd_ >= 0 && ::close(pos_fd_) != 0) die("cannot write POS_FILTERING");
+        pos_fd_ = -1;
+        if (neg_fd_ >= 0 && ::close(neg_fd_) != 0) die("cannot write NEG_FILTERING");
+        neg_fd_ = -1;
+    }
+
+  private:
+    static int create(const std::string &path) {
+        const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (fd < 0) die("cannot create " + path);
+        return fd;
+    }
+    int pos_fd_ = -1, neg_fd_ = -1;
+};
+
 class FilterWriter {
   public:
-    // pos_fp / neg_fp may be null (flag not given: such records are written nowhere, main.rs:350-359).
-    FilterWriter(FILE *pos_fp, FILE *neg_fp, size_t block, const std::vector<std::string> *leaf_ids, Pool *pool)
-        : pos_fp_(pos_fp), neg_fp_(neg_fp), block_(block), leaf_ids_(leaf_ids), pool_(pool) {}
+    // pos_fd / neg_fd may be -1 (flag not given: such records are written nowhere, main.rs:350-359).
+    FilterWriter(int pos_fd, int neg_fd, size_t block, const std::vector<std::string> *leaf_ids, Pool *pool)
+        : pos_fd_(pos_fd), neg_fd_(neg_fd), block_(block), leaf_ids_(leaf_ids), pool_(pool) {}
 
     // recs[0..n): the records of whole blocks (only the last block of the input may be short);
     // read_off[n+1], leaf[]: the per-read hit lists of pf_hits (DFS leaf indices).
     void write(const Record *recs, size_t n, const uint64_t *read_off, const uint32_t *leaf) {
-        if (!n || (!pos_fp_ && !neg_fp_)) return;
+        if (!n || (pos_fd_ < 0 && neg_fd_ < 0)) return;
         const size_t n_blocks = (n + block_ - 1) / block_;
         const size_t tasks = std::min<size_t>(n_blocks, (size_t)(pool_ ? pool_->size() : 1) * 4);
         if (pos_.size() < tasks) pos_.resize(tasks), neg_.resize(tasks);
@@ -60,7 +89,7 @@ class FilterWriter {
                     const Record &r = recs[i];
                     auto it = result_map.empty() ? result_map.end() : result_map.find(std::string_view(r.id, r.id_len));
                     const bool mapped = it != result_map.end();
-                    if ((mapped && !pos_fp_) || (!mapped && !neg_fp_)) continue;
+                    if ((mapped && pos_fd_ < 0) || (!mapped && neg_fd_ < 0)) continue;
                     std::string &o = mapped ? pos : neg;
                     o.push_back(r.has_qual ? '@' : '>');  // main.rs:394-404
                     o.append(r.id, r.id_len);
@@ -89,14 +118,35 @@ class FilterWriter {
         if (pool_) pool_->run((int)tasks, job);
         else
             for (size_t t = 0; t < tasks; ++t) job((int)t);
+        // input order = task order: every task's bytes go to their place in the file, all tasks at once (one thread
+        // copying 1.3 GB into the page cache was 3/4 of the output time)
+        std::vector<uint64_t> pos_at(tasks), neg_at(tasks);
         for (size_t t = 0; t < tasks; ++t) {
-            if (pos_fp_ && !pos_[t].empty() && fwrite(pos_[t].data(), 1, pos_[t].size(), pos_fp_) != pos_[t].size()) die("cannot write POS_FILTERING");
-            if (neg_fp_ && !neg_[t].empty() && fwrite(neg_[t].data(), 1, neg_[t].size(), neg_fp_) != neg_[t].size()) die("cannot write NEG_FILTERING");
+            pos_at[t] = pos_size_;
+            neg_at[t] = neg_size_;
+            pos_size_ += pos_[t].size();
+            neg_size_ += neg_[t].size();
         }
+        auto put = [&](int t) {
+            if (pos_fd_ >= 0) pwrite_all(pos_fd_, pos_[(size_t)t], pos_at[(size_t)t], "cannot write POS_FILTERING");
+            if (neg_fd_ >= 0) pwrite_all(neg_fd_, neg_[(size_t)t], neg_at[(size_t)t], "cannot write NEG_FILTERING");
+        };
+        if (pool_) pool_->run((int)tasks, put);
+        else
+            for (size_t t = 0; t < tasks; ++t) put((int)t);
     }
 
   private:
-    FILE *pos_fp_, *neg_fp_;
+    static void pwrite_all(int fd, const std::string &buf, uint64_t at, const char *what) {
+        size_t done = 0;
+        while (done < buf.size()) {
+            const ssize_t w = ::pwrite(fd, buf.data() + done, buf.size() - done, (off_t)(at + done));
+            if (w <= 0) die(what);
+            done += (size_t)w;
+        }
+    }
+    int pos_fd_, neg_fd_;
+    uint64_t pos_size_ = 0, neg_size_ = 0;
     size_t block_;
     const std::vector<std::string> *leaf_ids_;
     Pool *pool_;

@@ -344,13 +344,9 @@ int cmd_query(const Args &a) {
     }
     create_and_overwrite_directory(out);
     const char *ext = ingest->peek_format() == Fmt::Fastq ? "fq" : "fa";
-    FILE *pos_fp = nullptr, *neg_fp = nullptr;
-    if (pos && !(pos_fp = fopen((out + "/POS_FILTERING." + ext).c_str(), "wb"))) die("cannot create POS_FILTERING");
-    if (neg && !(neg_fp = fopen((out + "/NEG_FILTERING." + ext).c_str(), "wb"))) die("cannot create NEG_FILTERING");
-    if (pos_fp) setvbuf(pos_fp, nullptr, _IOFBF, 4u << 20);
-    if (neg_fp) setvbuf(neg_fp, nullptr, _IOFBF, 4u << 20);
+    FilterFiles files(out, ext, pos, neg);
     Pool out_pool(filtering ? host_threads : 1);
-    FilterWriter writer(pos_fp, neg_fp, block, &leaf_ids, &out_pool);
+    FilterWriter writer(files.pos_fd(), files.neg_fd(), block, &leaf_ids, &out_pool);
     timer.lap("setup");
 
     for (bool last = false; !last;) {
@@ -369,8 +365,7 @@ int cmd_query(const Args &a) {
         last = c->last;
         ingest->release(c);
     }
-    if (pos_fp && fclose(pos_fp) != 0) die("cannot write POS_FILTERING");
-    if (neg_fp && fclose(neg_fp) != 0) die("cannot write NEG_FILTERING");
+    files.close_all();
     check(pf_save_leaf_counts(db, (out + "/CLASSIFICATION.csv").c_str()), "save_leaf_counts");
     const PhaseTimer ingest_timer = ingest->timer();
     timer.lap("finish");

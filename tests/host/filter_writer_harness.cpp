@@ -21,12 +21,13 @@ int main(int argc, char **argv) {
     Pool pool(threads);
     ReadQueue q(reads, Fmt::Auto, &pool);
     const char *ext = q.peek_format() == Fmt::Fastq ? "fq" : "fa";
-    FILE *pf = pos ? fopen((out + "/POS_FILTERING." + ext).c_str(), "wb") : nullptr;
-    FILE *nf = neg ? fopen((out + "/NEG_FILTERING." + ext).c_str(), "wb") : nullptr;
-    FilterWriter w(pf, nf, block, &leaf_ids, &pool);
+    FilterFiles files(out, ext, pos, neg);
+    FilterWriter w(files.pos_fd(), files.neg_fd(), block, &leaf_ids, &pool);
     RawBuf buf;
     std::vector<Record> recs;
-    while (q.next_records(buf, 64u << 20, recs)) {}  // one small file: everything lands in one buffer
+    struct stat st;
+    if (stat(reads.c_str(), &st) != 0) return 3;
+    while (q.next_records(buf, (size_t)st.st_size + 4096, recs)) {}  // one plain file: everything lands in one buffer
     size_t g = 0;  // global read index: the rule depends on it, not on the batch
     for (size_t lo = 0; lo < recs.size(); lo += batch_reads) {
         const size_t n = std::min(batch_reads, recs.size() - lo);
@@ -41,7 +42,6 @@ int main(int argc, char **argv) {
         }
         w.write(recs.data() + lo, n, off.data(), leaf.data());
     }
-    if (pf) fclose(pf);
-    if (nf) fclose(nf);
+    files.close_all();
     return 0;
 }
