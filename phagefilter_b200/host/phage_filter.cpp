@@ -323,7 +323,8 @@ int cmd_query(const Args &a) {
     uint64_t total_reads = 0;
     // GPU batches are whole multiples of the reference's block, so block boundaries stay where they were
     const size_t batch_reads = std::max(block, gpu_batch / block * block);
-    auto ingest = std::make_unique<Ingest>(a.get("reads"), parse_fmt(a.get("format", "auto")), kParseBufBytes, block, batch_reads, true, host_threads, device);
+    const size_t buf_bytes = getenv("PF_PARSE_BUF_BYTES") ? strtoull(getenv("PF_PARSE_BUF_BYTES"), nullptr, 10) : kParseBufBytes;  // tests: many chunks
+    auto ingest = std::make_unique<Ingest>(a.get("reads"), parse_fmt(a.get("format", "auto")), buf_bytes, block, batch_reads, true, host_threads, device);
     // CUDA start-up and the database load run alone: started before them, the ingest threads' page faults and pinned
     // allocations contend with the driver's own memory mapping (measured: start-up up to 3.8 s instead of ~1 s)
     pf_db *db = nullptr;
