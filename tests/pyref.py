@@ -47,13 +47,20 @@ def optimal_num_hashes(bits: int, n: int) -> int:
     return min(max(v, 2), 200)
 
 
+_H12: Dict[tuple, Tuple[int, int]] = {}
+
+
 class Filter:
     def __init__(self, m: int, k_hashes: int, seeds: Tuple[int, int], rot: int):
         self.m, self.K, self.seeds, self.rot = m, k_hashes, seeds, rot
         self.bits = bytearray(m)  # one byte per bit: simple beats fast here
 
     def _indices(self, item: bytes):
-        h1, h2 = py_fx_hash(self.seeds[0], item, self.rot), py_fx_hash(self.seeds[1], item, self.rot)
+        key = (self.seeds, self.rot, item)
+        hh = _H12.get(key)
+        if hh is None:  # the two hashes depend on the item only: computed once per distinct k-mer (speed, not semantics)
+            hh = _H12[key] = (py_fx_hash(self.seeds[0], item, self.rot), py_fx_hash(self.seeds[1], item, self.rot))
+        h1, h2 = hh
         for i in range(self.K):
             g = h1 if i == 0 else h2 if i == 1 else (((h1 + i) & MASK) * h2) & MASK
             yield g % self.m

@@ -97,3 +97,40 @@ def test_oracle_and_python_restatement_agree(oracle, tmp_path, case):
         got = {(int(r), int(l)) for r, l in o2.query_batch(reads, 0.5).hits}
         assert got == p2.query_batch(reads, 0.5), depth
         assert [c for _, c in o2.leaf_counts()] == [n.mapped_reads for n in p2.leaves()]
+
+
+def test_python_restatement_reproduces_golden_fixture():
+    """tests/golden/expected.json is oracle-generated; the plain-Python restatement, built from the same genomes,
+    reproduces its geometry, topology, leaf order, hit sets and CLASSIFICATION.csv (theta 1.0 / 0.8 and --search-depth 2)."""
+    import json
+    import os
+    from phagefilter_b200.file_parser import read_records
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    exp = json.load(open(os.path.join(gold, "expected.json")))
+    genomes = [(r.id, r.sequence) for r in read_records(os.path.join(gold, "genomes.fa"))]
+    reads = [r.sequence for r in read_records(os.path.join(gold, "reads.fq"))]
+
+    def build():
+        t = pyref.Tree(exp["k"], exp["fpr"], exp["largest"], 0x5EED0001, 0x5EED0002)
+        for gid, seq in genomes:
+            t.insert(gid, seq)
+        return t
+    t = build()
+    assert (t.m, t.K) == (exp["num_bits"], exp["num_hashes"])
+    assert [n.tax_id for n in t.leaves()] == exp["leaf_ids"]
+    assert t.preorder() == [(bool(leaf), d) for _, leaf, d in exp["preorder"]]
+    for theta in ("1.0", "0.8"):
+        for n in t.leaves():
+            n.mapped_reads = 0
+        hits = t.query_batch(reads, float(theta))
+        got = [sorted(l for r, l in hits if r == i) for i in range(len(reads))]
+        assert got == exp["cases"][theta]["hits"], theta
+        assert t.classification_csv() == exp["cases"][theta]["csv"]
+    t2 = build()
+    t2.prune_tree(2)
+    hits = t2.query_batch(reads, 0.8)
+    case = exp["cases"]["depth2"]
+    assert [sorted(l for r, l in hits if r == i) for i in range(len(reads))] == case["hits"]
+    assert len(t2.leaves()) == len(case["leaf_ids"]) and t2.classification_csv().count("\n") == case["csv"].count("\n")
+    # pruned leaves are interior nodes: their names are arbitrary (random u16 in the reference), the counts are not
+    assert [c.split(",")[1] for c in t2.classification_csv().split()] == [c.split(",")[1] for c in case["csv"].split()]
