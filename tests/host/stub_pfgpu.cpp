@@ -61,4 +61,33 @@ int pf_save_leaf_counts(pf_db *, const char *csv_path) {
     return PF_OK;
 }
 void pf_db_close(pf_db *) {}
+
+// build / add: the stub "database" is a log of what the driver asked for, written at save time
+static std::string g_log;
+int pf_builder_create(uint64_t k, float fpr, uint32_t largest, uint64_t s1, uint64_t s2, int, int name_mode, uint64_t, pf_builder **out) {
+    char b[256];
+    snprintf(b, sizeof b, "create k=%llu fpr=%g largest=%u seeds=%llu,%llu names=%d\n", (unsigned long long)k, (double)fpr, largest,
+             (unsigned long long)s1, (unsigned long long)s2, name_mode);
+    g_log = b;
+    *out = reinterpret_cast<pf_builder *>(&g_log);
+    return PF_OK;
+}
+int pf_builder_open(const char *db_path, int, pf_builder **out) {
+    if (std::string(db_path).find("missing") != std::string::npos) return PF_ERR_IO;
+    g_log = std::string("open ") + db_path + "\n";
+    *out = reinterpret_cast<pf_builder *>(&g_log);
+    return PF_OK;
+}
+int pf_builder_insert(pf_builder *, const char *id, const uint8_t *seq, uint64_t len) {
+    g_log += std::string("insert ") + id + " " + std::string(reinterpret_cast<const char *>(seq), (size_t)len) + "\n";
+    return PF_OK;
+}
+int pf_builder_save(pf_builder *, const char *db_path) {
+    FILE *fp = fopen(db_path, "wb");  // the test passes a file path as --db-path
+    if (!fp) return PF_ERR_IO;
+    fwrite(g_log.data(), 1, g_log.size(), fp);
+    fclose(fp);
+    return PF_OK;
+}
+void pf_builder_free(pf_builder *) {}
 }

@@ -128,3 +128,38 @@ def test_query_driver_directory_no_flags_and_errors(stub, tmp_path):
     bad.write_bytes(b"@r1\nACGT\n+\nIIII\nnot a header\nAC\n+\nII\n")
     p = run_query(stub, ["-r", str(bad), "-o", str(out), "-d", str(tmp_path)])
     assert p.returncode == 101 and b"Expected @" in p.stderr
+
+
+def test_build_and_add_driver(stub, tmp_path):
+    """`build` / `add`: one leaf per record (main.rs:173-195), files popped from the end of the sorted listing, multi-line
+    and gzip FASTA, the flags of main.rs:38-99 -- against a log the stub builder writes."""
+    rng = np.random.default_rng(50)
+    d = tmp_path / "genomes"
+    d.mkdir()
+    parts = {}
+    for k, name in enumerate(["a.fna", "b.fasta.gz", "c.fa", "d.fas"]):
+        recs = [(f"{name}_{i}", np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, size=int(rng.integers(1, 4000)))].tobytes())
+                for i in range(1 + k)]
+        blob = b"".join(b">" + r.encode() + b" description\n" + b"".join(s[j:j + 70] + b"\n" for j in range(0, len(s), 70)) for r, s in recs)
+        with (gzip.open(d / name, "wb") if name.endswith(".gz") else open(d / name, "wb")) as f:
+            f.write(blob)
+        parts[name] = recs
+    (d / "README.txt").write_text("not a genome")
+    order = [x for name in sorted(parts, reverse=True) for x in parts[name]]
+    db = tmp_path / "db.log"
+    e = dict(os.environ, LD_PRELOAD=stub)
+    p = subprocess.run([BIN, "build", "-g", str(d), "-d", str(db), "-k", "21", "-f", "0.01", "-l", "5000", "--seed-one", "11", "--seed-two", "12",
+                        "-t", "4", "-c", "7", "--host-threads", "3"], capture_output=True, env=e, timeout=120)
+    assert p.returncode == 0, p.stderr.decode()
+    assert p.stdout.decode().splitlines() == ["Building the SBT...", "Finished."]
+    log = open(db, "rb").read().split(b"\n")
+    assert log[0] == b"create k=21 fpr=0.01 largest=5000 seeds=11,12 names=1"
+    assert log[1:-1] == [b"insert " + r.encode() + b" " + s for r, s in order]
+    p = subprocess.run([BIN, "add", "-g", str(d / "c.fa"), "-d", str(db)], capture_output=True, env=e, timeout=120)
+    assert p.returncode == 0 and p.stdout.decode().splitlines() == ["Adding new genomes to the SBT...", "Finished."]
+    log = open(db, "rb").read().split(b"\n")
+    assert log[0].startswith(b"open ") and log[1:-1] == [b"insert " + r.encode() + b" " + s for r, s in parts["c.fa"]]
+    p = subprocess.run([BIN, "add", "-g", str(d), "-d", str(tmp_path / "missing")], capture_output=True, env=e, timeout=120)
+    assert p.returncode == 101 and b"BloomTree::load" in p.stderr
+    p = subprocess.run([BIN, "build", "-g", str(d)], capture_output=True, env=e, timeout=120)
+    assert p.returncode == 101 and b"required arguments" in p.stderr
