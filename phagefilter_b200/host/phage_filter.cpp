@@ -228,8 +228,8 @@ class Ingest {
                     const size_t cnt = std::min(batch_reads_, n - lo);
                     ptrs.resize(cnt);
                     lens.resize(cnt);
-                    pool_.run((int)std::min<size_t>((size_t)pool_.size(), cnt / 65536 + 1), [&](int t) {
-                        const size_t T = std::min<size_t>((size_t)pool_.size(), cnt / 65536 + 1);
+                    const size_t T = std::min<size_t>((size_t)pool_.size(), cnt / 65536 + 1);
+                    pool_.run((int)T, [&](int t) {
                         for (size_t i = cnt * (size_t)t / T; i < cnt * ((size_t)t + 1) / T; ++i) {
                             ptrs[i] = (const uint8_t *)c->recs[lo + i].seq;  // k-mers come from the raw bytes (file_parser.rs:203-205)
                             lens[i] = c->recs[lo + i].seq_len;
