@@ -117,16 +117,25 @@ void pfo_hash_iter(uint64_t h1, uint64_t h2, uint32_t count, uint64_t *out) {
  * bio::alphabets::dna::complement table: identity except the IUPAC pairs below, with
  * lower-case variants mapped likewise (case preserved).
  * ---------------------------------------------------------------------------------------- */
+/* The table is filled once, at load time (constructor), before any thread can use it; comp_init() stays as a
+ * guard for static linking.  Every entry is computed by a pure function and stored exactly once with its
+ * final value, so even a concurrent second initialisation could only rewrite identical bytes (round 1 filled
+ * the table with the identity first and patched it afterwards: a late thread doing that inside the OpenMP
+ * region of query_impl made 'A'->'A' visible to threads already canonicalising). */
 static uint8_t g_comp[256];
-static int g_comp_init = 0;
-static void comp_init(void) {
-    if (g_comp_init) return;
-    for (int v = 0; v < 256; v++) g_comp[v] = (uint8_t)v;
-    const char *a = "AGCTYRWSKMDVHBN", *b = "TCGARYWSMKHBDVN";
+static volatile int g_comp_init = 0;
+static uint8_t comp_of(int v) {
+    static const char a[] = "AGCTYRWSKMDVHBN", b[] = "TCGARYWSMKHBDVN";
     for (int i = 0; a[i]; i++) {
-        g_comp[(uint8_t)a[i]] = (uint8_t)b[i];
-        g_comp[(uint8_t)a[i] + 32] = (uint8_t)(b[i] + 32);
+        if (v == (uint8_t)a[i]) return (uint8_t)b[i];
+        if (v == (uint8_t)a[i] + 32) return (uint8_t)(b[i] + 32);
     }
+    return (uint8_t)v;
+}
+__attribute__((constructor)) static void comp_init(void) {
+    if (g_comp_init) return;
+    for (int v = 0; v < 256; v++) g_comp[v] = comp_of(v);
+    __sync_synchronize();
     g_comp_init = 1;
 }
 uint8_t pfo_complement(uint8_t b) {
