@@ -170,6 +170,10 @@ typedef struct pf_stats_t {
     uint64_t group_rounds;    /* rounds of 32 k-mers each lane owned at once in the last call (1..8) */
     uint64_t memo_hits;       /* k-mers answered by the k-mer memo instead of K - 1 probes (pf_db_set_memo) */
     uint64_t memo_lookups;    /* k-mers looked up in the memo (one 8-byte read each) */
+    uint64_t sliced_blocks;   /* query calls evaluated on bit-sliced tiles (pf_db_set_mode); `pairs` are then (read, tile)
+                                 pairs and `probes_issued` the row (sector) loads, each answering a probe for a whole tile */
+    uint64_t sliced_tiles;    /* tiles of the current tiling */
+    uint64_t sliced_table_bytes; /* HBM held by their tables */
 } pf_stats_t;
 int pf_get_stats(pf_db *db, pf_stats_t *out);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can
@@ -184,6 +188,14 @@ int pf_db_set_exhaustive(pf_db *db, int on);
  * instead of the exact one; leaves and unverified nodes stay exact, so results are identical.
  * 0: every node is evaluated exactly (the frontier then equals the reference's, query.rs:113-141). */
 int pf_db_set_lazy(pf_db *db, int on);
+/* How a block is evaluated.  1: node at a time -- a warp per (read, node) pair probing that node's filter (one bit per
+ * 32-byte sector touched; filters stay L2-resident because the frontier is node-major).  2: bit-sliced tiles -- the
+ * filters of up to 256 nodes are stored transposed, so one sector load answers a bloom probe for every node of the tile
+ * (exact per-node k-mer counts, then the reference's descent rule on the pass bits).  0 (default): per (threshold, read
+ * length) whichever the cost model expects to be faster; the tiles are built on first use from the resident filters
+ * (about as much HBM again).  Results are identical in every mode.  The environment variable PF_MODE
+ * (auto|pair|sliced) sets the initial value. */
+int pf_db_set_mode(pf_db *db, int mode);
 /* 1 (default): k-mer memo at exact nodes.  BloomFilter::contains depends on a k-mer only through its 64-bit
  * hash_bytes value, so once a k-mer has passed all K probes at a node, every later occurrence of the same value at that
  * node within the block (sequencing depth: 30x in BASELINE config 2) is a hit after ONE table look-up instead of K - 1

@@ -104,6 +104,13 @@ class BloomTree:
         """k-mer memo at exact nodes (pf_db_set_memo): same results, fewer probes on deep-coverage batches."""
         _lib.check(_lib.lib().pf_db_set_memo(self._h, int(on), budget_bytes))
 
+    MODE_AUTO, MODE_PAIR, MODE_SLICED = 0, 1, 2
+
+    def set_mode(self, mode: int) -> None:
+        """pf_db_set_mode: 0 = cost model decides per (threshold, read length), 1 = node-at-a-time descent,
+        2 = bit-sliced tiles.  Results are identical in every mode."""
+        _lib.check(_lib.lib().pf_db_set_mode(self._h, int(mode)))
+
     def set_lazy(self, on: bool) -> None:
         _lib.check(_lib.lib().pf_db_set_lazy(self._h, int(on)))
 

@@ -96,6 +96,7 @@ struct PinnedBuf {  // grow-only pinned host array
 
 namespace pf {
 struct ShardState;
+struct SlicedState;
 }
 using namespace pf;  // internal header: the handle types below live at global scope (C ABI)
 
@@ -233,6 +234,11 @@ struct pf_db {
     std::vector<int32_t> h_owner;      // per node: -1 = top (replicated), else owning rank
     std::vector<uint32_t> cut_lo;      // [nranks + 1] node-id boundaries of the owners' ranges inside level cut_level
     pf::ShardState *shard = nullptr;   // exchange buffers (pf_shard.cu)
+    // ---- bit-sliced tiles (pf_sliced.cu): 0 = choose per (threshold, read length) by cost model, 1 = node-at-a-time
+    // descent only, 2 = sliced tiles only
+    int mode = 0;
+    double plan_cost = 0.0;            // expected bit probes of a read unrelated to the database under the current step plan
+    pf::SlicedState *sliced = nullptr;
     std::vector<uint8_t> nccl_id;      // ncclUniqueId handed to pf_db_open_sharded (the analysis at open is collective)
 };
 
@@ -270,4 +276,11 @@ int shard_plan(pf_db *db, int64_t cut_level_req);  // pf_shard.cu: cut level, ow
 int finish_csr(pf_db *db, uint32_t n_reads, uint64_t hits_total, int want_hits, uint32_t out_r0, uint32_t out_n,
                pf_hits *out, uint64_t *other_launches, uint64_t *d2h);
 void account_stats(pf_db *db, const Descent &st, uint64_t n_reads, uint64_t d2h);
+// pf_sliced.cu
+void sliced_free(pf_db *db);
+int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sliced);
+int sliced_begin_block(pf_db *db);
+uint64_t sliced_entry_tiles(const pf_db *db);
+int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint64_t kmer_base, uint32_t r0,
+               uint32_t n_chunk, Descent &st);
 }  // namespace pf

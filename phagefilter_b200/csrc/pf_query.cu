@@ -75,6 +75,7 @@ void pf::db_free(pf_db *db) {
     if (!db) return;
     cudaSetDevice(db->device);
     shard_free(db);
+    sliced_free(db);
     if (db->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(db->comm);
     cudaFree(db->d_left);
     cudaFree(db->d_right);
@@ -539,6 +540,7 @@ static void plan_steps(pf_db *db, float threshold, uint64_t n_nominal, std::vect
             steps[u] = plan_choose(f, K, n_nominal, allowed, below, &strides[u], &cost[u]);
         }
     }
+    db->plan_cost = nn ? cost[0] : 0.0;
 }
 int pf::update_steps(pf_db *db, float threshold, uint64_t n_nominal) {
     const int mode = db->exhaustive ? 2 : (db->lazy ? 1 : 0);
@@ -889,7 +891,10 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         return PF_ERR_STATE;
     }
     if ((rc = update_steps(db, threshold, bt->nominal_kmers))) return rc;
+    bool sliced = false;
+    if ((rc = sliced_prepare(db, threshold, bt->nominal_kmers, &sliced))) return rc;
     PF_CUDA_OK(cudaEventRecord(db->ev_begin, s));
+    if (sliced && (rc = sliced_begin_block(db))) return rc;
     PF_CUDA_OK(cudaMemsetAsync(db->d_blk_counts, 0, std::max<uint64_t>(db->n_leaves, 1) * 8, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_probes, 0, 24, s));
     PF_CUDA_OK(cudaMemsetAsync(db->d_totals, 0, sizeof(LevelTotals), s));
@@ -911,11 +916,15 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
                             ko.begin()) - 1;
             if (r1 <= r0) r1 = r0 + 1;
         }
+        if (sliced) {  // (read, entry tile) pairs of a chunk are indexed with 32 bits
+            const uint64_t cap = std::max<uint64_t>(1, 0xF0000000ULL / std::max<uint64_t>(sliced_entry_tiles(db), 1));
+            if (r1 - r0 > cap) r1 = r0 + (uint32_t)cap;
+        }
         const uint32_t n_chunk = r1 - r0;
         const uint64_t chunk_kmers = one_chunk ? bt->total_bases_bound : ko[r1] - ko[r0];
         const uint64_t kmer_base = one_chunk ? 0 : ko[r0];
         if ((rc = db->hb.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
-        if (db->hp.small_m && (rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
+        if (db->hp.small_m && !sliced && (rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
         PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, (2 + NODE_PASS_COPIES) * db->n_nodes * 4, s));
         PF_CUDA_OK(cudaMemsetAsync(db->d_work, 0, db->level_start.size() * 4, s));
         HashArgs h{};
@@ -927,7 +936,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         h.exc_bytes = bt->exc_bytes.p;
         h.kmer_off = bt->kmer_off.p;
         h.hb = db->hb.p;
-        h.idx0 = db->hp.small_m ? db->idx0.p : nullptr;
+        h.idx0 = (db->hp.small_m && !sliced) ? db->idx0.p : nullptr;
         h.hp = db->hp;
         h.kmer_base = kmer_base;
         h.read0 = r0;
@@ -941,7 +950,9 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         }
         st.n = 0;
         st.cur = 0;
-        if ((rc = run_levels(db, bt, threshold, want_hits, G, kmer_base, 0, n_levels, r0, n_chunk, st))) return rc;
+        if (sliced) rc = run_sliced(db, bt, threshold, want_hits, kmer_base, r0, n_chunk, st);
+        else rc = run_levels(db, bt, threshold, want_hits, G, kmer_base, 0, n_levels, r0, n_chunk, st);
+        if (rc) return rc;
         r0 = r1;
     }
     add_counts_kernel<<<(uint32_t)((db->n_leaves + 255) / 256), 256, 0, s>>>(db->d_counts, db->d_blk_counts,
@@ -963,6 +974,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         }
     }
     account_stats(db, st, n_reads, d2h);
+    if (sliced) db->stats.sliced_blocks++;
     return PF_OK;
 }
 
@@ -1067,6 +1079,7 @@ int pf_db_open(const char *db_path, int device, int64_t search_depth, pf_db **ou
     *out = nullptr;
     pf_db *db = new pf_db();
     db->device = device;
+    if (const char *m = getenv("PF_MODE")) db->mode = !strcmp(m, "pair") ? 1 : (!strcmp(m, "sliced") ? 2 : 0);
     int rc = db_open_impl(db, db_path, search_depth);
     if (rc != PF_OK) {
         std::string keep = g_error;
@@ -1139,6 +1152,14 @@ int pf_db_set_memo(pf_db *db, int on, uint64_t budget_bytes) {
 int pf_db_set_lazy(pf_db *db, int on) {
     if (!db) return PF_ERR_ARG;
     db->lazy = on ? 1 : 0;
+    return PF_OK;
+}
+int pf_db_set_mode(pf_db *db, int mode) {
+    if (!db || mode < 0 || mode > 2) {
+        set_error("pf_db_set_mode: bad argument");
+        return PF_ERR_ARG;
+    }
+    db->mode = mode;
     return PF_OK;
 }
 int pf_db_node_steps(pf_db *db, float threshold, uint64_t nominal_kmers, uint32_t *steps) {

@@ -1,0 +1,553 @@
+// pf_sliced.cu -- host side of the bit-sliced evaluation (pf_sliced.cuh): cutting the tree into tiles of up to 256
+// nodes, building the tiles' transposed tables from the resident filters, choosing between the node-at-a-time
+// descent (pf_query.cu) and the sliced one, and the tile-level descent itself.
+//
+// Reference semantics reproduced (paths relative to the reference root): query::_query_batch (query.rs:99-158) --
+// a node is evaluated for a read iff every ancestor passed, a leaf that passes counts the read (query.rs:143) and
+// records (read, genome) (query.rs:149-153); query::query_passes (query.rs:38-49); BloomFilter::contains
+// (bloom_filter.rs:312-332).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+
+#include "pf_db.h"
+#include "pf_sliced.cuh"
+
+namespace pf {
+
+struct SlicedState {
+    // plan (host)
+    std::vector<uint8_t> skip;             // per node: not evaluated (verified superset chain below, passes ~always)
+    std::vector<SlicedTileDev> tiles;
+    std::vector<uint32_t> col_slot;        // [tiles][256] filter slot per column
+    std::vector<uint32_t> child_tile, child_mask;
+    std::vector<uint32_t> entry_tiles;
+    std::vector<int32_t> tile_parent;
+    std::vector<std::vector<uint32_t>> tile_nodes;  // node of every column
+    uint64_t table_words = 0;
+    uint64_t entry_bytes = 0;
+    double est_sectors_per_read = 0.0;     // cost model: expected sector loads of a read unrelated to the database
+    // device
+    SlicedTileDev *d_tiles = nullptr;
+    uint32_t *d_tables = nullptr, *d_child_tile = nullptr, *d_child_mask = nullptr, *d_entry = nullptr;
+    uint32_t *d_tile_count = nullptr, *d_tile_cursor = nullptr;  // contiguous [2 * n_tiles]
+    unsigned long long *d_tile_base = nullptr, *d_counters = nullptr, *d_hit_cursor = nullptr;
+    unsigned int *d_work = nullptr;
+    uint32_t *h_tile_count = nullptr;            // pinned [n_tiles]
+    unsigned long long *h_counters = nullptr;    // pinned [4]
+    unsigned long long *h_tile_base = nullptr;   // pinned [n_tiles]
+    bool tables_ready = false;
+    DevBuf<uint32_t> fr_read[2], fr_tile[2], fr_src[2], reach[2], alive;
+    // what the plan was made for
+    float theta = -1.f;
+    uint64_t n_nominal = 0;
+    int decided_mode = 0;  // 1 pair, 2 sliced (for theta / n_nominal above)
+    bool failed = false;   // tables could not be built (memory): stay with the node-at-a-time path
+};
+
+static void sliced_release_device(SlicedState *s) {
+    cudaFree(s->d_tiles);
+    cudaFree(s->d_tables);
+    cudaFree(s->d_child_tile);
+    cudaFree(s->d_child_mask);
+    cudaFree(s->d_entry);
+    cudaFree(s->d_tile_count);
+    cudaFree(s->d_tile_base);
+    cudaFree(s->d_counters);
+    cudaFree(s->d_work);
+    if (s->h_tile_count) cudaFreeHost(s->h_tile_count);
+    if (s->h_counters) cudaFreeHost(s->h_counters);
+    if (s->h_tile_base) cudaFreeHost(s->h_tile_base);
+    s->d_tiles = nullptr;
+    s->d_tables = s->d_child_tile = s->d_child_mask = s->d_entry = s->d_tile_count = s->d_tile_cursor = nullptr;
+    s->d_tile_base = s->d_counters = s->d_hit_cursor = nullptr;
+    s->d_work = nullptr;
+    s->h_tile_count = nullptr;
+    s->h_counters = s->h_tile_base = nullptr;
+    s->tables_ready = false;
+}
+
+void sliced_free(pf_db *db) {
+    if (!db->sliced) return;
+    SlicedState *s = db->sliced;
+    sliced_release_device(s);
+    for (int i = 0; i < 2; i++) {
+        s->fr_read[i].release();
+        s->fr_tile[i].release();
+        s->fr_src[i].release();
+        s->reach[i].release();
+    }
+    s->alive.release();
+    delete s;
+    db->sliced = nullptr;
+}
+
+// ---- plan ------------------------------------------------------------------------------------------------------------
+static double phi_tab(double z) {  // standard normal CDF, coarse: only steers cost decisions, never results
+    return 0.5 * erfc(-z / 1.4142135623730951);
+}
+static uint64_t need_host(float threshold, uint64_t n) {  // query.rs:48
+    volatile float prod = threshold * (float)n;
+    const float c = ceilf(prod);
+    if (!(c > 0.0f)) return 0;
+    if (c >= 18446744073709551616.0f) return ~0ULL;
+    return (uint64_t)c;
+}
+// measured on a B200 (profiles/r2a_mb_gather_b200.csv): random row loads per second against the bytes they range over
+static double sector_rate(double footprint_bytes) {
+    static const double mb[] = {64, 80, 96, 115, 128, 160, 230, 460, 920, 2048, 8192};
+    static const double g[] = {289, 262, 159, 128, 117, 102, 80, 51.6, 44.4, 39.6, 37.1};
+    const double f = footprint_bytes / 1048576.0;
+    if (f <= mb[0]) return g[0] * 1e9;
+    for (int i = 1; i < 11; ++i)
+        if (f <= mb[i]) return (g[i - 1] + (g[i] - g[i - 1]) * (f - mb[i - 1]) / (mb[i] - mb[i - 1])) * 1e9;
+    return 36.5e9;
+}
+static uint32_t width_for(size_t cols) { return cols <= 32 ? 32u : (cols <= 64 ? 64u : (cols <= 128 ? 128u : 256u)); }
+
+// Cuts the (pruned, level-ordered) tree into tiles for `threshold` and reads of `n_nominal` k-mers.
+//  1. Skip set: interior nodes, connected to the root, below which every (node, child) pair was verified at load time to
+//     be a bitwise superset (child passes => node passes, see analyse_tree) and which an unrelated read passes almost
+//     surely (filter nearly full).  They are never evaluated: whatever passes a leaf below them passes them too.
+//  2. Every other node gets a column in exactly one tile.  A tile's roots all hang below columns of ONE parent tile
+//     (or below skipped nodes: entry tiles).  Where filters are still dense (fill > 1/2, in the node or below it) tiles
+//     are wide and shallow -- as many sibling subtrees side by side as fit, so the reads that die there touch few
+//     tiles; sparse subtrees are packed whole, several per tile, so a read that survives needs one more tile.
+static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, SlicedState &S) {
+    const size_t nn = db->n_nodes;
+    const uint32_t K = db->geom.num_hashes;
+    const double mbits = (double)db->geom.num_bits;
+    std::vector<uint32_t> parent(nn, NONE32);
+    for (size_t u = 0; u < nn; ++u) {
+        if (db->h_left[u] != NONE32) parent[db->h_left[u]] = (uint32_t)u;
+        if (db->h_right[u] != NONE32) parent[db->h_right[u]] = (uint32_t)u;
+    }
+    const uint64_t need = need_host(threshold, n_nominal);
+    const double n = (double)n_nominal;
+    std::vector<uint8_t> vb(nn, 1), inA(nn, 0);
+    std::vector<uint32_t> sz(nn, 1);
+    std::vector<double> q(nn, 0.0), fill(nn, 0.0);
+    for (size_t u = nn; u-- > 0;) {
+        const uint32_t l = db->h_left[u], r = db->h_right[u];
+        fill[u] = (double)db->h_pop[u] / mbits;
+        const double p = pow(fill[u], (double)K), mean = n * p, var = n * p * (1.0 - p);
+        q[u] = var < 1e-9 ? (mean + 0.5 >= (double)need ? 1.0 : 0.0) : phi_tab((mean - (double)need + 0.5) / sqrt(var));
+        inA[u] = fill[u] > 0.5;
+        if (db->h_leaf[u] >= 0) continue;
+        vb[u] = db->h_mono[u];
+        for (uint32_t c : {l, r})
+            if (c != NONE32) {
+                vb[u] = vb[u] && vb[c];
+                inA[u] = inA[u] || inA[c];
+                sz[u] += sz[c];
+            }
+    }
+    S.skip.assign(nn, 0);
+    for (size_t u = 0; u < nn; ++u) {
+        if (db->h_leaf[u] >= 0 || !vb[u] || q[u] < 0.9) continue;
+        if (u == 0 || S.skip[parent[u]]) S.skip[u] = 1;
+    }
+    S.tiles.clear();
+    S.col_slot.clear();
+    S.child_tile.clear();
+    S.child_mask.clear();
+    S.entry_tiles.clear();
+    S.tile_parent.clear();
+    S.tile_nodes.clear();
+    std::vector<int32_t> node_tile(nn, -1);
+    std::vector<uint32_t> node_col(nn, 0);
+    struct Job {
+        int32_t parent_tile;
+        std::vector<uint32_t> roots;
+    };
+    std::deque<Job> jobs;
+    {
+        Job j0{-1, {}};
+        for (size_t u = 0; u < nn; ++u)
+            if (!S.skip[u] && (u == 0 || S.skip[parent[u]])) j0.roots.push_back((uint32_t)u);
+        jobs.push_back(std::move(j0));
+    }
+    auto bfs_subtree = [&](uint32_t r, size_t cap, std::vector<uint32_t> &out) {  // level order, parents first
+        const size_t b = out.size();
+        out.push_back(r);
+        for (size_t i = b; i < out.size(); ++i)
+            for (uint32_t c : {db->h_left[out[i]], db->h_right[out[i]]})
+                if (c != NONE32 && out.size() - b < cap) out.push_back(c);
+    };
+    const uint64_t rows = 64ULL * db->wpf;
+    S.table_words = 0;
+    S.entry_bytes = 0;
+    while (!jobs.empty()) {
+        Job job = std::move(jobs.front());
+        jobs.pop_front();
+        std::vector<std::vector<uint32_t>> made;  // column lists of the tiles of this job
+        std::vector<uint32_t> RA, RB;
+        for (uint32_t r : job.roots) (inA[r] ? RA : RB).push_back(r);
+        for (size_t c0 = 0; c0 < RA.size(); c0 += SL_MAX_COLS) {
+            std::vector<uint32_t> cols(RA.begin() + c0, RA.begin() + std::min(RA.size(), c0 + SL_MAX_COLS));
+            const size_t cap = width_for(cols.size());
+            for (size_t i = 0; i < cols.size() && cols.size() < cap; ++i)
+                for (uint32_t c : {db->h_left[cols[i]], db->h_right[cols[i]]})
+                    if (c != NONE32 && cols.size() < cap) cols.push_back(c);
+            made.push_back(std::move(cols));
+        }
+        std::vector<uint32_t> cur;
+        for (uint32_t r : RB) {
+            if (sz[r] <= (uint32_t)SL_MAX_COLS) {
+                if (cur.size() + sz[r] > (size_t)SL_MAX_COLS) {
+                    made.push_back(std::move(cur));
+                    cur.clear();
+                }
+                bfs_subtree(r, SL_MAX_COLS, cur);
+            } else {
+                if (!cur.empty()) {
+                    made.push_back(std::move(cur));
+                    cur.clear();
+                }
+                std::vector<uint32_t> cols;
+                bfs_subtree(r, SL_MAX_COLS, cols);
+                made.push_back(std::move(cols));
+            }
+        }
+        if (!cur.empty()) made.push_back(std::move(cur));
+        const uint32_t first_link = (uint32_t)S.child_tile.size();
+        for (auto &cols : made) {
+            const uint32_t t = (uint32_t)S.tiles.size();
+            SlicedTileDev tm;
+            memset(&tm, 0, sizeof tm);
+            tm.n_cols = (uint32_t)cols.size();
+            tm.row_words = width_for(cols.size()) / 32u;
+            tm.table_off = S.table_words;
+            S.table_words += rows * tm.row_words;
+            tm.entry = job.parent_tile < 0;
+            if (tm.entry) S.entry_bytes += rows * tm.row_words * 4ULL;
+            S.col_slot.resize((size_t)(t + 1) * SL_MAX_COLS, NONE32);
+            for (size_t c = 0; c < cols.size(); ++c) {
+                node_tile[cols[c]] = (int32_t)t;
+                node_col[cols[c]] = (uint32_t)c;
+            }
+            std::vector<uint32_t> depth(cols.size(), 0);
+            uint32_t link_mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (size_t c = 0; c < cols.size(); ++c) {
+                const uint32_t u = cols[c];
+                S.col_slot[(size_t)t * SL_MAX_COLS + c] = db->h_slot[u];
+                tm.valid[c >> 5] |= 1u << (c & 31);
+                tm.leaf[c] = db->h_leaf[u];
+                if (db->h_leaf[u] >= 0) tm.leafmask[c >> 5] |= 1u << (c & 31);
+                const uint32_t p = parent[u];
+                if (p != NONE32 && node_tile[p] == (int32_t)t && node_col[p] < c) {
+                    tm.parent[c] = (uint16_t)node_col[p];
+                    depth[c] = depth[node_col[p]] + 1;
+                    tm.prop_iters = std::max(tm.prop_iters, depth[c]);
+                } else if (job.parent_tile < 0) {
+                    tm.parent[c] = 0xFFFFu;
+                } else {
+                    tm.parent[c] = (uint16_t)(0x8000u | node_col[p]);
+                    link_mask[node_col[p] >> 5] |= 1u << (node_col[p] & 31);
+                }
+            }
+            for (size_t c = cols.size(); c < (size_t)SL_MAX_COLS; ++c) {
+                tm.parent[c] = 0xFFFFu;
+                tm.leaf[c] = -1;
+            }
+            if (job.parent_tile >= 0) {
+                S.child_tile.push_back(t);
+                S.child_mask.insert(S.child_mask.end(), link_mask, link_mask + 8);
+            } else {
+                S.entry_tiles.push_back(t);
+            }
+            S.tiles.push_back(tm);
+            S.tile_parent.push_back(job.parent_tile);
+            S.tile_nodes.push_back(cols);
+        }
+        if (job.parent_tile >= 0) {
+            S.tiles[job.parent_tile].first_child = first_link;
+            S.tiles[job.parent_tile].n_children = (uint32_t)S.child_tile.size() - first_link;
+        }
+        // the tiles of this job are complete: their out-of-tile children are the roots of the next jobs
+        const uint32_t t_first = (uint32_t)(S.tiles.size() - made.size());
+        for (size_t k = 0; k < made.size(); ++k) {
+            const uint32_t t = t_first + (uint32_t)k;
+            Job nj{(int32_t)t, {}};
+            for (size_t c = 0; c < made[k].size(); ++c) {
+                const uint32_t u = made[k][c];
+                bool term = db->h_leaf[u] >= 0;
+                for (uint32_t ch : {db->h_left[u], db->h_right[u]})
+                    if (ch != NONE32 && node_tile[ch] != (int32_t)t) {
+                        term = true;
+                        nj.roots.push_back(ch);
+                    }
+                if (term) S.tiles[t].terminal[c >> 5] |= 1u << (c & 31);
+            }
+            std::sort(nj.roots.begin(), nj.roots.end());
+            if (!nj.roots.empty()) jobs.push_back(std::move(nj));
+        }
+    }
+    // cost model: sector loads of a read unrelated to the database; a tile below another one is reached with the
+    // probability that one of the columns above its roots passes
+    {
+        const size_t nt = S.tiles.size();
+        std::vector<double> pr(nn, 0.0);  // per node: probability that the node is reached and passes
+        for (size_t u = 0; u < nn; ++u) pr[u] = S.skip[u] ? 1.0 : (u == 0 ? 1.0 : pr[parent[u]]) * q[u];
+        double total = 0.0;
+        for (size_t t = 0; t < nt; ++t) {
+            double p = 1.0;
+            if (S.tile_parent[t] >= 0) {
+                // a root column is reached iff its parent (one tile up) was reached and passed; several roots may share
+                // a parent -- treating them as independent only makes the estimate larger
+                double none = 1.0;
+                for (uint32_t c = 0; c < S.tiles[t].n_cols; ++c)
+                    if (S.tiles[t].parent[c] & 0x8000u) none *= 1.0 - pr[parent[S.tile_nodes[t][c]]];
+                p = 1.0 - none;
+            }
+            total += p * n * (double)K;
+        }
+        S.est_sectors_per_read = total;
+    }
+}
+
+// ---- tables ----------------------------------------------------------------------------------------------------------
+static int build_tables(pf_db *db, SlicedState &S) {
+    sliced_release_device(&S);
+    const size_t nt = S.tiles.size();
+    size_t free_b = 0, total_b = 0;
+    PF_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t want = S.table_words * 4ULL;
+    if (want + (8ULL << 30) > free_b) {  // leave room for the batch, its hash cache and the frontier
+        set_error("sliced tables need %.1f GB, %.1f GB free", want / 1e9, free_b / 1e9);
+        return PF_ERR_NOMEM;
+    }
+    PF_CUDA_OK(cudaMalloc(&S.d_tables, std::max<uint64_t>(want, 4)));
+    PF_CUDA_OK(cudaMalloc(&S.d_tiles, nt * sizeof(SlicedTileDev)));
+    PF_CUDA_OK(cudaMalloc(&S.d_child_tile, std::max<size_t>(S.child_tile.size(), 1) * 4));
+    PF_CUDA_OK(cudaMalloc(&S.d_child_mask, std::max<size_t>(S.child_mask.size(), 1) * 4));
+    PF_CUDA_OK(cudaMalloc(&S.d_entry, std::max<size_t>(S.entry_tiles.size(), 1) * 4));
+    PF_CUDA_OK(cudaMalloc(&S.d_tile_count, 2 * nt * 4));
+    S.d_tile_cursor = S.d_tile_count + nt;
+    PF_CUDA_OK(cudaMalloc(&S.d_tile_base, nt * 8));
+    PF_CUDA_OK(cudaMalloc(&S.d_counters, 4 * 8));
+    S.d_hit_cursor = S.d_counters + 3;
+    PF_CUDA_OK(cudaMalloc(&S.d_work, 4));
+    PF_CUDA_OK(cudaMallocHost(&S.h_tile_count, nt * 4));
+    PF_CUDA_OK(cudaMallocHost(&S.h_counters, 4 * 8));
+    PF_CUDA_OK(cudaMallocHost(&S.h_tile_base, nt * 8));
+    cudaStream_t s = db->stream;
+    uint32_t *d_col_slot = nullptr;
+    PF_CUDA_OK(cudaMalloc(&d_col_slot, S.col_slot.size() * 4));
+    PF_CUDA_OK(cudaMemcpyAsync(d_col_slot, S.col_slot.data(), S.col_slot.size() * 4, cudaMemcpyHostToDevice, s));
+    PF_CUDA_OK(cudaMemcpyAsync(S.d_tiles, S.tiles.data(), nt * sizeof(SlicedTileDev), cudaMemcpyHostToDevice, s));
+    if (!S.child_tile.empty()) {
+        PF_CUDA_OK(cudaMemcpyAsync(S.d_child_tile, S.child_tile.data(), S.child_tile.size() * 4, cudaMemcpyHostToDevice, s));
+        PF_CUDA_OK(cudaMemcpyAsync(S.d_child_mask, S.child_mask.data(), S.child_mask.size() * 4, cudaMemcpyHostToDevice, s));
+    }
+    PF_CUDA_OK(cudaMemcpyAsync(S.d_entry, S.entry_tiles.data(), S.entry_tiles.size() * 4, cudaMemcpyHostToDevice, s));
+    const uint32_t gx = (uint32_t)(2 * db->wpf / 8);
+    for (size_t t0 = 0; t0 < nt; t0 += 32768) {
+        const uint32_t ny = (uint32_t)std::min<size_t>(32768, nt - t0);
+        slice_kernel<<<dim3(gx, ny), 256, 0, s>>>(db->d_filters, db->wpf, d_col_slot, S.d_tiles, (uint32_t)t0, S.d_tables);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(d_col_slot);
+    PF_CUDA_OK(e);
+    PF_CUDA_OK(cudaGetLastError());
+    S.tables_ready = true;
+    db->stats.sliced_tiles = nt;
+    db->stats.sliced_table_bytes = want;
+    return PF_OK;
+}
+
+// Decides how a batch with this threshold and nominal read length is evaluated and, for the sliced path, makes sure the
+// tiles exist.  Returns PF_OK with *use_sliced set.  Auto mode compares the two cost models: expected bit probes of the
+// node-at-a-time plan (L2-resident filter, ~240 G probes/s measured) against expected sector loads of the tiles at the
+// measured random-row rate for their footprint.
+int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sliced) {
+    *use_sliced = false;
+    if (db->mode == 1 || db->sharded || db->exhaustive || !db->lazy) return PF_OK;
+    if (!db->sliced) db->sliced = new SlicedState();
+    SlicedState &S = *db->sliced;
+    if (S.failed && db->mode != 2) return PF_OK;
+    if (S.decided_mode && S.theta == threshold && S.n_nominal == n_nominal && (db->mode == 0 || db->mode == S.decided_mode)) {
+        *use_sliced = S.decided_mode == 2;
+        if (*use_sliced) {
+            db->stats.sliced_tiles = S.tiles.size();
+            db->stats.sliced_table_bytes = S.table_words * 4ULL;
+        }
+        return PF_OK;
+    }
+    SlicedState P;  // plan into a scratch state first: the tables are rebuilt only if the tiling changed
+    plan_tiles(db, threshold, n_nominal, P);
+    bool sliced = db->mode == 2;
+    if (db->mode == 0) {
+        const double t_pair = db->plan_cost / 240e9;
+        const double t_sliced = P.est_sectors_per_read / sector_rate((double)P.entry_bytes);
+        sliced = t_sliced < 0.8 * t_pair;
+    }
+    S.theta = threshold;
+    S.n_nominal = n_nominal;
+    S.decided_mode = sliced ? 2 : 1;
+    if (!sliced) return PF_OK;
+    const bool same = S.tables_ready && S.skip == P.skip && S.tiles.size() == P.tiles.size();
+    if (!same) {
+        S.skip = std::move(P.skip);
+        S.tiles = std::move(P.tiles);
+        S.col_slot = std::move(P.col_slot);
+        S.child_tile = std::move(P.child_tile);
+        S.child_mask = std::move(P.child_mask);
+        S.entry_tiles = std::move(P.entry_tiles);
+        S.tile_parent = std::move(P.tile_parent);
+        S.tile_nodes = std::move(P.tile_nodes);
+        S.table_words = P.table_words;
+        S.entry_bytes = P.entry_bytes;
+        S.est_sectors_per_read = P.est_sectors_per_read;
+        int rc = build_tables(db, S);
+        if (rc != PF_OK) {
+            sliced_release_device(&S);
+            S.failed = true;
+            S.decided_mode = 1;
+            if (db->mode == 2) return rc;  // explicitly requested: report
+            return PF_OK;                  // auto: stay with the node-at-a-time path
+        }
+    }
+    db->stats.sliced_tiles = S.tiles.size();
+    db->stats.sliced_table_bytes = S.table_words * 4ULL;
+    *use_sliced = true;
+    return PF_OK;
+}
+
+uint64_t sliced_entry_tiles(const pf_db *db) { return db->sliced ? db->sliced->entry_tiles.size() : 0; }
+
+template <int PW>
+static void launch_sliced(const SlicedArgs &a, int grid, cudaStream_t s) {
+    if (a.hp.small_m) sliced_probe_kernel<PW, true><<<grid, SL_THREADS, 0, s>>>(a);
+    else sliced_probe_kernel<PW, false><<<grid, SL_THREADS, 0, s>>>(a);
+}
+
+// The tile-level descent for reads [r0, r0 + n_chunk) of the batch whose hash values are cached in db->hb.
+int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint64_t kmer_base, uint32_t r0,
+               uint32_t n_chunk, Descent &st) {
+    SlicedState &S = *db->sliced;
+    cudaStream_t s = db->stream;
+    const size_t nt = S.tiles.size();
+    int rc;
+    uint64_t n = (uint64_t)n_chunk * S.entry_tiles.size();
+    if (n > 0xFFFFFF00ULL) {
+        set_error("sliced frontier of %llu pairs exceeds the 32-bit pair index", (unsigned long long)n);
+        return PF_ERR_NOMEM;
+    }
+    int cur = 0;
+    bool entry = true;
+    const int grid = db->sm_count * 2;
+    while (n > 0) {
+        if ((rc = S.reach[cur].ensure(n * 8)) || (rc = S.alive.ensure(n))) return rc;
+        PF_CUDA_OK(cudaMemsetAsync(S.d_counters, 0, 3 * 8, s));
+        PF_CUDA_OK(cudaMemsetAsync(S.d_work, 0, 4, s));
+        PF_CUDA_OK(cudaMemsetAsync(S.d_tile_count, 0, 2 * nt * 4, s));
+        SlicedArgs a{};
+        a.fr_read = entry ? nullptr : S.fr_read[cur].p;
+        a.fr_tile = entry ? nullptr : S.fr_tile[cur].p;
+        a.fr_src = entry ? nullptr : S.fr_src[cur].p;
+        a.n_pairs = (uint32_t)n;
+        a.entry_tiles = S.d_entry;
+        a.read0 = r0;
+        a.n_chunk = n_chunk;
+        a.lengths = bt->lengths.p;
+        a.kmer_off = bt->kmer_off.p;
+        a.hb = db->hb.p;
+        a.kmer_base = kmer_base;
+        a.tiles = S.d_tiles;
+        a.tables = S.d_tables;
+        a.child_tile = S.d_child_tile;
+        a.child_mask = S.d_child_mask;
+        a.src_reach = S.reach[cur ^ 1].p;
+        a.reach = S.reach[cur].p;
+        a.alive = S.alive.p;
+        a.tile_count = S.d_tile_count;
+        a.counters = S.d_counters;
+        a.work_ctr = S.d_work;
+        a.hp = db->hp;
+        a.threshold = threshold;
+        a.grab = bt->max_kmers <= 256 ? 4u : 1u;
+        while (db->ev_probe.size() < st.n_ev + 2) {
+            cudaEvent_t e;
+            PF_CUDA_OK(cudaEventCreate(&e));
+            db->ev_probe.push_back(e);
+        }
+        PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev], s));
+        if (bt->max_kmers < 256) launch_sliced<8>(a, grid, s);
+        else if (bt->max_kmers < 65536) launch_sliced<16>(a, grid, s);
+        else launch_sliced<32>(a, grid, s);
+        PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev + 1], s));
+        st.n_ev += 2;
+        st.probe_launches++;
+        st.pairs += n;
+        st.levels++;
+        PF_CUDA_OK(cudaMemcpyAsync(S.h_counters, S.d_counters, 3 * 8, cudaMemcpyDeviceToHost, s));
+        PF_CUDA_OK(cudaMemcpyAsync(S.h_tile_count, S.d_tile_count, nt * 4, cudaMemcpyDeviceToHost, s));
+        PF_CUDA_OK(cudaStreamSynchronize(s));
+        st.probes += S.h_counters[0];
+        const uint64_t n_alive = S.h_counters[1], hits = S.h_counters[2];
+        uint64_t next_n = 0;
+        for (size_t t = 0; t < nt; ++t) {
+            S.h_tile_base[t] = next_n;
+            next_n += S.h_tile_count[t];
+        }
+        if (next_n > 0xFFFFFF00ULL) {
+            set_error("sliced frontier of %llu pairs exceeds the 32-bit pair index", (unsigned long long)next_n);
+            return PF_ERR_NOMEM;
+        }
+        const int nxt = cur ^ 1;
+        if (n_alive) {
+            if (next_n && ((rc = S.fr_read[nxt].ensure(next_n)) || (rc = S.fr_tile[nxt].ensure(next_n)) ||
+                           (rc = S.fr_src[nxt].ensure(next_n))))
+                return rc;
+            if (want_hits && hits &&
+                ((rc = db->hit_read.grow_keep(st.hits_total + hits, st.hits_total, s)) ||
+                 (rc = db->hit_leaf.grow_keep(st.hits_total + hits, st.hits_total, s))))
+                return rc;
+            PF_CUDA_OK(cudaMemcpyAsync(S.d_tile_base, S.h_tile_base, nt * 8, cudaMemcpyHostToDevice, s));
+            SlicedEmitArgs e{};
+            e.fr_read = a.fr_read;
+            e.fr_tile = a.fr_tile;
+            e.entry_tiles = S.d_entry;
+            e.read0 = r0;
+            e.n_chunk = n_chunk;
+            e.alive = S.alive.p;
+            e.n_alive = (uint32_t)n_alive;
+            e.reach = S.reach[cur].p;
+            e.tiles = S.d_tiles;
+            e.child_tile = S.d_child_tile;
+            e.child_mask = S.d_child_mask;
+            e.tile_base = S.d_tile_base;
+            e.tile_cursor = S.d_tile_cursor;
+            e.nx_read = S.fr_read[nxt].p;
+            e.nx_tile = S.fr_tile[nxt].p;
+            e.nx_src = S.fr_src[nxt].p;
+            e.hit_read = db->hit_read.p;
+            e.hit_leaf = db->hit_leaf.p;
+            e.read_hits = db->read_hits.p;
+            e.hit_cursor = S.d_hit_cursor;
+            e.blk_counts = db->d_blk_counts;
+            e.want_hits = want_hits;
+            const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_alive + 7) / 8, (uint64_t)db->sm_count * 8);
+            sliced_emit_kernel<<<blocks, 256, 0, s>>>(e);
+            st.other_launches++;
+        }
+        st.hits_total += hits;
+        st.hits_before = st.hits_total;
+        n = next_n;
+        cur = nxt;
+        entry = false;
+    }
+    return PF_OK;
+}
+
+// hit cursor of the emit kernel: hits of earlier chunks of the same block stay in front
+int sliced_begin_block(pf_db *db) {
+    SlicedState &S = *db->sliced;
+    PF_CUDA_OK(cudaMemsetAsync(S.d_hit_cursor, 0, 8, db->stream));
+    return PF_OK;
+}
+
+}  // namespace pf

@@ -1,0 +1,504 @@
+// pf_sliced.cuh -- bit-sliced evaluation of the gSBT (sm_100a): one 32-byte sector answers one bloom probe for
+// up to 256 tree nodes at once.
+//
+// The node-at-a-time path (pf_kernels.cuh) reads one BIT per sector it touches.  Here the filters of a group of
+// up to 256 nodes (a "tile") are stored transposed: row i of the tile's table holds bit i of every node's filter
+// (BitVec<usize, Lsb0>, bloom_filter.rs:84-93), one column per node, row width 4..32 bytes.  For a k-mer,
+// BloomFilter::contains (bloom_filter.rs:312-332) at ALL nodes of the tile is then the AND of the K rows
+// g_i mod m (hash_iter.rs:13-27): K sector loads instead of K per node.  query_passes (query.rs:38-49) for all
+// columns is a bit-sliced count of those masks over the read's k-mers compared with ceil(theta * n_k), and
+// _query_batch's descent (query.rs:99-158: a node is reached iff every ancestor passed) is applied to the
+// resulting pass bits inside the tile and across tiles.  Every node is evaluated exactly with its own filter, so the
+// result is the reference's for any tree (including the non-superset filters its u16 name collisions produce).
+#pragma once
+#include "pf_kernels.cuh"
+
+namespace pf {
+
+constexpr int SL_MAX_COLS = 256;
+constexpr int SL_THREADS = 256;
+constexpr int SL_STEP_BATCH = 5;  // row loads a lane keeps in flight per k-mer
+
+struct SlicedTileDev {
+    uint64_t table_off;   // first u32 word of the tile's table
+    uint32_t n_cols;
+    uint32_t row_words;   // 1, 2, 4 or 8 u32 words per row (32..256 columns)
+    uint32_t prop_iters;  // depth of the deepest column below the tile's roots
+    uint32_t first_child, n_children;  // links to the tiles whose roots hang below this tile's columns
+    uint32_t entry;       // 1: every root is reached unconditionally (nothing evaluated above it)
+    uint32_t valid[8];    // columns in use
+    uint32_t terminal[8]; // columns that are tree leaves or have a child in another tile
+    uint32_t leafmask[8]; // columns that are tree leaves
+    uint16_t parent[SL_MAX_COLS];  // in-tile parent column; roots: 0x8000 | column in the parent tile (entry: 0xFFFF)
+    int32_t leaf[SL_MAX_COLS];     // left-first DFS leaf index (query.rs:197-218) or -1
+};
+
+struct SlicedArgs {
+    // frontier of (read, tile) pairs; entry depth (fr_read == null): pair i = (read0 + i % n_chunk, entry_tiles[i / n_chunk])
+    const uint32_t *fr_read, *fr_tile, *fr_src;
+    uint32_t n_pairs;
+    const uint32_t *entry_tiles;
+    uint32_t read0, n_chunk;
+    // reads
+    const uint32_t *lengths;
+    const uint64_t *kmer_off;
+    const uint64_t *hb;
+    uint64_t kmer_base;
+    // tiles
+    const SlicedTileDev *tiles;
+    const uint32_t *tables;
+    const uint32_t *child_tile;  // [links]
+    const uint32_t *child_mask;  // [links][8] columns of the parent tile above the child tile's roots
+    const uint32_t *src_reach;   // [pairs of the previous depth][8]
+    // outputs
+    uint32_t *reach;             // [n_pairs][8] columns reached AND passed (written for pairs listed in `alive`)
+    uint32_t *alive;             // indices of the pairs with a hit or a successor, any order
+    uint32_t *tile_count;        // per tile: pairs the next depth will hold
+    unsigned long long *counters;  // [0] sectors loaded, [1] alive pairs, [2] leaf hits
+    unsigned int *work_ctr;
+    HashParams hp;
+    float threshold;
+    uint32_t grab;
+};
+
+template <int RW>
+PF_D void sl_load_row(const uint32_t *p, uint32_t (&w)[RW]) {
+    if constexpr (RW == 8) {
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "l"(p));
+    } else if constexpr (RW == 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+    } else if constexpr (RW == 2) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        w[0] = v.x, w[1] = v.y;
+    } else {
+        w[0] = __ldg(p);
+    }
+}
+// streaming 8-byte load: the cached hash values are read once per (read, tile) pair and must not displace table rows
+PF_D uint64_t sl_ld_stream(const uint64_t *p) {
+    return __ldcs(reinterpret_cast<const unsigned long long *>(p));  // ld.global.cs: evict-first in L1 and L2
+}
+PF_D uint32_t sl_xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
+PF_D uint32_t sl_maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+
+template <int RW>
+struct SlLog2 { static constexpr int v = RW == 8 ? 3 : (RW == 4 ? 2 : (RW == 2 ? 1 : 0)); };
+// After the reduce-scatter below lane l owns the row word with this index ...
+template <int RW>
+PF_D uint32_t sl_word_of_lane(uint32_t lane) {
+    uint32_t j = 0;
+#pragma unroll
+    for (int b = 0; b < SlLog2<RW>::v; ++b) j |= ((lane >> b) & 1u) << (SlLog2<RW>::v - 1 - b);
+    return j;
+}
+// ... and this is the lowest lane that owns word j.
+template <int RW>
+PF_D uint32_t sl_lane_of_word(uint32_t j) {
+    uint32_t l = 0;
+#pragma unroll
+    for (int b = 0; b < SlLog2<RW>::v; ++b) l |= ((j >> (SlLog2<RW>::v - 1 - b)) & 1u) << b;
+    return l;
+}
+
+// Per column, the number of lanes whose mask has the column's bit set, as a 6-plane bit-sliced number for the row word
+// this lane owns (sl_word_of_lane): a reduce-scatter over the low lane bits (each stage halves the words a lane keeps
+// and adds the partner's planes with full adders), then an all-reduce over the remaining lane bits.
+template <int RW>
+PF_D void sl_count_columns(const uint32_t (&m)[RW], uint32_t lane, uint32_t (&cnt)[6]) {
+    constexpr int L = SlLog2<RW>::v;
+    uint32_t a[6][RW];
+#pragma unroll
+    for (int w = 0; w < RW; ++w) a[0][w] = m[w];
+#pragma unroll
+    for (int b = 0; b < L; ++b) {
+        const int P = 1 + b, H = RW >> (b + 1);
+        const bool hi = (lane >> b) & 1u;
+#pragma unroll
+        for (int w = 0; w < H; ++w) {
+            uint32_t carry = 0;
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl) {
+                const uint32_t lo_v = a[pl][w], hi_v = a[pl][w + H];
+                const uint32_t keep = hi ? hi_v : lo_v, send = hi ? lo_v : hi_v;
+                const uint32_t recv = __shfl_xor_sync(0xFFFFFFFFu, send, 1 << b);
+                a[pl][w] = sl_xor3(keep, recv, carry);
+                carry = sl_maj(keep, recv, carry);
+            }
+            a[P][w] = carry;
+        }
+    }
+#pragma unroll
+    for (int b = L; b < 5; ++b) {
+        const int P = 1 + b;
+        uint32_t carry = 0;
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) {
+            const uint32_t keep = a[pl][0];
+            const uint32_t recv = __shfl_xor_sync(0xFFFFFFFFu, keep, 1 << b);
+            a[pl][0] = sl_xor3(keep, recv, carry);
+            carry = sl_maj(keep, recv, carry);
+        }
+        a[P][0] = carry;
+    }
+#pragma unroll
+    for (int pl = 0; pl < 6; ++pl) cnt[pl] = a[pl][0];
+}
+
+// columns whose bit-sliced counter is >= c
+template <int PW>
+PF_D uint32_t sl_ge(const uint32_t (&acc)[PW], uint32_t c) {
+    if (PW < 32 && (c >> PW) != 0u) return 0u;
+    uint32_t gt = 0u, eq = 0xFFFFFFFFu;
+#pragma unroll
+    for (int pl = PW - 1; pl >= 0; --pl) {
+        const uint32_t cb = ((c >> pl) & 1u) ? 0xFFFFFFFFu : 0u;
+        gt |= eq & acc[pl] & ~cb;
+        eq &= ~(acc[pl] ^ cb);
+    }
+    return gt | eq;
+}
+
+// One (read, tile) pair.  Returns true when the pair has an output (a leaf hit or a successor tile); the columns
+// reached and passed are then in reach_out (replicated in every lane).  s_bits: 8 words of shared memory of this warp.
+template <int RW, int PW, bool SMALL_M>
+PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t r, uint32_t src, uint32_t lane,
+                  uint32_t *s_bits, uint32_t (&reach_out)[RW], uint32_t &sectors) {
+    const HashParams &hp = a.hp;
+    const uint32_t n_k = kmers_of(ldg32(a.lengths + r), hp.k);
+    const uint32_t need = need_of(a.threshold, n_k);
+    const bool allowed0 = need == n_k && n_k != 0u;
+    const uint32_t *__restrict__ table = a.tables + tm->table_off;
+    const uint64_t *__restrict__ hbp = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
+    const uint32_t my_word = sl_word_of_lane<RW>(lane);
+    const uint32_t valid_mine = tm->valid[my_word], term_mine = tm->terminal[my_word];
+    uint32_t live[RW], term[RW];
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        live[w] = tm->valid[w];
+        term[w] = tm->terminal[w];
+    }
+    uint32_t acc[PW];
+#pragma unroll
+    for (int pl = 0; pl < PW; ++pl) acc[pl] = 0u;
+    const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
+    const uint32_t K = hp.K;
+    for (uint32_t base = 0; base < n_k; base += 32u) {
+        const bool have = base + lane < n_k;
+        const uint64_t hbv = have ? sl_ld_stream(hbp + base + lane) : 0ULL;
+        const uint64_t h1 = fx_finish(hp.c1, hbv, hp.rot), h2 = fx_finish(hp.c2, hbv, hp.rot);
+        uint32_t m[RW];
+#pragma unroll
+        for (int w = 0; w < RW; ++w) m[w] = 0xFFFFFFFFu;  // lanes without a k-mer stay neutral for the AND below
+        bool on = have;
+        uint64_t g = h1;  // g_0 = h1, g_1 = h2, g_i = (h1 + i) * h2 = g_{i-1} + h2 from g_2 on (hash_iter.rs:17-24)
+        bool pair_dead = false;
+        for (uint32_t s = 0; s < K; s += SL_STEP_BATCH) {
+            uint32_t rows[SL_STEP_BATCH][RW];
+#pragma unroll
+            for (int b = 0; b < SL_STEP_BATCH; ++b) {
+#pragma unroll
+                for (int w = 0; w < RW; ++w) rows[b][w] = 0xFFFFFFFFu;
+                if (s + b < K) {
+                    if (on) {
+                        uint64_t idx;
+                        if (SMALL_M) idx = mod_small(g, M0, M1, m32);
+                        else idx = mod_any(g, hp.m, hp.M);
+                        sl_load_row<RW>(table + idx * RW, rows[b]);
+                        ++sectors;
+                    }
+                    const uint32_t i = s + b;
+                    g = i == 0u ? h2 : (i == 1u ? (h1 + 2ULL) * h2 : g + h2);
+                }
+            }
+            uint32_t any_live = 0u;
+#pragma unroll
+            for (int w = 0; w < RW; ++w) {
+#pragma unroll
+                for (int b = 0; b < SL_STEP_BATCH; ++b) m[w] &= rows[b][w];
+                any_live |= m[w] & live[w];
+            }
+            // BloomFilter::contains stops at the first clear bit; here a k-mer stops once it is absent from every
+            // column that can still matter
+            on = on && any_live != 0u;
+            if (allowed0) {
+                // theta = 1.0: one absent k-mer settles a column, so the columns alive are the AND over the lanes
+                uint32_t t = 0u;
+#pragma unroll
+                for (int w = 0; w < RW; ++w) {
+                    live[w] &= __reduce_and_sync(0xFFFFFFFFu, m[w]);
+                    t |= live[w] & term[w];
+                }
+                if (t == 0u) {
+                    pair_dead = true;
+                    break;
+                }
+            }
+            if (!__any_sync(0xFFFFFFFFu, on)) break;
+        }
+        if (pair_dead) return false;
+        if (!have) {
+#pragma unroll
+            for (int w = 0; w < RW; ++w) m[w] = 0u;
+        }
+        uint32_t cnt[6];
+        sl_count_columns<RW>(m, lane, cnt);
+        {  // acc += cnt
+            uint32_t carry = 0u;
+#pragma unroll
+            for (int pl = 0; pl < PW; ++pl) {
+                const uint32_t x = pl < 6 ? cnt[pl] : 0u;
+                const uint32_t s = sl_xor3(acc[pl], x, carry);
+                carry = sl_maj(acc[pl], x, carry);
+                acc[pl] = s;
+            }
+        }
+        // read-level early exit: a column that cannot reach `need` any more even if all remaining k-mers hit
+        const uint32_t done = min(base + 32u, n_k), rest = n_k - done;
+        if (need > rest) {
+            const uint32_t alive_mine = sl_ge<PW>(acc, need - rest) & valid_mine;
+            if (!__any_sync(0xFFFFFFFFu, (alive_mine & term_mine) != 0u)) return false;
+            if (!allowed0 && rest) {
+#pragma unroll
+                for (int w = 0; w < RW; ++w) live[w] = __shfl_sync(0xFFFFFFFFu, alive_mine, sl_lane_of_word<RW>(w));
+            }
+        }
+    }
+    // query_passes (query.rs:48): hits >= ceil(theta * n_k)
+    const uint32_t pass_mine = sl_ge<PW>(acc, need) & valid_mine;
+    uint32_t pass[RW], t = 0u;
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        pass[w] = __shfl_sync(0xFFFFFFFFu, pass_mine, sl_lane_of_word<RW>(w));
+        t |= pass[w] & term[w];
+    }
+    if (t == 0u) return false;
+    // _query_batch (query.rs:99-158): a column is reached iff its parent was reached and passed.  Roots take that from
+    // the pair one tile up (or unconditionally in an entry tile); inside the tile the bits are relaxed prop_iters times.
+    uint32_t par[RW];
+    uint32_t reach[RW];
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        const uint32_t c = 32u * w + lane;
+        par[w] = tm->parent[c];
+        bool bit = (pass[w] >> lane) & 1u;
+        if (bit && (par[w] & 0x8000u)) {
+            if (par[w] != 0xFFFFu) {
+                const uint32_t pc = par[w] & 0x7FFFu;
+                bit = (ldg32(a.src_reach + (size_t)src * 8u + (pc >> 5)) >> (pc & 31u)) & 1u;
+            }
+        } else if (bit) {
+            bit = false;  // decided by the relaxation below
+        }
+        reach[w] = __ballot_sync(0xFFFFFFFFu, bit);
+    }
+    const uint32_t iters = tm->prop_iters;
+    for (uint32_t it = 0; it < iters; ++it) {
+        __syncwarp();
+        if (lane < RW) {
+#pragma unroll
+            for (int w = 0; w < RW; ++w)
+                if (lane == (uint32_t)w) s_bits[w] = reach[w];
+        }
+        __syncwarp();
+        uint32_t changed = 0u;
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            bool bit = (reach[w] >> lane) & 1u;
+            if (!bit && ((pass[w] >> lane) & 1u) && !(par[w] & 0x8000u))
+                bit = (s_bits[par[w] >> 5] >> (par[w] & 31u)) & 1u;
+            const uint32_t nw = __ballot_sync(0xFFFFFFFFu, bit);
+            changed |= nw ^ reach[w];
+            reach[w] = nw;
+        }
+        if (!changed) break;
+    }
+    t = 0u;
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        reach_out[w] = reach[w];
+        t |= reach[w] & term[w];
+    }
+    return t != 0u;
+}
+
+template <int RW, int PW, bool SMALL_M>
+PF_D void sl_pair_and_record(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t pair, uint32_t r,
+                             uint32_t src, uint32_t lane, uint32_t *s_bits, uint32_t &sectors) {
+    uint32_t reach[RW];
+    if (!sl_pair<RW, PW, SMALL_M>(a, tm, r, src, lane, s_bits, reach, sectors)) return;
+    // record: reach vector, alive list, per-tile successor counts, hit count
+    if (lane < 8u) {
+        uint32_t v = 0u;
+#pragma unroll
+        for (int w = 0; w < RW; ++w)
+            if (lane == (uint32_t)w) v = reach[w];
+        a.reach[(size_t)pair * 8u + lane] = v;
+    }
+    uint32_t hits = 0u;
+#pragma unroll
+    for (int w = 0; w < RW; ++w) hits += __popc(reach[w] & tm->leafmask[w]);
+    if (lane == 0u) {
+        const unsigned long long slot = atomicAdd(a.counters + 1, 1ULL);
+        a.alive[slot] = pair;
+        if (hits) atomicAdd(a.counters + 2, (unsigned long long)hits);
+    }
+    for (uint32_t c = lane; c < tm->n_children; c += 32u) {
+        const uint32_t *cm = a.child_mask + (size_t)(tm->first_child + c) * 8u;
+        uint32_t t = 0u;
+#pragma unroll
+        for (int w = 0; w < RW; ++w) t |= reach[w] & ldg32(cm + w);
+        if (t) atomicAdd(a.tile_count + ldg32(a.child_tile + tm->first_child + c), 1u);
+    }
+}
+
+// Persistent grid; a warp takes `grab` consecutive pairs per ticket and works them one after the other.
+template <int PW, bool SMALL_M>
+static __global__ void __launch_bounds__(SL_THREADS, 2) sliced_probe_kernel(const SlicedArgs a) {
+    __shared__ uint32_t s_bits_all[SL_THREADS / 32][8];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t *const s_bits = s_bits_all[threadIdx.x >> 5];
+    uint32_t sectors = 0u;
+    unsigned long long sectors_total = 0ULL;
+    for (;;) {
+        uint32_t g0 = 0;
+        if (lane == 0) g0 = atomicAdd(a.work_ctr, a.grab);
+        g0 = __shfl_sync(0xFFFFFFFFu, g0, 0);
+        if (g0 >= a.n_pairs) break;
+        const uint32_t g1 = min(g0 + a.grab, a.n_pairs);
+        for (uint32_t i = g0; i < g1; ++i) {
+            uint32_t r, t, src = NONE32_D;
+            if (a.fr_read) {
+                r = ldg32(a.fr_read + i);
+                t = ldg32(a.fr_tile + i);
+                src = ldg32(a.fr_src + i);
+            } else {
+                const uint32_t e = i / a.n_chunk;
+                r = a.read0 + (i - e * a.n_chunk);
+                t = ldg32(a.entry_tiles + e);
+            }
+            const SlicedTileDev *tm = a.tiles + t;
+            switch (tm->row_words) {
+                case 8: sl_pair_and_record<8, PW, SMALL_M>(a, tm, i, r, src, lane, s_bits, sectors); break;
+                case 4: sl_pair_and_record<4, PW, SMALL_M>(a, tm, i, r, src, lane, s_bits, sectors); break;
+                case 2: sl_pair_and_record<2, PW, SMALL_M>(a, tm, i, r, src, lane, s_bits, sectors); break;
+                default: sl_pair_and_record<1, PW, SMALL_M>(a, tm, i, r, src, lane, s_bits, sectors); break;
+            }
+        }
+        sectors_total += __reduce_add_sync(0xFFFFFFFFu, sectors);
+        sectors = 0u;
+    }
+    if (lane == 0 && sectors_total) atomicAdd(a.counters, sectors_total);
+}
+
+// Second pass over the pairs that have an output: leaf hits go to the hit list and the per-leaf histogram
+// (mapped_reads, query.rs:143; ResultMap::add_read_map, result_map.rs:20-22), successor tiles get their (read, tile,
+// source pair) entries, tile-major.
+struct SlicedEmitArgs {
+    const uint32_t *fr_read, *fr_tile;  // null at the entry depth (see SlicedArgs)
+    const uint32_t *entry_tiles;
+    uint32_t read0, n_chunk;
+    const uint32_t *alive;
+    uint32_t n_alive;
+    const uint32_t *reach;
+    const SlicedTileDev *tiles;
+    const uint32_t *child_tile, *child_mask;
+    const unsigned long long *tile_base;  // per tile: first slot in the next frontier
+    uint32_t *tile_cursor;
+    uint32_t *nx_read, *nx_tile, *nx_src;
+    uint32_t *hit_read, *hit_leaf, *read_hits;
+    unsigned long long *hit_cursor;  // next free slot of the hit list
+    unsigned long long *blk_counts;
+    int want_hits;
+};
+static __global__ void sliced_emit_kernel(const SlicedEmitArgs a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t x = warp; x < a.n_alive; x += n_warps) {
+        const uint32_t i = ldg32(a.alive + x);
+        uint32_t r, t;
+        if (a.fr_read) {
+            r = ldg32(a.fr_read + i);
+            t = ldg32(a.fr_tile + i);
+        } else {
+            const uint32_t e = i / a.n_chunk;
+            r = a.read0 + (i - e * a.n_chunk);
+            t = ldg32(a.entry_tiles + e);
+        }
+        const SlicedTileDev *tm = a.tiles + t;
+        uint32_t reach[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) reach[w] = ldg32(a.reach + (size_t)i * 8u + w);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t bits = reach[w] & tm->leafmask[w];
+            if (!bits) continue;  // warp-uniform
+            const uint32_t n = __popc(bits);
+            const bool mine = (bits >> lane) & 1u;
+            const int32_t lf = mine ? tm->leaf[32 * w + lane] : -1;
+            if (mine) atomicAdd(a.blk_counts + lf, 1ULL);
+            if (a.want_hits) {
+                unsigned long long p0 = 0;
+                if (lane == 0) p0 = atomicAdd(a.hit_cursor, (unsigned long long)n);
+                p0 = __shfl_sync(0xFFFFFFFFu, p0, 0);
+                if (mine) {
+                    const unsigned long long p = p0 + __popc(bits & ((1u << lane) - 1u));
+                    a.hit_read[p] = r;
+                    a.hit_leaf[p] = (uint32_t)lf;
+                }
+                if (lane == 0 && a.want_hits == 1) atomicAdd(a.read_hits + r, n);
+            }
+        }
+        for (uint32_t c = lane; c < tm->n_children; c += 32u) {
+            const uint32_t *cm = a.child_mask + (size_t)(tm->first_child + c) * 8u;
+            uint32_t any = 0u;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) any |= reach[w] & ldg32(cm + w);
+            if (any) {
+                const uint32_t ct = ldg32(a.child_tile + tm->first_child + c);
+                const unsigned long long p = a.tile_base[ct] + atomicAdd(a.tile_cursor + ct, 1u);
+                a.nx_read[p] = r;
+                a.nx_tile[p] = ct;
+                a.nx_src[p] = i;
+            }
+        }
+    }
+}
+
+// Builds one tile's table from the row-major filters: block (bx, tile) transposes the 256 bit positions
+// [256 bx, 256 bx + 256) of up to 256 filters with warp ballots.  Warp j handles the columns 32 j .. 32 j + 31.
+static __global__ void __launch_bounds__(256) slice_kernel(const uint64_t *__restrict__ filters, uint64_t wpf,
+                                                           const uint32_t *__restrict__ col_slot,  // [tiles][256]
+                                                           const SlicedTileDev *__restrict__ tiles, uint32_t tile0,
+                                                           uint32_t *tables) {
+    const uint32_t t = tile0 + blockIdx.y;
+    const SlicedTileDev *tm = tiles + t;
+    const uint32_t rw = tm->row_words;
+    const uint32_t wj = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (wj >= rw) return;
+    const uint32_t slot = col_slot[(size_t)t * SL_MAX_COLS + 32u * wj + lane];
+    const uint64_t w0 = (uint64_t)blockIdx.x * 8u;  // first u32 word of this block's bit range
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 0u;
+    if (slot != NONE32_D && w0 < 2u * wpf) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(filters + (uint64_t)slot * wpf) + w0);
+        const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
+        x[0] = v0.x, x[1] = v0.y, x[2] = v0.z, x[3] = v0.w, x[4] = v1.x, x[5] = v1.y, x[6] = v1.z, x[7] = v1.w;
+    }
+    uint32_t *out = tables + tm->table_off + (w0 * 32u) * rw + wj;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const uint32_t v = __ballot_sync(0xFFFFFFFFu, (x[i] >> b) & 1u);
+            if (lane == (uint32_t)b) mine = v;
+        }
+        out[((uint64_t)i * 32u + lane) * rw] = mine;  // row 32 (w0 + i) + lane, word wj
+    }
+}
+
+}  // namespace pf

@@ -16,6 +16,15 @@ def _check(oracle, ot, gt, reads, theta):
     gt.reset_stats()
     want = ot.query_batch(reads, theta)
     sched = ot.query_sched(reads, theta, lazy=True)
+    # bit-sliced tiles, then whatever the cost model picks
+    for mode in (2, 0):
+        gt.set_mode(mode)
+        gt.reset_counts()
+        assert gpu_query(gt, reads, theta) == want.hit_sets(len(reads)), mode
+        assert get_leaf_counts(gt) == ot.leaf_counts(), mode
+    gt.set_mode(1)  # node-at-a-time descent: work counts are predicted by the oracle's restatement of its schedule
+    gt.reset_counts()
+    gt.reset_stats()
     # default: k-mer memo on -- same results and pairs (how many probes are issued depends on timing)
     got = gpu_query(gt, reads, theta)
     assert got == want.hit_sets(len(reads))
@@ -32,6 +41,7 @@ def _check(oracle, ot, gt, reads, theta):
     assert get_leaf_counts(gt) == ot.leaf_counts()
     st = gt.stats()
     assert (st.pairs, st.probes_issued) == (sched.pairs, sched.probes_sched)
+    gt.set_mode(0)
     return want, st
 
 

@@ -64,6 +64,12 @@ def test_fuzz(oracle, tmp_path, seed):
         ot.reset_counts()
         ref = ot.query_batch(reads, theta)
         want = ref.hit_sets(len(reads))
+        for mode in (2, 0):  # bit-sliced tiles; the cost model's choice
+            gt.set_mode(mode)
+            gt.reset_counts()
+            assert gpu_query(gt, reads, theta) == want, (seed, theta, "mode", mode)
+            assert get_leaf_counts(gt) == ot.leaf_counts(), (seed, theta, "mode", mode)
+        gt.set_mode(1)  # node-at-a-time descent: the work counts below are its schedule's
         for lazy in (True, False):
             sched = ot.query_sched(reads, theta, lazy=lazy)
             for memo in (True, False):  # the k-mer memo never changes results; without it the work is deterministic

@@ -28,6 +28,19 @@ def _compare(oracle, otree, gtree, reads, theta, check_probes=True):
     ores = otree.query_batch(reads, theta)  # the reference's semantics
     want = ores.hit_sets(len(reads))
     ghits = None
+    # bit-sliced tiles (pf_sliced.cu): every node evaluated exactly, 256 at a time
+    gtree.set_mode(2)
+    gtree.reset_counts()
+    gtree.reset_stats()
+    assert gpu_query(gtree, reads, theta) == want, "sliced"
+    assert get_leaf_counts(gtree) == otree.leaf_counts(), "sliced"
+    assert gtree.stats().sliced_blocks == 1
+    # whatever the cost model picks
+    gtree.set_mode(0)
+    gtree.reset_counts()
+    assert gpu_query(gtree, reads, theta) == want, "auto"
+    assert get_leaf_counts(gtree) == otree.leaf_counts(), "auto"
+    gtree.set_mode(1)  # node-at-a-time descent: its work counts are predicted exactly by the oracle's restatement
     for lazy, memo in ((True, True), (True, False), (False, True), (False, False)):
         gtree.reset_counts()
         gtree.reset_stats()
@@ -58,6 +71,7 @@ def _compare(oracle, otree, gtree, reads, theta, check_probes=True):
         assert (st.pairs, st.probes_issued) == (ores.pairs, ores.probes_ref)
         gtree.set_exhaustive(False)
     gtree.set_lazy(True)
+    gtree.set_mode(0)
 
 
 @pytest.mark.parametrize("k", [3, 4, 5])

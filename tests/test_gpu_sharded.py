@@ -66,6 +66,7 @@ def test_single_rank_shard_equals_oracle(oracle, db, cut, theta):
     assert len(leaf) == 0 and get_leaf_counts(tree) == ot.leaf_counts()
     # the same work as the replicated tree does (same plan, same pairs)
     rep_tree = BloomTree.load(d)
+    rep_tree.set_mode(1)      # the sharded descent is node-at-a-time
     rep_tree.set_memo(False)  # deterministic work counts
     tree.set_memo(False)
     query_packed(rep_tree, p, theta)
