@@ -237,7 +237,7 @@ struct pf_db {
     // ---- bit-sliced tiles (pf_sliced.cu): 0 = choose per (threshold, read length) by cost model, 1 = node-at-a-time
     // descent only, 2 = sliced tiles only
     int mode = 0;
-    double plan_cost = 0.0;            // expected bit probes of a read unrelated to the database under the current step plan
+    double plan_cost = 0.0;            // expected bit probes PER K-MER of a read unrelated to the database under the current step plan
     pf::SlicedState *sliced = nullptr;
     std::vector<uint8_t> nccl_id;      // ncclUniqueId handed to pf_db_open_sharded (the analysis at open is collective)
 };

@@ -29,6 +29,8 @@ struct SlicedState {
     uint64_t table_words = 0;
     uint64_t entry_bytes = 0;
     double est_sectors_per_read = 0.0;     // cost model: expected sector loads of a read unrelated to the database
+    double est_seconds_per_read = 0.0;     // ... and the time they take at the measured random-row rates
+    double est_seconds_related = 0.0;      // the same for a read that belongs to a genome of the database
     // device
     SlicedTileDev *d_tiles = nullptr;
     uint32_t *d_tables = nullptr, *d_child_tile = nullptr, *d_child_mask = nullptr, *d_entry = nullptr;
@@ -44,6 +46,7 @@ struct SlicedState {
     float theta = -1.f;
     uint64_t n_nominal = 0;
     int decided_mode = 0;  // 1 pair, 2 sliced (for theta / n_nominal above)
+    int decided_under = -1;  // pf_db_set_mode value the decision was taken under
     bool failed = false;   // tables could not be built (memory): stay with the node-at-a-time path
 };
 
@@ -107,48 +110,68 @@ static double sector_rate(double footprint_bytes) {
 }
 static uint32_t width_for(size_t cols) { return cols <= 32 ? 32u : (cols <= 64 ? 64u : (cols <= 128 ? 128u : 256u)); }
 
-// Cuts the (pruned, level-ordered) tree into tiles for `threshold` and reads of `n_nominal` k-mers.
-//  1. Skip set: interior nodes, connected to the root, below which every (node, child) pair was verified at load time to
-//     be a bitwise superset (child passes => node passes, see analyse_tree) and which an unrelated read passes almost
-//     surely (filter nearly full).  They are never evaluated: whatever passes a leaf below them passes them too.
-//  2. Every other node gets a column in exactly one tile.  A tile's roots all hang below columns of ONE parent tile
-//     (or below skipped nodes: entry tiles).  Where filters are still dense (fill > 1/2, in the node or below it) tiles
-//     are wide and shallow -- as many sibling subtrees side by side as fit, so the reads that die there touch few
-//     tiles; sparse subtrees are packed whole, several per tile, so a read that survives needs one more tile.
-static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, SlicedState &S) {
+// Per-node facts the tiling works from (host only).
+struct TreeFacts {
+    std::vector<uint32_t> parent, sz, leaves;  // subtree size in nodes / in tree leaves
+    std::vector<uint8_t> vb, inA;              // vb: every (node, child) pair below was verified a bitwise superset
+    std::vector<double> fill, p, q;            // p: a k-mer unrelated to the node passes it; q: an unrelated read passes it
+    double n = 0, allowed = 0;
+    uint64_t need = 0;
+};
+static void tree_facts(const pf_db *db, float threshold, uint64_t n_nominal, TreeFacts &F) {
     const size_t nn = db->n_nodes;
     const uint32_t K = db->geom.num_hashes;
     const double mbits = (double)db->geom.num_bits;
-    std::vector<uint32_t> parent(nn, NONE32);
+    F.parent.assign(nn, NONE32);
     for (size_t u = 0; u < nn; ++u) {
-        if (db->h_left[u] != NONE32) parent[db->h_left[u]] = (uint32_t)u;
-        if (db->h_right[u] != NONE32) parent[db->h_right[u]] = (uint32_t)u;
+        if (db->h_left[u] != NONE32) F.parent[db->h_left[u]] = (uint32_t)u;
+        if (db->h_right[u] != NONE32) F.parent[db->h_right[u]] = (uint32_t)u;
     }
-    const uint64_t need = need_host(threshold, n_nominal);
-    const double n = (double)n_nominal;
-    std::vector<uint8_t> vb(nn, 1), inA(nn, 0);
-    std::vector<uint32_t> sz(nn, 1);
-    std::vector<double> q(nn, 0.0), fill(nn, 0.0);
+    F.need = need_host(threshold, n_nominal);
+    F.n = (double)n_nominal;
+    F.allowed = F.need > n_nominal ? 0.0 : (double)(n_nominal - F.need);
+    F.vb.assign(nn, 1);
+    F.inA.assign(nn, 0);
+    F.sz.assign(nn, 1);
+    F.leaves.assign(nn, 0);
+    F.p.assign(nn, 0.0);
+    F.fill.assign(nn, 0.0);
+    F.q.assign(nn, 0.0);
     for (size_t u = nn; u-- > 0;) {
-        const uint32_t l = db->h_left[u], r = db->h_right[u];
-        fill[u] = (double)db->h_pop[u] / mbits;
-        const double p = pow(fill[u], (double)K), mean = n * p, var = n * p * (1.0 - p);
-        q[u] = var < 1e-9 ? (mean + 0.5 >= (double)need ? 1.0 : 0.0) : phi_tab((mean - (double)need + 0.5) / sqrt(var));
-        inA[u] = fill[u] > 0.5;
-        if (db->h_leaf[u] >= 0) continue;
-        vb[u] = db->h_mono[u];
-        for (uint32_t c : {l, r})
+        const double fill = (double)db->h_pop[u] / mbits;
+        const double p = pow(fill, (double)K), mean = F.n * p, var = F.n * p * (1.0 - p);
+        F.p[u] = p;
+        F.fill[u] = fill;
+        F.q[u] = var < 1e-9 ? (mean + 0.5 >= (double)F.need ? 1.0 : 0.0) : phi_tab((mean - (double)F.need + 0.5) / sqrt(var));
+        F.inA[u] = fill > 0.5;
+        if (db->h_leaf[u] >= 0) {
+            F.leaves[u] = 1;
+            continue;
+        }
+        F.vb[u] = db->h_mono[u];
+        for (uint32_t c : {db->h_left[u], db->h_right[u]})
             if (c != NONE32) {
-                vb[u] = vb[u] && vb[c];
-                inA[u] = inA[u] || inA[c];
-                sz[u] += sz[c];
+                F.vb[u] = F.vb[u] && F.vb[c];
+                F.inA[u] = F.inA[u] || F.inA[c];
+                F.sz[u] += F.sz[c];
+                F.leaves[u] += F.leaves[c];
             }
     }
-    S.skip.assign(nn, 0);
-    for (size_t u = 0; u < nn; ++u) {
-        if (db->h_leaf[u] >= 0 || !vb[u] || q[u] < 0.9) continue;
-        if (u == 0 || S.skip[parent[u]]) S.skip[u] = 1;
-    }
+}
+
+// Cuts the (pruned, level-ordered) tree into tiles given the set of nodes that are not evaluated.
+//  * Skipped nodes: interior, connected to the root, and every (node, child) pair below them was verified at load time
+//    to be a bitwise superset (analyse_tree), so whatever passes a leaf below them passes them too: evaluating the
+//    nodes of the cut exactly selects exactly the reads the reference's descent would let through.
+//  * Every other node gets a column in exactly one tile.  A tile's roots all hang below columns of ONE parent tile (or
+//    below skipped nodes: entry tiles, evaluated for every read).  Where filters are still dense (fill > 1/2, in the
+//    node or below it) tiles are wide and shallow -- as many sibling subtrees side by side as fit, so the reads that
+//    die there touch few tiles; sparse subtrees are packed whole, several per tile, so a read that survives needs one
+//    more tile.
+// Also fills the cost model: expected seconds of sector loads for a read unrelated to the database.
+static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
+    const size_t nn = db->n_nodes;
+    const uint32_t K = db->geom.num_hashes;
     S.tiles.clear();
     S.col_slot.clear();
     S.child_tile.clear();
@@ -166,7 +189,7 @@ static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, Sli
     {
         Job j0{-1, {}};
         for (size_t u = 0; u < nn; ++u)
-            if (!S.skip[u] && (u == 0 || S.skip[parent[u]])) j0.roots.push_back((uint32_t)u);
+            if (!S.skip[u] && (u == 0 || S.skip[F.parent[u]])) j0.roots.push_back((uint32_t)u);
         jobs.push_back(std::move(j0));
     }
     auto bfs_subtree = [&](uint32_t r, size_t cap, std::vector<uint32_t> &out) {  // level order, parents first
@@ -184,7 +207,9 @@ static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, Sli
         jobs.pop_front();
         std::vector<std::vector<uint32_t>> made;  // column lists of the tiles of this job
         std::vector<uint32_t> RA, RB;
-        for (uint32_t r : job.roots) (inA[r] ? RA : RB).push_back(r);
+        // entry tiles see every read: roots side by side, as few tiles as possible.  Below them come the reads that
+        // (mostly) belong there: whole subtrees, several per tile, so that such a read needs one more tile only.
+        for (uint32_t r : job.roots) (job.parent_tile < 0 ? RA : RB).push_back(r);
         for (size_t c0 = 0; c0 < RA.size(); c0 += SL_MAX_COLS) {
             std::vector<uint32_t> cols(RA.begin() + c0, RA.begin() + std::min(RA.size(), c0 + SL_MAX_COLS));
             const size_t cap = width_for(cols.size());
@@ -195,8 +220,8 @@ static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, Sli
         }
         std::vector<uint32_t> cur;
         for (uint32_t r : RB) {
-            if (sz[r] <= (uint32_t)SL_MAX_COLS) {
-                if (cur.size() + sz[r] > (size_t)SL_MAX_COLS) {
+            if (F.sz[r] <= (uint32_t)SL_MAX_COLS) {
+                if (cur.size() + F.sz[r] > (size_t)SL_MAX_COLS) {
                     made.push_back(std::move(cur));
                     cur.clear();
                 }
@@ -236,7 +261,7 @@ static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, Sli
                 tm.valid[c >> 5] |= 1u << (c & 31);
                 tm.leaf[c] = db->h_leaf[u];
                 if (db->h_leaf[u] >= 0) tm.leafmask[c >> 5] |= 1u << (c & 31);
-                const uint32_t p = parent[u];
+                const uint32_t p = F.parent[u];
                 if (p != NONE32 && node_tile[p] == (int32_t)t && node_col[p] < c) {
                     tm.parent[c] = (uint16_t)node_col[p];
                     depth[c] = depth[node_col[p]] + 1;
@@ -285,26 +310,133 @@ static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, Sli
             if (!nj.roots.empty()) jobs.push_back(std::move(nj));
         }
     }
-    // cost model: sector loads of a read unrelated to the database; a tile below another one is reached with the
-    // probability that one of the columns above its roots passes
+    // Cost model (steers choices only, never results).  A read unrelated to the database leaves a tile once every
+    // terminal column has more than `allowed` k-mers proven absent.  With s probe steps per k-mer, a terminal of fill f
+    // proves an unrelated k-mer absent with probability r = 1 - f^s, so it needs about (allowed + 1) / r k-mers (plus two
+    // standard deviations), in rounds of 32 k-mers of s row loads.  Per tile the pre-test depth s (0 = none) is chosen
+    // to minimise the expected row loads, assuming half of the reads that arrive belong below the tile (they pay the
+    // pre-test on top of the exact pass).  A tile below another one is reached by an unrelated read with the
+    // probability that one of the columns above its roots passes.
     {
         const size_t nt = S.tiles.size();
-        std::vector<double> pr(nn, 0.0);  // per node: probability that the node is reached and passes
-        for (size_t u = 0; u < nn; ++u) pr[u] = S.skip[u] ? 1.0 : (u == 0 ? 1.0 : pr[parent[u]]) * q[u];
-        double total = 0.0;
+        std::vector<double> pr(nn, 0.0);  // per node: probability that an unrelated read reaches and passes it
+        for (size_t u = 0; u < nn; ++u) pr[u] = S.skip[u] ? 1.0 : (u == 0 ? 1.0 : pr[F.parent[u]]) * F.q[u];
+        double total_s = 0.0, total_sectors = 0.0;
+        uint32_t max_depth = 0;
+        std::vector<uint32_t> tdepth(nt, 0);
+        const double a1 = F.allowed + 1.0, n = F.n;
         for (size_t t = 0; t < nt; ++t) {
-            double p = 1.0;
+            SlicedTileDev &tm = S.tiles[t];
+            if (S.tile_parent[t] >= 0) tdepth[t] = tdepth[S.tile_parent[t]] + 1;
+            max_depth = std::max(max_depth, tdepth[t]);
+            double reach = 1.0;
             if (S.tile_parent[t] >= 0) {
-                // a root column is reached iff its parent (one tile up) was reached and passed; several roots may share
-                // a parent -- treating them as independent only makes the estimate larger
                 double none = 1.0;
-                for (uint32_t c = 0; c < S.tiles[t].n_cols; ++c)
-                    if (S.tiles[t].parent[c] & 0x8000u) none *= 1.0 - pr[parent[S.tile_nodes[t][c]]];
-                p = 1.0 - none;
+                for (uint32_t c = 0; c < tm.n_cols; ++c)
+                    if (tm.parent[c] & 0x8000u) none *= 1.0 - pr[F.parent[S.tile_nodes[t][c]]];
+                reach = 1.0 - none;
             }
-            total += p * n * (double)K;
+            double fmax = 0.0;  // the terminal that holds out longest is the fullest one
+            for (uint32_t c = 0; c < tm.n_cols; ++c)
+                if ((tm.terminal[c >> 5] >> (c & 31)) & 1u) fmax = std::max(fmax, F.fill[S.tile_nodes[t][c]]);
+            fmax = std::min(fmax, 0.999999);
+            auto kmers_to_die = [&](uint32_t s) {  // k-mers until the fullest terminal is ruled out, or -1: it survives
+                const double r = 1.0 - pow(fmax, (double)s);
+                const double j = (a1 + 2.0 * sqrt(a1 * (1.0 - r))) / r;
+                if (j > n) return -1.0;
+                return F.allowed == 0.0 ? std::max(16.0, j) : ceil(j / 32.0) * 32.0;
+            };
+            // Filter-only tile: no leaf column and every column's subtree verified (child passes => node passes all the
+            // way down).  Such a tile only has to weed out reads: what its pre-test cannot rule out goes on to the tiles
+            // below, which are evaluated exactly -- a leaf that passes there implies that these columns pass too.
+            bool filt_ok = true;
+            for (uint32_t c = 0; c < tm.n_cols && filt_ok; ++c)
+                filt_ok = F.vb[S.tile_nodes[t][c]] && db->h_leaf[S.tile_nodes[t][c]] < 0;
+            const double jK = kmers_to_die(K);
+            const double exact_unrel = (jK < 0 ? n : jK) * (double)K, exact_rel = n * (double)K;
+            double best = 0.5 * exact_unrel + 0.5 * exact_rel, best_unrel = exact_unrel;
+            uint32_t best_s = 0;
+            const bool pretest_useful = tm.entry || reach > 0.5;
+            for (uint32_t s = 1; pretest_useful && s < K && s <= (uint32_t)SL_STEP_BATCH; ++s) {
+                const double j = kmers_to_die(s);
+                const double unrel = j < 0 ? n * (double)s + exact_unrel : j * (double)s;
+                const double c = 0.5 * unrel + 0.5 * (n * (double)s + (filt_ok ? 0.0 : exact_rel));
+                if (c < best) {
+                    best = c;
+                    best_unrel = unrel;
+                    best_s = s;
+                }
+            }
+            tm.pre_steps = best_s;
+            tm.filter_only = best_s != 0 && filt_ok;
+            const double bytes = (double)(64ULL * db->wpf) * tm.row_words * 4.0;
+            // entry tiles are worked tile-major, one table hot at a time; deeper tiles are touched at random
+            const double rate = tm.entry ? sector_rate(bytes) : sector_rate(1e12);
+            total_s += reach * best_unrel / rate;
+            total_sectors += reach * best_unrel;
         }
-        S.est_sectors_per_read = total;
+        S.est_sectors_per_read = total_sectors;
+        S.est_seconds_per_read = total_s;
+        // a read that belongs to a genome of the database walks one tile per tile-tree level with all its k-mers
+        S.est_seconds_related = (double)(max_depth + 1) * n * (double)K / sector_rate(1e12);
+    }
+}
+
+// Chooses the cut: the skipped top is "every verified interior node with more than G leaves below it", for the G that
+// makes an unrelated read cheapest under the cost model (deeper cuts have emptier filters, so reads die after fewer
+// k-mers, but need more columns and hence more tiles).  G = infinity (nothing skipped) is always a candidate and the
+// only one when the top of the tree holds an unverified node.
+static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, SlicedState &S) {
+    TreeFacts F;
+    tree_facts(db, threshold, n_nominal, F);
+    const size_t nn = db->n_nodes;
+    std::vector<uint64_t> cand{~0ULL};
+    for (double g = (double)std::max<uint64_t>(db->n_leaves, 1); g >= 1.0; g /= 1.4142135623730951) {
+        const uint64_t G = (uint64_t)g;
+        if (cand.back() != G) cand.push_back(G);
+    }
+    SlicedState best;
+    bool have = false;
+    std::vector<uint8_t> prev_skip;
+    for (uint64_t G : cand) {
+        SlicedState T;
+        T.skip.assign(nn, 0);
+        for (size_t u = 0; u < nn; ++u) {
+            if (db->h_leaf[u] >= 0 || !F.vb[u] || (uint64_t)F.leaves[u] <= G) continue;
+            if (u == 0 || T.skip[F.parent[u]]) T.skip[u] = 1;
+        }
+        if (have && T.skip == prev_skip) continue;
+        prev_skip = T.skip;
+        tile_tree(db, F, T);
+        if (getenv("PF_SLICED_DEBUG"))
+            fprintf(stderr, "[sliced plan] G=%llu skipped=%zu entry_tiles=%zu tiles=%zu est=%.2f ns/read (%.0f sectors)\n",
+                    (unsigned long long)G, (size_t)std::count(T.skip.begin(), T.skip.end(), 1), T.entry_tiles.size(),
+                    T.tiles.size(), T.est_seconds_per_read * 1e9, T.est_sectors_per_read);
+        if (!have || T.est_seconds_per_read < best.est_seconds_per_read) {
+            best = std::move(T);
+            have = true;
+        }
+    }
+    S.skip = std::move(best.skip);
+    S.tiles = std::move(best.tiles);
+    S.col_slot = std::move(best.col_slot);
+    S.child_tile = std::move(best.child_tile);
+    S.child_mask = std::move(best.child_mask);
+    S.entry_tiles = std::move(best.entry_tiles);
+    S.tile_parent = std::move(best.tile_parent);
+    S.tile_nodes = std::move(best.tile_nodes);
+    S.table_words = best.table_words;
+    S.entry_bytes = best.entry_bytes;
+    S.est_sectors_per_read = best.est_sectors_per_read;
+    S.est_seconds_per_read = best.est_seconds_per_read;
+    S.est_seconds_related = best.est_seconds_related;
+    if (getenv("PF_SLICED_DEBUG")) {
+        fprintf(stderr, "[sliced plan] chosen: %zu tiles, %zu entry, tables %.2f GB, est %.2f ns/read\n", S.tiles.size(),
+                S.entry_tiles.size(), S.table_words * 4.0 / 1e9, S.est_seconds_per_read * 1e9);
+        for (uint32_t t : S.entry_tiles)
+            fprintf(stderr, "[sliced plan]   entry tile %u: %u columns, row %u B, %u children, pre-test %u steps%s\n", t,
+                    S.tiles[t].n_cols, S.tiles[t].row_words * 4, S.tiles[t].n_children, S.tiles[t].pre_steps,
+                    S.tiles[t].filter_only ? " (filter only)" : "");
     }
 }
 
@@ -368,7 +500,7 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
     if (!db->sliced) db->sliced = new SlicedState();
     SlicedState &S = *db->sliced;
     if (S.failed && db->mode != 2) return PF_OK;
-    if (S.decided_mode && S.theta == threshold && S.n_nominal == n_nominal && (db->mode == 0 || db->mode == S.decided_mode)) {
+    if (S.decided_mode && S.theta == threshold && S.n_nominal == n_nominal && S.decided_under == db->mode) {
         *use_sliced = S.decided_mode == 2;
         if (*use_sliced) {
             db->stats.sliced_tiles = S.tiles.size();
@@ -380,13 +512,18 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
     plan_tiles(db, threshold, n_nominal, P);
     bool sliced = db->mode == 2;
     if (db->mode == 0) {
-        const double t_pair = db->plan_cost / 240e9;
-        const double t_sliced = P.est_sectors_per_read / sector_rate((double)P.entry_bytes);
+        const double t_pair = db->plan_cost * (double)n_nominal / 240e9;  // the step plan's cost is in probes per k-mer
+        // half of the reads are assumed to belong to the database (the planner cannot know the sample's composition)
+        const double t_sliced = 0.5 * P.est_seconds_per_read + 0.5 * P.est_seconds_related;
         sliced = t_sliced < 0.8 * t_pair;
+        if (getenv("PF_SLICED_DEBUG"))
+            fprintf(stderr, "[sliced plan] auto: node-at-a-time %.1f ns/read, sliced %.1f ns/read -> %s\n", t_pair * 1e9, t_sliced * 1e9,
+                    sliced ? "sliced" : "node-at-a-time");
     }
     S.theta = threshold;
     S.n_nominal = n_nominal;
     S.decided_mode = sliced ? 2 : 1;
+    S.decided_under = db->mode;
     if (!sliced) return PF_OK;
     const bool same = S.tables_ready && S.skip == P.skip && S.tiles.size() == P.tiles.size();
     if (!same) {
@@ -401,6 +538,8 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
         S.table_words = P.table_words;
         S.entry_bytes = P.entry_bytes;
         S.est_sectors_per_read = P.est_sectors_per_read;
+        S.est_seconds_per_read = P.est_seconds_per_read;
+        S.est_seconds_related = P.est_seconds_related;
         int rc = build_tables(db, S);
         if (rc != PF_OK) {
             sliced_release_device(&S);

@@ -26,6 +26,8 @@ struct SlicedTileDev {
     uint32_t prop_iters;  // depth of the deepest column below the tile's roots
     uint32_t first_child, n_children;  // links to the tiles whose roots hang below this tile's columns
     uint32_t entry;       // 1: every root is reached unconditionally (nothing evaluated above it)
+    uint32_t pre_steps;   // probe steps of the sound pre-test pass (0 = none), chosen by the cost model
+    uint32_t filter_only; // 1: the pre-test is all this tile does (its columns are implied by what passes below them)
     uint32_t valid[8];    // columns in use
     uint32_t terminal[8]; // columns that are tree leaves or have a child in another tile
     uint32_t leafmask[8]; // columns that are tree leaves
@@ -161,30 +163,19 @@ PF_D uint32_t sl_ge(const uint32_t (&acc)[PW], uint32_t c) {
     return gt | eq;
 }
 
-// One (read, tile) pair.  Returns true when the pair has an output (a leaf hit or a successor tile); the columns
-// reached and passed are then in reach_out (replicated in every lane).  s_bits: 8 words of shared memory of this warp.
+// One pass over the k-mers of a read against one tile, `steps` probe steps per k-mer (steps = K: exact;
+// fewer: a k-mer with no clear bit among its first `steps` rows only counts as POSSIBLY present, so the column counts are
+// upper bounds).  In: alive_mine / live = columns not yet proven unable to pass (this lane's word / all words).
+// Out: the same, narrowed; acc = per-column counts of this lane's word.  Returns false as soon as no terminal column can
+// pass any more (read-level early exit; the rest of the read could not change that).
 template <int RW, int PW, bool SMALL_M>
-PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t r, uint32_t src, uint32_t lane,
-                  uint32_t *s_bits, uint32_t (&reach_out)[RW], uint32_t &sectors) {
-    const HashParams &hp = a.hp;
-    const uint32_t n_k = kmers_of(ldg32(a.lengths + r), hp.k);
-    const uint32_t need = need_of(a.threshold, n_k);
-    const bool allowed0 = need == n_k && n_k != 0u;
-    const uint32_t *__restrict__ table = a.tables + tm->table_off;
-    const uint64_t *__restrict__ hbp = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
-    const uint32_t my_word = sl_word_of_lane<RW>(lane);
-    const uint32_t valid_mine = tm->valid[my_word], term_mine = tm->terminal[my_word];
-    uint32_t live[RW], term[RW];
-#pragma unroll
-    for (int w = 0; w < RW; ++w) {
-        live[w] = tm->valid[w];
-        term[w] = tm->terminal[w];
-    }
-    uint32_t acc[PW];
+PF_D bool sl_scan(const HashParams &hp, const uint32_t *__restrict__ table, const uint64_t *__restrict__ hbp, uint32_t n_k,
+                  uint32_t need, uint32_t steps, uint32_t lane, const uint32_t (&term)[RW], uint32_t term_mine,
+                  uint32_t &alive_mine, uint32_t (&live)[RW], uint32_t (&acc)[PW], uint32_t &sectors) {
+    const bool allowed0 = need == n_k;
+    const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
 #pragma unroll
     for (int pl = 0; pl < PW; ++pl) acc[pl] = 0u;
-    const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
-    const uint32_t K = hp.K;
     for (uint32_t base = 0; base < n_k; base += 32u) {
         const bool have = base + lane < n_k;
         const uint64_t hbv = have ? sl_ld_stream(hbp + base + lane) : 0ULL;
@@ -194,14 +185,13 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
         for (int w = 0; w < RW; ++w) m[w] = 0xFFFFFFFFu;  // lanes without a k-mer stay neutral for the AND below
         bool on = have;
         uint64_t g = h1;  // g_0 = h1, g_1 = h2, g_i = (h1 + i) * h2 = g_{i-1} + h2 from g_2 on (hash_iter.rs:17-24)
-        bool pair_dead = false;
-        for (uint32_t s = 0; s < K; s += SL_STEP_BATCH) {
+        for (uint32_t s = 0; s < steps; s += SL_STEP_BATCH) {
             uint32_t rows[SL_STEP_BATCH][RW];
 #pragma unroll
             for (int b = 0; b < SL_STEP_BATCH; ++b) {
 #pragma unroll
                 for (int w = 0; w < RW; ++w) rows[b][w] = 0xFFFFFFFFu;
-                if (s + b < K) {
+                if (s + b < steps) {
                     if (on) {
                         uint64_t idx;
                         if (SMALL_M) idx = mod_small(g, M0, M1, m32);
@@ -231,14 +221,10 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
                     live[w] &= __reduce_and_sync(0xFFFFFFFFu, m[w]);
                     t |= live[w] & term[w];
                 }
-                if (t == 0u) {
-                    pair_dead = true;
-                    break;
-                }
+                if (t == 0u) return false;
             }
             if (!__any_sync(0xFFFFFFFFu, on)) break;
         }
-        if (pair_dead) return false;
         if (!have) {
 #pragma unroll
             for (int w = 0; w < RW; ++w) m[w] = 0u;
@@ -250,24 +236,174 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
 #pragma unroll
             for (int pl = 0; pl < PW; ++pl) {
                 const uint32_t x = pl < 6 ? cnt[pl] : 0u;
-                const uint32_t s = sl_xor3(acc[pl], x, carry);
+                const uint32_t sum = sl_xor3(acc[pl], x, carry);
                 carry = sl_maj(acc[pl], x, carry);
-                acc[pl] = s;
+                acc[pl] = sum;
             }
         }
-        // read-level early exit: a column that cannot reach `need` any more even if all remaining k-mers hit
+        // a column cannot pass any more once its count plus all remaining k-mers stays below `need`
         const uint32_t done = min(base + 32u, n_k), rest = n_k - done;
         if (need > rest) {
-            const uint32_t alive_mine = sl_ge<PW>(acc, need - rest) & valid_mine;
+            alive_mine &= sl_ge<PW>(acc, need - rest);
             if (!__any_sync(0xFFFFFFFFu, (alive_mine & term_mine) != 0u)) return false;
-            if (!allowed0 && rest) {
+            if (rest) {
 #pragma unroll
-                for (int w = 0; w < RW; ++w) live[w] = __shfl_sync(0xFFFFFFFFu, alive_mine, sl_lane_of_word<RW>(w));
+                for (int w = 0; w < RW; ++w) live[w] &= __shfl_sync(0xFFFFFFFFu, alive_mine, sl_lane_of_word<RW>(w));
             }
         }
     }
-    // query_passes (query.rs:48): hits >= ceil(theta * n_k)
-    const uint32_t pass_mine = sl_ge<PW>(acc, need) & valid_mine;
+    if (allowed0) {  // columns settled by the AND inside the rounds
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int w = 0; w < RW; ++w)
+            if (sl_word_of_lane<RW>(lane) == (uint32_t)w) mine = live[w];
+        alive_mine &= mine;
+    }
+    return true;
+}
+
+// The same pass for a shallow pre-test (ST = 1 or 2 probe steps): RB rounds of 32 k-mers are in flight together, so a
+// lane still has RB * ST independent row loads outstanding; the columns are re-examined every RB rounds.
+template <int RW, int PW, bool SMALL_M, int RB, int ST>
+PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ table, const uint64_t *__restrict__ hbp,
+                          uint32_t n_k, uint32_t need, uint32_t lane, const uint32_t (&term)[RW], uint32_t term_mine,
+                          uint32_t &alive_mine, uint32_t (&live)[RW], uint32_t (&acc)[PW], uint32_t &sectors) {
+    const bool allowed0 = need == n_k;
+    const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
+#pragma unroll
+    for (int pl = 0; pl < PW; ++pl) acc[pl] = 0u;
+    for (uint32_t base = 0; base < n_k; base += 32u * RB) {
+        uint64_t hbv[RB];
+        bool have[RB];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            have[j] = base + 32u * j + lane < n_k;
+            hbv[j] = have[j] ? sl_ld_stream(hbp + base + 32u * j + lane) : 0ULL;
+        }
+        uint32_t rows[RB][ST][RW];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            const uint64_t h1 = fx_finish(hp.c1, hbv[j], hp.rot), h2 = fx_finish(hp.c2, hbv[j], hp.rot);
+#pragma unroll
+            for (int st = 0; st < ST; ++st) {
+#pragma unroll
+                for (int w = 0; w < RW; ++w) rows[j][st][w] = 0xFFFFFFFFu;
+                if (have[j]) {
+                    const uint64_t g = st == 0 ? h1 : h2;  // g_0 = h1, g_1 = h2 (hash_iter.rs:17-24)
+                    uint64_t idx;
+                    if (SMALL_M) idx = mod_small(g, M0, M1, m32);
+                    else idx = mod_any(g, hp.m, hp.M);
+                    sl_load_row<RW>(table + idx * RW, rows[j][st]);
+                    ++sectors;
+                }
+            }
+        }
+        if (allowed0) {
+            uint32_t t = 0u;
+#pragma unroll
+            for (int w = 0; w < RW; ++w) {
+                uint32_t all = 0xFFFFFFFFu;
+#pragma unroll
+                for (int j = 0; j < RB; ++j)
+#pragma unroll
+                    for (int st = 0; st < ST; ++st) all &= rows[j][st][w];
+                live[w] &= __reduce_and_sync(0xFFFFFFFFu, all);
+                t |= live[w] & term[w];
+            }
+            if (t == 0u) return false;
+        }
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            if (base + 32u * j >= n_k) break;  // warp-uniform
+            uint32_t m[RW];
+#pragma unroll
+            for (int w = 0; w < RW; ++w) {
+                m[w] = have[j] ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+                for (int st = 0; st < ST; ++st) m[w] &= rows[j][st][w];
+            }
+            uint32_t cnt[6];
+            sl_count_columns<RW>(m, lane, cnt);
+            uint32_t carry = 0u;
+#pragma unroll
+            for (int pl = 0; pl < PW; ++pl) {
+                const uint32_t x = pl < 6 ? cnt[pl] : 0u;
+                const uint32_t sum = sl_xor3(acc[pl], x, carry);
+                carry = sl_maj(acc[pl], x, carry);
+                acc[pl] = sum;
+            }
+        }
+        const uint32_t done = min(base + 32u * RB, n_k), rest = n_k - done;
+        if (need > rest) {
+            alive_mine &= sl_ge<PW>(acc, need - rest);
+            if (!__any_sync(0xFFFFFFFFu, (alive_mine & term_mine) != 0u)) return false;
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < RW; ++w) live[w] &= __shfl_sync(0xFFFFFFFFu, alive_mine, sl_lane_of_word<RW>(w));
+    if (allowed0) {
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int w = 0; w < RW; ++w)
+            if (sl_word_of_lane<RW>(lane) == (uint32_t)w) mine = live[w];
+        alive_mine &= mine;
+    }
+    return true;
+}
+
+// One (read, tile) pair.  Returns true when the pair has an output (a leaf hit or a successor tile); the columns
+// reached and passed are then in reach_out (replicated in every lane).  s_bits: 8 words of shared memory of this warp.
+template <int RW, int PW, bool SMALL_M>
+PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t r, uint32_t src, uint32_t lane,
+                  uint32_t *s_bits, uint32_t (&reach_out)[RW], uint32_t &sectors) {
+    const HashParams &hp = a.hp;
+    const uint32_t n_k = kmers_of(ldg32(a.lengths + r), hp.k);
+    const uint32_t need = need_of(a.threshold, n_k);
+    const uint32_t *__restrict__ table = a.tables + tm->table_off;
+    const uint64_t *__restrict__ hbp = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
+    const uint32_t my_word = sl_word_of_lane<RW>(lane);
+    const uint32_t valid_mine = tm->valid[my_word], term_mine = tm->terminal[my_word];
+    uint32_t live[RW], term[RW];
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        live[w] = tm->valid[w];
+        term[w] = tm->terminal[w];
+    }
+    uint32_t alive_mine = valid_mine;
+    uint32_t acc[PW];
+#pragma unroll
+    for (int pl = 0; pl < PW; ++pl) acc[pl] = 0u;
+    if (need > n_k) return false;  // theta > 1: nothing can pass
+    if (n_k != 0u && need != 0u) {  // need == 0 (theta = 0, or no k-mers at all): every column passes (query.rs:48)
+        // Sound pre-test with the first few probe steps only: most reads that do not belong below this tile are
+        // settled here at a fraction of the row loads; the others are then evaluated exactly, from scratch, with the
+        // columns the pre-test has already ruled out switched off.
+        const uint32_t pre = tm->pre_steps;
+        if (pre != 0u && pre < hp.K) {
+            bool ok;
+            if (pre == 1u)
+                ok = sl_scan_shallow<RW, PW, SMALL_M, 4, 1>(hp, table, hbp, n_k, need, lane, term, term_mine, alive_mine, live,
+                                                            acc, sectors);
+            else if (pre == 2u)
+                ok = sl_scan_shallow<RW, PW, SMALL_M, 2, 2>(hp, table, hbp, n_k, need, lane, term, term_mine, alive_mine, live,
+                                                            acc, sectors);
+            else
+                ok = sl_scan<RW, PW, SMALL_M>(hp, table, hbp, n_k, need, pre, lane, term, term_mine, alive_mine, live, acc,
+                                              sectors);
+            if (!ok) return false;
+        }
+        if (pre != 0u && pre < hp.K && tm->filter_only) {
+            // columns the pre-test could not rule out count as passed: the exact tiles below decide (see plan)
+#pragma unroll
+            for (int pl = 0; pl < PW; ++pl) acc[pl] = 0xFFFFFFFFu;
+        } else if (!sl_scan<RW, PW, SMALL_M>(hp, table, hbp, n_k, need, hp.K, lane, term, term_mine, alive_mine, live, acc,
+                                             sectors)) {
+            return false;
+        }
+    }
+    // query_passes (query.rs:48): hits >= ceil(theta * n_k).  Columns ruled out earlier may hold stale counts (their
+    // k-mers stop being probed), hence the mask.
+    const uint32_t pass_mine = sl_ge<PW>(acc, need) & alive_mine;
     uint32_t pass[RW], t = 0u;
 #pragma unroll
     for (int w = 0; w < RW; ++w) {
