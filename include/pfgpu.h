@@ -174,6 +174,7 @@ typedef struct pf_stats_t {
                                  pairs and `probes_issued` the row (sector) loads, each answering a probe for a whole tile */
     uint64_t sliced_tiles;    /* tiles of the current tiling */
     uint64_t sliced_table_bytes; /* HBM held by their tables */
+    uint64_t chunk_splits;    /* times a chunk of reads was cut in half because its frontier outgrew the pair index */
 } pf_stats_t;
 int pf_get_stats(pf_db *db, pf_stats_t *out);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can
@@ -206,6 +207,10 @@ int pf_db_set_memo(pf_db *db, int on, uint64_t budget_bytes);
 /* hash_bytes of every k-mer is computed once per batch and cached in HBM (8 B per k-mer); a batch whose
  * cache would exceed `bytes` (default 16 GiB) is processed in several chunks of reads. */
 int pf_db_set_hash_cache_bytes(pf_db *db, uint64_t bytes);
+/* (read, node) pairs are indexed with 32 bits.  A block whose frontier would outgrow that is not refused: the library
+ * works through it in chunks of reads and halves a chunk whose frontier grows past `pairs` (default and maximum
+ * 0xFF000000).  Results do not depend on the value; tests set it low to exercise the splitting. */
+int pf_db_set_frontier_cap(pf_db *db, uint64_t pairs);
 /* Probe steps per node (level order, n_nodes entries) a query with `threshold` uses for a batch whose reads
  * of mean length have `nominal_kmers` k-mers (K = exact, 0 = skipped). */
 int pf_db_node_steps(pf_db *db, float threshold, uint64_t nominal_kmers, uint32_t *steps);

@@ -395,6 +395,13 @@ struct pfo_tree {
     pfo_node **pre;
     uint64_t n_pre;
     int dirty;
+    /* reference-faithful filter cache (pfo_tree_load_lazy): BFLruCache (cache.rs:13-17, 55-88) -- an LRU of `lru_cap`
+     * filters keyed by the node's file name, a miss re-reads and decodes "<db>/<name>.bf" (bloom_filter.rs:153-174) */
+    int lru_cap, lru_n;
+    pfo_filter **lru_filter;
+    const char **lru_key; /* points at the owning node's bf_path */
+    uint64_t *lru_stamp, lru_clock;
+    uint64_t lru_loads, lru_hits, lru_bytes;
 };
 
 static uint64_t splitmix64(uint64_t *s) {
@@ -457,6 +464,10 @@ void pfo_tree_free(pfo_tree *t) {
     }
     free(t->filters);
     free(t->filter_keys);
+    for (int i = 0; i < t->lru_n; i++) pfo_filter_free(t->lru_filter[i]);
+    free(t->lru_filter);
+    free(t->lru_key);
+    free(t->lru_stamp);
     free(t->name_used);
     free(t->directory);
     free(t->leaves);
@@ -647,9 +658,44 @@ static int load_filters(pfo_tree *t, pfo_node *n, const char *dir) {
     if (load_filters(t, n->left, dir)) return -1;
     return load_filters(t, n->right, dir);
 }
-/* BloomTree::load (bloom_tree.rs:364-386); all filters are loaded eagerly (the reference
- * loads lazily through the LRU cache, cache.rs:56-77 -- same bits either way). */
-pfo_tree *pfo_tree_load(const char *dir, int rot) {
+/* get_filter (cache.rs:56-77): hit -> most recently used; miss -> load_from_file, insert, evict the least recently
+ * used.  Called from the (serial) recursion only, like the reference's write-locked cache. */
+static const pfo_filter *lru_get(pfo_tree *t, const pfo_node *n) {
+    t->lru_clock++;
+    for (int i = 0; i < t->lru_n; i++)
+        if (!strcmp(t->lru_key[i], n->bf_path)) {
+            t->lru_stamp[i] = t->lru_clock;
+            t->lru_hits++;
+            return t->lru_filter[i];
+        }
+    char p[4096];
+    join_path(p, sizeof p, t->directory, n->bf_path);
+    pfo_filter *f = pfo_filter_load(p);
+    if (!f) return NULL;
+    t->lru_loads++;
+    t->lru_bytes += (f->m + 63) / 64 * 8;
+    int slot = t->lru_n;
+    if (t->lru_n == t->lru_cap) {
+        slot = 0;
+        for (int i = 1; i < t->lru_n; i++)
+            if (t->lru_stamp[i] < t->lru_stamp[slot]) slot = i;
+        pfo_filter_free(t->lru_filter[slot]);
+    } else {
+        t->lru_n++;
+    }
+    t->lru_filter[slot] = f;
+    t->lru_key[slot] = n->bf_path;
+    t->lru_stamp[slot] = t->lru_clock;
+    return f;
+}
+static const pfo_filter *node_filter(pfo_tree *t, const pfo_node *n) {
+    return t->lru_cap ? lru_get(t, n) : t->filters[n->filter];
+}
+
+/* BloomTree::load (bloom_tree.rs:364-386).  lru_cap == 0: all filters are loaded eagerly and kept (same bits as the
+ * reference's lazy cache, no disk traffic while querying).  lru_cap > 0: reference-faithful -- only tree.bin is read
+ * here and filters come through an LRU of that capacity (`--cache-size`, main.rs:119-122). */
+static pfo_tree *tree_load_impl(const char *dir, int rot, int lru_cap) {
     char p[4096];
     join_path(p, sizeof p, dir, "tree.bin");
     FILE *fp = fopen(p, "rb");
@@ -675,6 +721,23 @@ pfo_tree *pfo_tree_load(const char *dir, int rot) {
         return NULL;
     }
     t->directory = strdup(dir);
+    if (lru_cap > 0) {
+        t->lru_cap = lru_cap;
+        t->lru_filter = (pfo_filter **)calloc((size_t)lru_cap, sizeof *t->lru_filter);
+        t->lru_key = (const char **)calloc((size_t)lru_cap, sizeof *t->lru_key);
+        t->lru_stamp = (uint64_t *)calloc((size_t)lru_cap, sizeof *t->lru_stamp);
+        if (t->root) {
+            const pfo_filter *f = lru_get(t, t->root);
+            if (!f) {
+                pfo_tree_free(t);
+                return NULL;
+            }
+            t->m = f->m;
+            t->K = f->K;
+            t->lru_loads = t->lru_hits = t->lru_bytes = 0;
+        }
+        return t;
+    }
     if (load_filters(t, t->root, dir)) {
         pfo_tree_free(t);
         return NULL;
@@ -684,6 +747,15 @@ pfo_tree *pfo_tree_load(const char *dir, int rot) {
         t->K = t->filters[0]->K;
     }
     return t;
+}
+pfo_tree *pfo_tree_load(const char *dir, int rot) { return tree_load_impl(dir, rot, 0); }
+pfo_tree *pfo_tree_load_lazy(const char *dir, int rot, int cache_size) {
+    return tree_load_impl(dir, rot, cache_size < 1 ? 1 : cache_size);
+}
+void pfo_tree_cache_stats(const pfo_tree *t, uint64_t *loads, uint64_t *hits, uint64_t *bytes) {
+    *loads = t->lru_loads;
+    *hits = t->lru_hits;
+    *bytes = t->lru_bytes;
 }
 /* prune_tree (bloom_tree.rs:302-330): nodes at depth >= search_depth lose their children */
 static void prune_rec(pfo_node *n, uint64_t depth, uint64_t search_depth) {
@@ -912,7 +984,8 @@ static uint64_t subtree_leaves(const pfo_node *n) {
 
 /* _query_batch (query.rs:99-158): pre-order, left then right, on the surviving subset */
 static void query_rec(qctx *c, pfo_node *node, const uint32_t *set, uint64_t n_set) {
-    const pfo_filter *f = c->t->filters[node->filter];
+    const pfo_filter *f = node_filter(c->t, node); /* bf_cache.get_filter(&node.bloom_filter_path), query.rs:107-110 */
+    if (!f) return;                                /* pfo_filter_load has set the error message */
     size_t k = (size_t)c->t->kmer_size;
     int rot = c->t->rot;
     uint8_t *flag = (uint8_t *)malloc(n_set ? n_set : 1);
@@ -1166,6 +1239,14 @@ static int query_impl(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, ui
     }
     uint32_t *all = (uint32_t *)malloc((n_reads ? n_reads : 1) * 4);
     for (uint32_t i = 0; i < n_reads; i++) all[i] = i;
+    if (sched && t->lru_cap) {
+        set_err("the kernel-schedule restatement needs every filter resident (pfo_tree_load, not pfo_tree_load_lazy)");
+        free(all);
+        free(koff);
+        free(kbuf);
+        free(reads);
+        return -1;
+    }
     if (sched) {
         refresh(t);
         {   /* nominal read: mean length of the block, as the kernel's planner */
@@ -1184,6 +1265,39 @@ static int query_impl(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, ui
     free(kbuf);
     free(reads);
     return g_err[0] ? -1 : 0;
+}
+/* The reference's query driver loop (main.rs:334-368): the read set is cut into blocks of `block_size` reads
+ * (`--block-size-reads`, default 100, main.rs:115-118) and query_batch runs once per block, serially; hit read indices
+ * are relative to the whole set.  With a tree from pfo_tree_load_lazy every block re-walks the tree through the LRU. */
+int pfo_query_blocks(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, float threshold,
+                     int threads, int want_hits, uint32_t block_size, pfo_query_result *out) {
+    memset(out, 0, sizeof *out);
+    if (block_size == 0) block_size = 1;
+    uint64_t cap = 0;
+    for (uint32_t b0 = 0; b0 < n_reads; b0 += block_size) {
+        const uint32_t nb = n_reads - b0 < block_size ? n_reads - b0 : block_size;
+        pfo_query_result r;
+        if (query_impl(t, seqs, offs + b0, nb, threshold, threads, want_hits, 0, 0, 1, &r)) {
+            pfo_query_result_free(&r);
+            return -1;
+        }
+        if (r.n_hits) {
+            if (out->n_hits + r.n_hits > cap) {
+                cap = (out->n_hits + r.n_hits) * 2;
+                out->hit_read = (uint32_t *)realloc(out->hit_read, cap * 4);
+                out->hit_leaf = (uint32_t *)realloc(out->hit_leaf, cap * 4);
+            }
+            for (uint64_t i = 0; i < r.n_hits; i++) {
+                out->hit_read[out->n_hits + i] = r.hit_read[i] + b0;
+                out->hit_leaf[out->n_hits + i] = r.hit_leaf[i];
+            }
+            out->n_hits += r.n_hits;
+        }
+        out->pairs += r.pairs;
+        out->probes_ref += r.probes_ref;
+        pfo_query_result_free(&r);
+    }
+    return 0;
 }
 void pfo_query_result_free(pfo_query_result *r) {
     free(r->hit_read);

@@ -122,6 +122,13 @@ typedef struct pfo_query_result {
 int pfo_query_batch(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads,
                     float threshold, int threads, int want_hits, pfo_query_result *out);
 void pfo_query_result_free(pfo_query_result *r);
+/* The reference's driver loop around query_batch (main.rs:334-368): blocks of `block_size` reads, serially. */
+int pfo_query_blocks(pfo_tree *t, const uint8_t *seqs, const uint64_t *offs, uint32_t n_reads, float threshold,
+                     int threads, int want_hits, uint32_t block_size, pfo_query_result *out);
+/* Reference-faithful filter store: only tree.bin is read; filters come through an LRU of `cache_size` entries and a
+ * miss re-reads "<db>/<name>.bf" from disk (BFLruCache, cache.rs:55-88; --cache-size, main.rs:119-122).  Query only. */
+pfo_tree *pfo_tree_load_lazy(const char *dir, int rot, int cache_size);
+void pfo_tree_cache_stats(const pfo_tree *t, uint64_t *loads, uint64_t *hits, uint64_t *bytes);
 /* Restatement of the GPU kernel's schedule (NOT of the reference): same decisions, different amount of
  * work.  lazy=1: verified-monotone interior nodes get the step-limited pre-test (see pfo_node_steps);
  * lazy=0: every node exact with read-level early exit.  Fills hits, pairs and probes_sched; leaf counters

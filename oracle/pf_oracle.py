@@ -105,6 +105,11 @@ def lib():
     L.pfo_query_batch.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, C.c_float, C.c_int, C.c_int,
                                   C.POINTER(_QueryResult)]
     L.pfo_query_result_free.argtypes = [C.POINTER(_QueryResult)]
+    L.pfo_query_blocks.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, C.c_float, C.c_int, C.c_int, C.c_uint32,
+                                   C.POINTER(_QueryResult)]
+    L.pfo_tree_load_lazy.restype = C.c_void_p
+    L.pfo_tree_load_lazy.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.pfo_tree_cache_stats.argtypes = [C.c_void_p, u64p, u64p, u64p]
     L.pfo_query_batch_sched.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, C.c_float, C.c_int, C.c_int,
                                         C.c_int, C.c_uint32, C.POINTER(_QueryResult)]
     L.pfo_need.restype = C.c_uint64
@@ -259,6 +264,41 @@ class Tree:
         if not p:
             raise RuntimeError(lib().pfo_last_error().decode())
         return cls(0, _ptr=p)
+
+    @classmethod
+    def load_lazy(cls, directory: str, cache_size: int = 10, rot: int = DEFAULT_ROT) -> "Tree":
+        """Reference-faithful filter store: only tree.bin is read, filters come through an LRU of `cache_size` entries
+        and every miss re-reads the .bf file (BFLruCache, cache.rs:55-88; --cache-size default 10, main.rs:119-122)."""
+        p = lib().pfo_tree_load_lazy(directory.encode(), rot, cache_size)
+        if not p:
+            raise RuntimeError(lib().pfo_last_error().decode())
+        return cls(0, _ptr=p)
+
+    def cache_stats(self) -> Tuple[int, int, int]:
+        """(filter files loaded, cache hits, filter bytes decoded) of a load_lazy tree."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib().pfo_tree_cache_stats(self._p, C.byref(a), C.byref(b), C.byref(c))
+        return int(a.value), int(b.value), int(c.value)
+
+    def query_blocks(self, reads: Sequence[bytes], threshold: float, block_size: int = 100, threads: int = 0,
+                     want_hits: bool = True, concat: Tuple[bytes, np.ndarray] | None = None) -> QueryResult:
+        """The reference's driver loop (main.rs:334-368): query_batch once per block of `block_size` reads
+        (--block-size-reads, default 100); hit read indices are relative to the whole set."""
+        seqs, offs = concat if concat is not None else concat_reads(reads)
+        n = len(offs) - 1
+        res = _QueryResult()
+        rc = lib().pfo_query_blocks(self._p, seqs, offs.ctypes.data_as(C.POINTER(C.c_uint64)), n, C.c_float(threshold),
+                                    threads, int(want_hits), block_size, C.byref(res))
+        if rc:
+            raise RuntimeError(lib().pfo_last_error().decode())
+        nh = int(res.n_hits)
+        hits = np.zeros((nh, 2), dtype=np.uint32)
+        if nh:
+            hits[:, 0] = np.ctypeslib.as_array(res.hit_read, shape=(nh,))
+            hits[:, 1] = np.ctypeslib.as_array(res.hit_leaf, shape=(nh,))
+        out = QueryResult(hits, int(res.pairs), int(res.probes_ref), int(res.probes_sched))
+        lib().pfo_query_result_free(C.byref(res))
+        return out
 
     def insert(self, genome_id: str, seq: bytes) -> None:
         lib().pfo_tree_insert(self._p, genome_id.encode(), seq, len(seq))

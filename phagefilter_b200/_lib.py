@@ -57,6 +57,7 @@ class Stats(C.Structure):
         ("probe_kernel_ms", C.c_double), ("device_ms", C.c_double), ("group_rounds", C.c_uint64),
         ("memo_hits", C.c_uint64), ("memo_lookups", C.c_uint64),
         ("sliced_blocks", C.c_uint64), ("sliced_tiles", C.c_uint64), ("sliced_table_bytes", C.c_uint64),
+        ("chunk_splits", C.c_uint64),
     ]
 
 
@@ -104,6 +105,7 @@ SYMBOLS = {
     "pf_db_set_exhaustive": (C.c_int, [_VP, C.c_int]),
     "pf_db_set_lazy": (C.c_int, [_VP, C.c_int]),
     "pf_db_set_mode": (C.c_int, [_VP, C.c_int]),
+    "pf_db_set_frontier_cap": (C.c_int, [_VP, C.c_uint64]),
     "pf_db_set_memo": (C.c_int, [_VP, C.c_int, C.c_uint64]),
     "pf_db_set_hash_cache_bytes": (C.c_int, [_VP, C.c_uint64]),
     "pf_db_node_steps": (C.c_int, [_VP, C.c_float, C.c_uint64, C.POINTER(C.c_uint32)]),

@@ -111,6 +111,10 @@ class BloomTree:
         2 = bit-sliced tiles.  Results are identical in every mode."""
         _lib.check(_lib.lib().pf_db_set_mode(self._h, int(mode)))
 
+    def set_frontier_cap(self, pairs: int) -> None:
+        """pf_db_set_frontier_cap: chunks of reads whose frontier outgrows this many pairs are cut in half and redone."""
+        _lib.check(_lib.lib().pf_db_set_frontier_cap(self._h, pairs))
+
     def set_lazy(self, on: bool) -> None:
         _lib.check(_lib.lib().pf_db_set_lazy(self._h, int(on)))
 

@@ -100,6 +100,8 @@ struct SlicedState;
 }
 using namespace pf;  // internal header: the handle types below live at global scope (C ABI)
 
+constexpr int PF_SPLIT_CHUNK = -100;  // internal: the chunk's frontier outgrew frontier_cap, retry with fewer reads
+
 struct pf_dev_batch {
     uint32_t n_reads = 0, n_exc = 0;
     uint64_t n_words = 0, exc_nbytes = 0;
@@ -202,7 +204,10 @@ struct pf_db {
     int32_t *d_leaf = nullptr;
     uint64_t *d_filters = nullptr;
     // accumulators and per-block scratch
-    unsigned long long *d_counts = nullptr, *d_blk_counts = nullptr;
+    unsigned long long *d_counts = nullptr, *d_blk_counts = nullptr, *d_blk_snapshot = nullptr;
+    // largest frontier (pairs) one chunk of reads may produce; 32-bit pair indices and ticket counters that every
+    // persistent warp bumps once more after the last pair (~2e5 x 32) leave this much room
+    uint64_t frontier_cap = 0xFF000000ULL;
     uint32_t *d_node_pass = nullptr, *d_cursor = nullptr;  // contiguous [2 * n_nodes], then:
     uint32_t *d_node_pass_copies = nullptr;                // [NODE_PASS_COPIES * n_nodes] counters the probe kernel adds to
     unsigned long long *d_next_base = nullptr, *d_hit_base = nullptr;
@@ -280,6 +285,7 @@ void account_stats(pf_db *db, const Descent &st, uint64_t n_reads, uint64_t d2h)
 void sliced_free(pf_db *db);
 int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sliced);
 int sliced_begin_block(pf_db *db);
+int sliced_set_hit_cursor(pf_db *db, uint64_t hits);
 uint64_t sliced_entry_tiles(const pf_db *db);
 int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint64_t kmer_base, uint32_t r0,
                uint32_t n_chunk, Descent &st);

@@ -526,7 +526,7 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
                 }
                 if (!my_decided && my_nk) my_r0 = min(32u, my_ns) | (stride << 8);
                 my_k0 = mine.koff - a.kmer_base;
-                my_off = off | (my_nk << 8);  // first sampled k-mer (< 8) | n_k << 8
+                my_off = off;  // first sampled k-mer (< 8); n_k travels in its own word (reads may have >= 2^24 k-mers)
             }
             uint32_t idxv[PROBE_CHUNK], wv[PROBE_CHUNK];
 #pragma unroll
@@ -534,8 +534,9 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
                 const uint32_t r0 = __shfl_sync(0xFFFFFFFFu, my_r0, sb + p);
                 const uint64_t k0 = __shfl_sync(0xFFFFFFFFu, my_k0, sb + p);
                 const uint32_t o4 = __shfl_sync(0xFFFFFFFFu, my_off, sb + p);
+                const uint32_t nk4 = __shfl_sync(0xFFFFFFFFu, my_nk, sb + p);
                 idxv[p] = 0xFFFFFFFFu;
-                if (lane < (r0 & 0xFFu)) idxv[p] = ldg32(a.idx0 + k0 + idx0_slot((o4 & 0xFFu) + lane * (r0 >> 8), o4 >> 8));
+                if (lane < (r0 & 0xFFu)) idxv[p] = ldg32(a.idx0 + k0 + idx0_slot(o4 + lane * (r0 >> 8), nk4));
             }
 #pragma unroll
             for (int p = 0; p < PROBE_CHUNK; ++p) {

@@ -86,6 +86,7 @@ void pf::db_free(pf_db *db) {
     cudaFree(db->d_entry);
     cudaFree(db->d_counts);
     cudaFree(db->d_blk_counts);
+    cudaFree(db->d_blk_snapshot);
     cudaFree(db->d_node_pass);
     cudaFree(db->d_next_base);
     cudaFree(db->d_hit_base);
@@ -339,6 +340,7 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     size_t nn = db->n_nodes, nl = std::max<uint64_t>(db->n_leaves, 1), nlev = db->level_start.size();
     PF_CUDA_OK(cudaMalloc(&db->d_counts, nl * 8));
     PF_CUDA_OK(cudaMalloc(&db->d_blk_counts, nl * 8));
+    PF_CUDA_OK(cudaMalloc(&db->d_blk_snapshot, nl * 8));
     // [node totals | cursors | NODE_PASS_COPIES x per-node counters], zeroed together per chunk of reads
     PF_CUDA_OK(cudaMalloc(&db->d_node_pass, (2 + NODE_PASS_COPIES) * nn * 4));
     db->d_cursor = db->d_node_pass + nn;
@@ -736,11 +738,7 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         const uint32_t e0 = db->entry_start[l], n_entry = db->entry_start[l + 1] - e0;
         if (n_entry && inj_n) {
             const uint64_t add = (uint64_t)inj_n * n_entry;
-            if (n + add > 0xFFFFFFF0ULL) {
-                set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
-                          (unsigned long long)(n + add));
-                return PF_ERR_NOMEM;
-            }
+            if (n + add > db->frontier_cap) return PF_SPLIT_CHUNK;  // query_impl retries with fewer reads
             if ((rc = db->fr_read[cur].grow_keep(n + add, n, s)) || (rc = db->fr_node[cur].grow_keep(n + add, n, s)))
                 return rc;
             inject_frontier_kernel<<<(uint32_t)std::min<uint64_t>((add + 255) / 256, 8192), 256, 0, s>>>(
@@ -812,11 +810,7 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         st.probes = db->h_totals->probes;
         st.memo_hits = db->h_totals->memo_hits;
         st.memo_lookups = db->h_totals->memo_lookups;
-        if (next_n > 0xFFFFFFF0ULL) {
-            set_error("frontier of %llu pairs exceeds the 32-bit pair index: use smaller read blocks",
-                      (unsigned long long)next_n);
-            return PF_ERR_NOMEM;
-        }
+        if (next_n > db->frontier_cap) return PF_SPLIT_CHUNK;
         const int nxt = cur ^ 1;
         if (next_n && ((rc = db->fr_read[nxt].ensure(next_n)) || (rc = db->fr_node[nxt].ensure(next_n)))) return rc;
         // hits of earlier levels and chunks live in the same arrays: grow with copy
@@ -908,6 +902,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     const uint64_t budget_kmers = std::max<uint64_t>(db->hash_cache_bytes / 12, 1);  // 8 B hash + 4 B index
     const std::vector<uint64_t> &ko = bt->h_kmer_off;
     const bool one_chunk = ko.empty();  // prefix sum lives on the device only; the whole batch fits the cache
+    uint32_t max_chunk_reads = 0xFFFFFFFFu;
     for (uint32_t r0 = 0; r0 < n_reads;) {
         // chunk [r0, r1): as many reads as the hash cache holds (always at least one)
         uint32_t r1 = n_reads;
@@ -917,12 +912,19 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
             if (r1 <= r0) r1 = r0 + 1;
         }
         if (sliced) {  // (read, entry tile) pairs of a chunk are indexed with 32 bits
-            const uint64_t cap = std::max<uint64_t>(1, 0xF0000000ULL / std::max<uint64_t>(sliced_entry_tiles(db), 1));
+            const uint64_t cap = std::max<uint64_t>(1, db->frontier_cap / std::max<uint64_t>(sliced_entry_tiles(db), 1));
             if (r1 - r0 > cap) r1 = r0 + (uint32_t)cap;
         }
+        if (r1 - r0 > max_chunk_reads) r1 = r0 + max_chunk_reads;  // an earlier attempt overflowed the frontier
         const uint32_t n_chunk = r1 - r0;
+        // with the prefix sum on the device only, a cut chunk still uses the whole batch's k-mer index space
         const uint64_t chunk_kmers = one_chunk ? bt->total_bases_bound : ko[r1] - ko[r0];
         const uint64_t kmer_base = one_chunk ? 0 : ko[r0];
+        // A frontier that outgrows the 32-bit pair index makes the chunk start over with half the reads; the chunk's
+        // side effects so far (leaf histogram, hit list, per-read hit counts) are undone first.
+        const uint64_t hits_at_chunk = st.hits_total;
+        PF_CUDA_OK(cudaMemcpyAsync(db->d_blk_snapshot, db->d_blk_counts, std::max<uint64_t>(db->n_leaves, 1) * 8,
+                                   cudaMemcpyDeviceToDevice, s));
         if ((rc = db->hb.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
         if (db->hp.small_m && !sliced && (rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
         PF_CUDA_OK(cudaMemsetAsync(db->d_node_pass, 0, (2 + NODE_PASS_COPIES) * db->n_nodes * 4, s));
@@ -952,6 +954,23 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         st.cur = 0;
         if (sliced) rc = run_sliced(db, bt, threshold, want_hits, kmer_base, r0, n_chunk, st);
         else rc = run_levels(db, bt, threshold, want_hits, G, kmer_base, 0, n_levels, r0, n_chunk, st);
+        if (rc == PF_SPLIT_CHUNK) {
+            if (n_chunk <= 1) {
+                set_error("one read alone produces a frontier beyond the 32-bit pair index");
+                return PF_ERR_NOMEM;
+            }
+            max_chunk_reads = n_chunk / 2;
+            PF_CUDA_OK(cudaMemcpyAsync(db->d_blk_counts, db->d_blk_snapshot, std::max<uint64_t>(db->n_leaves, 1) * 8,
+                                       cudaMemcpyDeviceToDevice, s));
+            if (want_hits) PF_CUDA_OK(cudaMemsetAsync(db->read_hits.p + r0, 0, (size_t)n_chunk * 4, s));
+            st.hits_total = st.hits_before = hits_at_chunk;
+            unsigned long long h64 = hits_at_chunk;
+            PF_CUDA_OK(cudaMemcpyAsync(&db->d_totals->hits_total, &h64, 8, cudaMemcpyHostToDevice, s));
+            if (sliced && (rc = sliced_set_hit_cursor(db, hits_at_chunk))) return rc;
+            PF_CUDA_OK(cudaStreamSynchronize(s));
+            db->stats.chunk_splits++;
+            continue;
+        }
         if (rc) return rc;
         r0 = r1;
     }
@@ -986,6 +1005,10 @@ int pf::batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b, c
     }
     if (in->n_exc && (!in->exc_index || !in->exc_off || !in->exc_bytes)) {
         set_error("pf_read_batch: exception arrays missing");
+        return PF_ERR_ARG;
+    }
+    if (in->n_reads > 0xFF000000u) {
+        set_error("pf_read_batch: at most 0xFF000000 reads per batch (32-bit work tickets)");
         return PF_ERR_ARG;
     }
     PF_CUDA_OK(cudaSetDevice(db->device));
@@ -1152,6 +1175,14 @@ int pf_db_set_memo(pf_db *db, int on, uint64_t budget_bytes) {
 int pf_db_set_lazy(pf_db *db, int on) {
     if (!db) return PF_ERR_ARG;
     db->lazy = on ? 1 : 0;
+    return PF_OK;
+}
+int pf_db_set_frontier_cap(pf_db *db, uint64_t pairs) {
+    if (!db || pairs < 1 || pairs > 0xFF000000ULL) {
+        set_error("pf_db_set_frontier_cap: 1 .. 0xFF000000 pairs");
+        return PF_ERR_ARG;
+    }
+    db->frontier_cap = pairs;
     return PF_OK;
 }
 int pf_db_set_mode(pf_db *db, int mode) {

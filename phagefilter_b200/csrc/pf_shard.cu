@@ -52,6 +52,16 @@ __global__ void add_u64_kernel(uint64_t *a, uint32_t n, uint64_t base) {
 }
 __global__ void set_u64_kernel(uint64_t *p, uint64_t v) { *p = v; }
 
+// the sharded descent does not cut chunks: a frontier beyond the pair index is the caller's to split
+static int shard_rc(int rc) {
+    if (rc == PF_SPLIT_CHUNK) {
+        pf::set_error("frontier exceeds the 32-bit pair index: use smaller read blocks with a sharded tree");
+        return PF_ERR_NOMEM;
+    }
+    return rc;
+}
+
+
 // The frontier at the cut level is sorted by node; rank d owns the nodes [cut_lo[d], cut_lo[d+1]).
 // out[d] = number of pairs going to rank d; out[nranks + 1 + d] = first pair of that slice.
 __global__ void frontier_bounds_kernel(const uint32_t *__restrict__ fr_node, uint32_t n, const uint32_t *__restrict__ cut_lo,
@@ -454,7 +464,7 @@ static int query_sharded_impl(pf_db *db, const pf_dev_batch *local, float thresh
 
     // ---- phase A: the replicated top, this rank's reads ---------------------------------------------------
     if ((rc = hash_range(db, g, r_me, n_me, nullptr, st))) return rc;
-    if ((rc = run_levels(db, &g, threshold, want_hits ? 1 : 0, G, 0, 0, Lc, r_me, n_me, st))) return rc;
+    if ((rc = run_levels(db, &g, threshold, want_hits ? 1 : 0, G, 0, 0, Lc, r_me, n_me, st))) return shard_rc(rc);
     const uint64_t hits_a = st.hits_total, pairs_a = st.pairs;
     if (Lc >= n_levels) st.n = 0;  // nothing below the cut
 
@@ -504,7 +514,7 @@ static int query_sharded_impl(pf_db *db, const pf_dev_batch *local, float thresh
             st.other_launches++;
             if ((rc = hash_range(db, g, 0, nT, S->need_hash.p, st))) return rc;
         }
-        if ((rc = run_levels(db, &g, threshold, want_hits ? 2 : 0, G, 0, Lc, n_levels, 0, nT, st))) return rc;
+        if ((rc = run_levels(db, &g, threshold, want_hits ? 2 : 0, G, 0, Lc, n_levels, 0, nT, st))) return shard_rc(rc);
     }
     add_counts_kernel<<<(uint32_t)((db->n_leaves + 255) / 256), 256, 0, s>>>(db->d_counts, db->d_blk_counts, (uint32_t)db->n_leaves);
     st.other_launches++;

@@ -571,10 +571,7 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
     const size_t nt = S.tiles.size();
     int rc;
     uint64_t n = (uint64_t)n_chunk * S.entry_tiles.size();
-    if (n > 0xFFFFFF00ULL) {
-        set_error("sliced frontier of %llu pairs exceeds the 32-bit pair index", (unsigned long long)n);
-        return PF_ERR_NOMEM;
-    }
+    if (n > db->frontier_cap) return PF_SPLIT_CHUNK;
     int cur = 0;
     bool entry = true;
     const int grid = db->sm_count * 2;
@@ -632,10 +629,7 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
             S.h_tile_base[t] = next_n;
             next_n += S.h_tile_count[t];
         }
-        if (next_n > 0xFFFFFF00ULL) {
-            set_error("sliced frontier of %llu pairs exceeds the 32-bit pair index", (unsigned long long)next_n);
-            return PF_ERR_NOMEM;
-        }
+        if (next_n > db->frontier_cap) return PF_SPLIT_CHUNK;
         const int nxt = cur ^ 1;
         if (n_alive) {
             if (next_n && ((rc = S.fr_read[nxt].ensure(next_n)) || (rc = S.fr_tile[nxt].ensure(next_n)) ||
@@ -686,6 +680,13 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
 int sliced_begin_block(pf_db *db) {
     SlicedState &S = *db->sliced;
     PF_CUDA_OK(cudaMemsetAsync(S.d_hit_cursor, 0, 8, db->stream));
+    return PF_OK;
+}
+int sliced_set_hit_cursor(pf_db *db, uint64_t hits) {  // a chunk starts over (query_impl)
+    SlicedState &S = *db->sliced;
+    S.h_counters[3] = hits;
+    PF_CUDA_OK(cudaMemcpyAsync(S.d_hit_cursor, S.h_counters + 3, 8, cudaMemcpyHostToDevice, db->stream));
+    PF_CUDA_OK(cudaStreamSynchronize(db->stream));
     return PF_OK;
 }
 

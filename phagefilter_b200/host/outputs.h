@@ -95,10 +95,21 @@ class FilterWriter {
                     o.append(r.id, r.id_len);
                     if (mapped) {  // get_ext_id, result_map.rs:24-37
                         o.append(" |");
+                        // ResultMap holds a HashSet<String> of genome ids (result_map.rs:10): two leaves with the same
+                        // tax_id (a FASTA id built or added twice) are listed once
                         bool first = true;
+                        const size_t ids_at = o.size();
                         for (uint32_t l : it->second) {
+                            const std::string &gid = (*leaf_ids_)[l];
+                            bool seen = false;
+                            for (size_t p = ids_at; !seen && p < o.size();) {
+                                const size_t e = std::min(o.find(',', p), o.size());
+                                seen = o.compare(p, e - p, gid) == 0;
+                                p = e + 1;
+                            }
+                            if (seen) continue;
                             if (!first) o.push_back(',');
-                            o.append((*leaf_ids_)[l]);
+                            o.append(gid);
                             first = false;
                         }
                     }

@@ -444,6 +444,16 @@ int cmd_parse(const Args &a) {
 }  // namespace
 
 int main(int argc, char **argv) {
+    // clap-verbosity-flag is a global argument of the reference (main.rs:38-44): `phage_filter -vv query ...` is valid
+    auto is_verbosity = [](const std::string &t) {
+        if (t == "--verbose" || t == "--quiet") return true;
+        if (t.size() < 2 || t[0] != '-' || t[1] == '-') return false;
+        return t.find_first_not_of(t[1] == 'v' ? 'v' : 'q', 1) == std::string::npos && (t[1] == 'v' || t[1] == 'q');
+    };
+    while (argc >= 2 && is_verbosity(argv[1])) {
+        ++argv;
+        --argc;
+    }
     if (argc < 2) die("usage: phage_filter <build|add|query> [options]");
     const std::string cmd = argv[1];
     if (cmd == "build")

@@ -67,3 +67,40 @@ def reads_to_concat(reads: np.ndarray) -> Tuple[bytes, np.ndarray]:
     n, L = reads.shape
     offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
     return reads.tobytes(), offs
+
+
+def simulate_reads_fast(genomes: List[Tuple[str, bytes]], n_reads: int, read_len: int, seed: int,
+                        error_rates: Tuple[float, ...] = (0.0, 0.01), background_frac: float = 0.0,
+                        chunk: int = 250_000) -> Tuple[np.ndarray, np.ndarray]:
+    """Same model and return values as simulate_reads, drawn in a cheaper order (a different random stream): which reads
+    are background is decided first, background reads are filled directly with uniform bases, and only the reads that
+    come from a genome pay for the gather and the substitution mask.  For large spike-in workloads (BASELINE configs
+    3-5: 90 % background) this is about 5x faster."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cat = np.frombuffer(b"".join(g for _, g in genomes), dtype=np.uint8)
+    lens = np.array([len(g) for _, g in genomes], dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    ok = np.nonzero(lens >= read_len)[0]
+    reads = np.empty((n_reads, read_len), dtype=np.uint8)
+    src = np.full(n_reads, -1, dtype=np.int64)
+    rates = np.array(error_rates, dtype=np.float64)
+    ar = np.arange(read_len, dtype=np.int64)
+    for lo in range(0, n_reads, chunk):
+        hi = min(lo + chunk, n_reads)
+        n = hi - lo
+        bg = rng.random(n) < background_frac
+        blk = reads[lo:hi]
+        n_bg = int(bg.sum())
+        if n_bg:
+            blk[bg] = _ACGT[rng.integers(0, 4, size=(n_bg, read_len), dtype=np.uint8)]
+        fg = np.nonzero(~bg)[0]
+        if len(fg):
+            gi = ok[rng.integers(0, len(ok), size=len(fg))]
+            st = (rng.random(len(fg)) * (lens[gi] - read_len + 1)).astype(np.int64)
+            sub = cat[(starts[gi] + st)[:, None] + ar[None, :]].copy()
+            er = rates[(lo + fg) % len(rates)]
+            mask = rng.random((len(fg), read_len)) < er[:, None]
+            sub[mask] = _ACGT[rng.integers(0, 4, size=int(mask.sum()), dtype=np.uint8)]
+            blk[fg] = sub
+            src[lo + fg] = gi
+    return reads, src

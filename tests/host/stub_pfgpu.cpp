@@ -4,6 +4,7 @@
 // real query path.  Hits are fabricated by the rule of tests/host/filter_writer_harness.cpp (global read index g: g % 4 == 0
 // -> no hit, else g % 3 hits at leaves (7g + 5j) % 9).  The packer entry points are NOT stubbed: they come from libpfgpu.so.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <string>
@@ -24,6 +25,7 @@ const char *pf_last_error(void) { return "stub"; }
 int pf_db_open(const char *db_path, int, int64_t, pf_db **out) {
     if (!db_path || !*db_path || std::string(db_path).find("missing") != std::string::npos) return PF_ERR_IO;
     for (uint32_t l = 0; l < kLeaves; ++l) g_names[l] = "genome_" + std::to_string(l);
+    if (getenv("PF_STUB_DUP_NAMES")) g_names[1] = g_names[5];  // two leaves with one tax_id (a FASTA id added twice)
     *out = reinterpret_cast<pf_db *>(&g_read);
     return PF_OK;
 }

@@ -163,3 +163,30 @@ def test_build_and_add_driver(stub, tmp_path):
     assert p.returncode == 101 and b"BloomTree::load" in p.stderr
     p = subprocess.run([BIN, "build", "-g", str(d)], capture_output=True, env=e, timeout=120)
     assert p.returncode == 101 and b"required arguments" in p.stderr
+
+
+def test_global_verbosity_flags_and_duplicate_genome_ids(stub, tmp_path):
+    """clap-verbosity-flag is global in the reference (`phage_filter -vv query ...`, main.rs:38-44), and ResultMap keeps a
+    HashSet<String> of genome ids (result_map.rs:10), so two leaves that carry the same tax_id are listed once."""
+    rng = np.random.default_rng(5)
+    recs = [(f"r{i}", b"ACGT" * 10, None) for i in range(400)]
+    reads = tmp_path / "reads.fa"
+    write_records(reads, recs, False)
+    out = tmp_path / "out"
+    e = dict(os.environ, LD_PRELOAD=stub, PF_STUB_DUP_NAMES="1")
+    p = subprocess.run([BIN, "-vv", "query", "-r", str(reads), "-o", str(out), "-d", str(tmp_path), "--pos-filter"],
+                       capture_output=True, env=e, timeout=120)
+    assert p.returncode == 0, p.stderr.decode()
+    heads = [ln for ln in (out / "POS_FILTERING.fa").read_text().splitlines() if ln.startswith(">")]
+    assert heads
+    both = 0
+    for h in heads:
+        rid, ids = h[1:].split(" |")
+        g = int(rid[1:])
+        want = {("genome_5" if l == 1 else f"genome_{l}") for l in {(g * 7 + j * 5) % 9 for j in range(g % 3)}}
+        got = ids.split(",")
+        assert len(got) == len(set(got)) and set(got) == want, h
+        both += {(g * 7 + j * 5) % 9 for j in range(g % 3)} >= {1, 5}
+    assert both > 0  # the case really occurred
+    q = subprocess.run([BIN, "-q", "--version"], capture_output=True, env=e, timeout=60)
+    assert q.returncode == 0 and b"PhageFilter" in q.stdout

@@ -347,3 +347,30 @@ def test_kmer_memo_deep_coverage(oracle, tmp_path):
             assert st.memo_hits > 0.05 * 131 * len(want.hits)
             assert st.probes_issued < 0.9 * sched.probes_sched
     gt.close()
+
+
+def test_frontier_cap_splits_chunks(oracle, tmp_path):
+    """A block whose (read, node) frontier outgrows the pair index is worked through in smaller chunks of reads instead of
+    being refused (round-1 behaviour: PF_ERR_NOMEM).  Forced here with a tiny cap; results must not change."""
+    from phagefilter_b200.query import get_leaf_counts
+    rng = np.random.default_rng(31)
+    genomes = random_genomes(rng, 24, 1500, 2500)
+    d = str(tmp_path / "db")
+    ot = oracle_build_db(oracle, genomes, 20, d, largest=3000)
+    reads = sample_reads(rng, genomes, 3000, 120, 0.01) + [b"ACGTACGTAC", b""]
+    gt = _open(d)
+    for theta in (1.0, 0.6):
+        ot.reset_counts()
+        want = ot.query_batch(reads, theta)
+        for mode in (1, 2):
+            gt.set_mode(mode)
+            gt.set_frontier_cap(0xFF000000)
+            gt.reset_counts()
+            assert gpu_query(gt, reads, theta) == want.hit_sets(len(reads))
+            gt.set_frontier_cap(1500)  # fewer pairs than reads: the block must be cut several times
+            gt.reset_counts()
+            gt.reset_stats()
+            assert gpu_query(gt, reads, theta) == want.hit_sets(len(reads)), (theta, mode)
+            assert get_leaf_counts(gt) == ot.leaf_counts(), (theta, mode)
+            assert gt.stats().chunk_splits >= 1, (theta, mode)
+    gt.close()

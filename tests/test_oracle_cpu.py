@@ -230,3 +230,29 @@ def test_probe_counts_consistent(oracle):
         assert exact.hit_sets(len(reads)) == want and lazy.hit_sets(len(reads)) == want
         assert exact.pairs == r.pairs and lazy.pairs > 0  # the plan may skip saturated top nodes entirely
         assert 0 < exact.probes_sched <= r.probes_ref and 0 < lazy.probes_sched
+
+
+def test_reference_faithful_lru_mode_equals_resident_mode(oracle, tmp_path):
+    """BFLruCache (cache.rs:55-88) + the block loop of main.rs:334-368: filters re-read from disk through an LRU of
+    --cache-size entries, query_batch per --block-size-reads block.  Same hits, counters and work as one resident pass."""
+    from tests.util import oracle_build_db, random_genomes, sample_reads
+    rng = np.random.default_rng(5)
+    genomes = random_genomes(rng, 14, 1200, 2500)
+    d = str(tmp_path / "db")
+    oracle_build_db(oracle, genomes, 20, d, largest=3000)
+    reads = sample_reads(rng, genomes, 350, 100, 0.01) + [b"ACGT", b"N" * 40]
+    full = oracle.Tree.load(d)
+    want = full.query_batch(reads, 0.8)
+    for cache, block in ((1, 100), (3, 7), (10, 100), (64, 1000)):
+        lazy = oracle.Tree.load_lazy(d, cache_size=cache)
+        got = lazy.query_blocks(reads, 0.8, block_size=block, threads=4)
+        assert sorted(map(tuple, got.hits.tolist())) == sorted(map(tuple, want.hits.tolist()))
+        assert lazy.leaf_counts() == full.leaf_counts()
+        assert got.probes_ref == want.probes_ref
+        loads, hits, nbytes = lazy.cache_stats()
+        n_blocks = -(-len(reads) // block)
+        assert loads >= 1 and nbytes == loads * ((full.num_bits + 63) // 64 * 8)
+        if cache == 1:
+            assert loads >= n_blocks  # a one-entry cache reloads at least the root's sibling chain every block
+        with pytest.raises(RuntimeError):
+            lazy.query_sched(reads, 0.8)
