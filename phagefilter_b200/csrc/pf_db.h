@@ -242,6 +242,10 @@ struct pf_db {
     // ---- bit-sliced tiles (pf_sliced.cu): 0 = choose per (threshold, read length) by cost model, 1 = node-at-a-time
     // descent only, 2 = sliced tiles only
     int mode = 0;
+    // L2 residency (access-policy window on the stream): bytes of L2 set aside for persisting lines, largest window, and
+    // per level the range of filter slots its nodes use
+    uint64_t l2_persist_bytes = 0, l2_window_max = 0;
+    std::vector<uint32_t> level_slot_lo, level_slot_hi;
     double plan_cost = 0.0;            // expected bit probes PER K-MER of a read unrelated to the database under the current step plan
     pf::SlicedState *sliced = nullptr;
     std::vector<uint8_t> nccl_id;      // ncclUniqueId handed to pf_db_open_sharded (the analysis at open is collective)

@@ -27,6 +27,10 @@ constexpr int PROBE_GRAB = 32;   // most pairs fetched per warp per work-counter
 constexpr int HASH_THREADS = 256;
 
 PF_D uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
+// Streamed once per level (frontier, cached hash values and step-0 indices, pass flags): evict-first loads / stores
+// (ld.global.cs / st.global.cs) so that they do not displace the filters being probed from L2.
+PF_D uint32_t lds32(const uint32_t *p) { return __ldcs(p); }
+PF_D uint64_t lds64(const uint64_t *p) { return __ldcs(reinterpret_cast<const unsigned long long *>(p)); }
 
 // number of k-mers of a read (file_parser.rs:136-139)
 PF_HD uint32_t kmers_of(uint32_t len, uint32_t k) { return (k == 0u || k > len) ? 0u : len - k + 1u; }
@@ -101,8 +105,8 @@ static __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashArg
                     const uint64_t x = (lo >> sh) | ((hi << 1) << (63u - sh));
                     const uint64_t hb = canonical_hash_2bit<(KM ? KM : 17)>(x);
                     if (base + lane < n_k) {
-                        out[base + lane] = hb;
-                        if (out0) out0[idx0_slot(base + lane, n_k)] = mod_small(fx_finish(a.hp.c1, hb, a.hp.rot), M0, M1, m32);
+                        __stcs(reinterpret_cast<unsigned long long *>(out + base + lane), (unsigned long long)hb);
+                        if (out0) __stcs(out0 + idx0_slot(base + lane, n_k), mod_small(fx_finish(a.hp.c1, hb, a.hp.rot), M0, M1, m32));
                     }
                     lo = hi;
                 }
@@ -257,11 +261,11 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
         uint32_t idx[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) idx[j] = 0;
-        if (pre < 0 && (st.alive & 1u)) idx[0] = ldg32(i0p + idx0_slot(kidx, nk_full));
+        if (pre < 0 && (st.alive & 1u)) idx[0] = lds32(i0p + idx0_slot(kidx, nk_full));
         if (n_steps > 1u) {
 #pragma unroll
             for (int j = 0; j < G; ++j)
-                if ((st.alive >> j) & 1u) hb[j] = __ldg(hbp + kidx + (uint32_t)j * kstep);
+                if ((st.alive >> j) & 1u) hb[j] = lds64(hbp + kidx + (uint32_t)j * kstep);
         }
         // step 0, first round
         probes += min(32u, cnt);
@@ -279,7 +283,7 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
         if (G > 1 && cnt > 32u) {
 #pragma unroll
             for (int j = 1; j < G; ++j)
-                if ((st.alive >> j) & 1u) idx[j] = ldg32(i0p + idx0_slot(kidx + (uint32_t)j * kstep, nk_full));
+                if ((st.alive >> j) & 1u) idx[j] = lds32(i0p + idx0_slot(kidx + (uint32_t)j * kstep, nk_full));
             probes += cnt - 32u;
             dead += __reduce_add_sync(0xFFFFFFFFu, probe_idx_phase<G, (G > 1 ? 1 : 0), G>(filt, idx, st.alive));
             if (!exhaustive && dead > limit) {
@@ -290,7 +294,7 @@ PF_D bool probe_group(const uint32_t *__restrict__ filt, const HashParams &hp, u
     } else {
 #pragma unroll
         for (int j = 0; j < G; ++j)
-            if ((st.alive >> j) & 1u) hb[j] = __ldg(hbp + kidx + (uint32_t)j * kstep);
+            if ((st.alive >> j) & 1u) hb[j] = lds64(hbp + kidx + (uint32_t)j * kstep);
 #pragma unroll
         for (int j = 0; j < G; ++j) st.g[j] = fx_finish(hp.c1, hb[j], hp.rot);
         probes += min(32u, cnt);
@@ -486,8 +490,8 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
         const uint32_t n_grab = min(a.grab, a.n_pairs - g0);
         PairMeta mine{};
         if (lane < n_grab) {
-            mine.r = ldg32(a.fr_read + g0 + lane);
-            mine.u = ldg32(a.fr_node + g0 + lane);
+            mine.r = lds32(a.fr_read + g0 + lane);
+            mine.u = lds32(a.fr_node + g0 + lane);
             mine.len = ldg32(a.lengths + mine.r);
             mine.koff = __ldg(a.kmer_off + mine.r);
             mine.slot = ldg32(a.node_slot + mine.u);
@@ -536,7 +540,7 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
                 const uint32_t o4 = __shfl_sync(0xFFFFFFFFu, my_off, sb + p);
                 const uint32_t nk4 = __shfl_sync(0xFFFFFFFFu, my_nk, sb + p);
                 idxv[p] = 0xFFFFFFFFu;
-                if (lane < (r0 & 0xFFu)) idxv[p] = ldg32(a.idx0 + k0 + idx0_slot(o4 + lane * (r0 >> 8), nk4));
+                if (lane < (r0 & 0xFFu)) idxv[p] = lds32(a.idx0 + k0 + idx0_slot(o4 + lane * (r0 >> 8), nk4));
             }
 #pragma unroll
             for (int p = 0; p < PROBE_CHUNK; ++p) {
@@ -588,7 +592,7 @@ static __global__ void __launch_bounds__(PROBE_THREADS, (G <= 2 ? 6 : (G <= 5 ? 
         // node; same-address atomics serialise in L2 (measured: 1 M of them cost ~0.5 ms), so the counter is kept in
         // NODE_PASS_COPIES copies, one per group of CTAs, summed by level_scan_kernel
         const bool pass = lane < n_grab && my_pass;
-        if (lane < n_grab) a.pass[g0 + lane] = pass ? 1 : 0;
+        if (lane < n_grab) __stcs(a.pass + g0 + lane, (uint8_t)(pass ? 1 : 0));
         if (pass) atomicAdd(np_mine + mine.u, 1u);
         probes_total += probes + __reduce_add_sync(0xFFFFFFFFu, my_probes);
         memo_total += memo_hits;
@@ -715,8 +719,8 @@ static __global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, cons
     __shared__ uint32_t s_cnt[32], s_base;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const bool on = i < n && pass[i];
-    const uint32_t u = on ? fr_node[i] : NONE32_D, r = on ? fr_read[i] : 0u;
+    const bool on = i < n && __ldcs(pass + i);
+    const uint32_t u = on ? lds32(fr_node + i) : NONE32_D, r = on ? lds32(fr_read + i) : 0u;
     const uint32_t u0 = fr_node[blockIdx.x * blockDim.x];  // the block's first pair exists: grid = ceil(n / block)
     const bool is0 = on && u == u0;
     const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, is0);
@@ -760,13 +764,13 @@ static __global__ void scatter_kernel(const uint32_t *__restrict__ fr_read, cons
         const uint32_t c = node_pass[u];
         const uint32_t l = left[u], rr = right[u];
         if (l != NONE32_D) {
-            nx_read[p] = r;
-            nx_node[p] = l;
+            __stcs(nx_read + p, r);
+            __stcs(nx_node + p, l);
             p += c;
         }
         if (rr != NONE32_D) {
-            nx_read[p] = r;
-            nx_node[p] = rr;
+            __stcs(nx_read + p, r);
+            __stcs(nx_node + p, rr);
         }
     }
 }

@@ -195,6 +195,20 @@ void pf::flatten(pf_db *db, int64_t search_depth) {
     db->n_slots = slot_of.size();
 }
 
+
+// slots are numbered in level order, so the filters of one level are (nearly) one contiguous range of the buffer
+static void level_slot_ranges(pf_db *db) {
+    const size_t n_levels = db->level_start.size() - 1;
+    db->level_slot_lo.assign(n_levels, NONE32);
+    db->level_slot_hi.assign(n_levels, 0);
+    for (size_t l = 0; l < n_levels; ++l)
+        for (uint32_t u = db->level_start[l]; u < db->level_start[l + 1]; ++u) {
+            if (db->h_slot[u] == NONE32) continue;  // subtree shards: filter held by another rank
+            db->level_slot_lo[l] = std::min(db->level_slot_lo[l], db->h_slot[u]);
+            db->level_slot_hi[l] = std::max(db->level_slot_hi[l], db->h_slot[u]);
+        }
+}
+
 template <class T>
 static int upload(T **dst, const std::vector<T> &v, cudaStream_t s) {
     PF_CUDA_OK(cudaMalloc(dst, std::max<size_t>(v.size(), 1) * sizeof(T)));
@@ -242,6 +256,18 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     PF_CUDA_OK(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
     PF_CUDA_OK(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
     PF_CUDA_OK(cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, db->device));
+    {   // L2 set-aside for persisting accesses: the filters a level is probing are pinned there with an access-policy
+        // window on the stream (run_levels), everything streamed is loaded evict-first (pf_kernels.cuh)
+        int persist = 0, window = 0;
+        const char *off = getenv("PF_L2_PERSIST");
+        if (!(off && off[0] == '0') && cudaDeviceGetAttribute(&persist, cudaDevAttrMaxPersistingL2CacheSize, db->device) == cudaSuccess &&
+            cudaDeviceGetAttribute(&window, cudaDevAttrMaxAccessPolicyWindowSize, db->device) == cudaSuccess && persist > 0 &&
+            window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist) == cudaSuccess) {
+            db->l2_persist_bytes = (uint64_t)persist;
+            db->l2_window_max = (uint64_t)window;
+        }
+        cudaGetLastError();
+    }
     timing.lap("cuda_init");
     if (db->sharded) {  // the load-time analysis of a sharded tree ends in an all-reduce
         int crc = comm_init_impl(db, db->nranks, db->rank, db->nccl_id.data());
@@ -263,6 +289,7 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
         int prc = shard_plan(db, db->cut_level_req);
         if (prc != PF_OK) return prc;
     }
+    level_slot_ranges(db);
     // decode every distinct filter once; geometry must be uniform
     std::vector<std::string> slot_path(db->n_slots);
     for (size_t q = 0; q < db->n_nodes; ++q)
@@ -791,6 +818,19 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
             a.order_span = (n_chunks + a.order_streams - 1) / a.order_streams;
         }
         if ((rc = ensure_events(db, st.n_ev + 2))) return rc;
+        if (db->l2_persist_bytes && db->level_slot_lo[l] != NONE32) {
+            // the level's filters as persisting lines: with more bytes than the set-aside, hitRatio makes that share of
+            // the window's lines persisting and the rest ordinary, instead of thrashing the set-aside
+            cudaStreamAttrValue v{};
+            const uint64_t bytes = std::min<uint64_t>((uint64_t)(db->level_slot_hi[l] - db->level_slot_lo[l] + 1) * db->wpf * 8,
+                                                      db->l2_window_max);
+            v.accessPolicyWindow.base_ptr = (void *)(db->d_filters + (uint64_t)db->level_slot_lo[l] * db->wpf);
+            v.accessPolicyWindow.num_bytes = bytes;
+            v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)db->l2_persist_bytes / (double)bytes);
+            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            PF_CUDA_OK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v));
+        }
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev], s));
         launch_probe(a, G, db->sm_count, s);
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev + 1], s));
@@ -826,6 +866,11 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         st.other_launches++;
         st.n = next_n;
         st.cur = nxt;
+    }
+    if (db->l2_persist_bytes) {  // later kernels on this stream (CSR, the next block's hashing) use L2 normally
+        cudaStreamAttrValue v{};
+        v.accessPolicyWindow.num_bytes = 0;
+        PF_CUDA_OK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v));
     }
     return PF_OK;
 }

@@ -356,6 +356,7 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
             const double exact_unrel = (jK < 0 ? n : jK) * (double)K, exact_rel = n * (double)K;
             double best = 0.5 * exact_unrel + 0.5 * exact_rel, best_unrel = exact_unrel;
             uint32_t best_s = 0;
+            double best_j = 0.0;
             const bool pretest_useful = tm.entry || reach > 0.5;
             for (uint32_t s = 1; pretest_useful && s < K && s <= (uint32_t)SL_STEP_BATCH; ++s) {
                 const double j = kmers_to_die(s);
@@ -365,10 +366,12 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
                     best = c;
                     best_unrel = unrel;
                     best_s = s;
+                    best_j = j;
                 }
             }
             tm.pre_steps = best_s;
             tm.filter_only = best_s != 0 && filt_ok;
+            tm.pre_rounds = (uint32_t)std::min(4.0, std::max(1.0, ceil(best_j / 32.0)));
             const double bytes = (double)(64ULL * db->wpf) * tm.row_words * 4.0;
             // entry tiles are worked tile-major, one table hot at a time; deeper tiles are touched at random
             const double rate = tm.entry ? sector_rate(bytes) : sector_rate(1e12);

@@ -28,6 +28,8 @@ struct SlicedTileDev {
     uint32_t entry;       // 1: every root is reached unconditionally (nothing evaluated above it)
     uint32_t pre_steps;   // probe steps of the sound pre-test pass (0 = none), chosen by the cost model
     uint32_t filter_only; // 1: the pre-test is all this tile does (its columns are implied by what passes below them)
+    uint32_t pre_rounds;  // rounds of 32 k-mers the shallow pre-test keeps in flight between two looks at the columns
+    uint32_t pad_;
     uint32_t valid[8];    // columns in use
     uint32_t terminal[8]; // columns that are tree leaves or have a child in another tile
     uint32_t leafmask[8]; // columns that are tree leaves
@@ -266,18 +268,20 @@ PF_D bool sl_scan(const HashParams &hp, const uint32_t *__restrict__ table, cons
 // lane still has RB * ST independent row loads outstanding; the columns are re-examined every RB rounds.
 template <int RW, int PW, bool SMALL_M, int RB, int ST>
 PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ table, const uint64_t *__restrict__ hbp,
-                          uint32_t n_k, uint32_t need, uint32_t lane, const uint32_t (&term)[RW], uint32_t term_mine,
-                          uint32_t &alive_mine, uint32_t (&live)[RW], uint32_t (&acc)[PW], uint32_t &sectors) {
+                          uint32_t n_k, uint32_t need, uint32_t rounds, uint32_t lane, const uint32_t (&term)[RW],
+                          uint32_t term_mine, uint32_t &alive_mine, uint32_t (&live)[RW], uint32_t (&acc)[PW],
+                          uint32_t &sectors) {
+    rounds = min(max(rounds, 1u), (uint32_t)RB);  // the plan expects reads to be settled after about this many rounds
     const bool allowed0 = need == n_k;
     const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
 #pragma unroll
     for (int pl = 0; pl < PW; ++pl) acc[pl] = 0u;
-    for (uint32_t base = 0; base < n_k; base += 32u * RB) {
+    for (uint32_t base = 0; base < n_k; base += 32u * rounds) {
         uint64_t hbv[RB];
         bool have[RB];
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
-            have[j] = base + 32u * j + lane < n_k;
+            have[j] = (uint32_t)j < rounds && base + 32u * j + lane < n_k;
             hbv[j] = have[j] ? sl_ld_stream(hbp + base + 32u * j + lane) : 0ULL;
         }
         uint32_t rows[RB][ST][RW];
@@ -314,7 +318,7 @@ PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ tab
         }
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
-            if (base + 32u * j >= n_k) break;  // warp-uniform
+            if ((uint32_t)j >= rounds || base + 32u * j >= n_k) break;  // warp-uniform
             uint32_t m[RW];
 #pragma unroll
             for (int w = 0; w < RW; ++w) {
@@ -333,7 +337,7 @@ PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ tab
                 acc[pl] = sum;
             }
         }
-        const uint32_t done = min(base + 32u * RB, n_k), rest = n_k - done;
+        const uint32_t done = min(base + 32u * rounds, n_k), rest = n_k - done;
         if (need > rest) {
             alive_mine &= sl_ge<PW>(acc, need - rest);
             if (!__any_sync(0xFFFFFFFFu, (alive_mine & term_mine) != 0u)) return false;
@@ -382,10 +386,10 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
         if (pre != 0u && pre < hp.K) {
             bool ok;
             if (pre == 1u)
-                ok = sl_scan_shallow<RW, PW, SMALL_M, 4, 1>(hp, table, hbp, n_k, need, lane, term, term_mine, alive_mine, live,
+                ok = sl_scan_shallow<RW, PW, SMALL_M, 4, 1>(hp, table, hbp, n_k, need, tm->pre_rounds, lane, term, term_mine, alive_mine, live,
                                                             acc, sectors);
             else if (pre == 2u)
-                ok = sl_scan_shallow<RW, PW, SMALL_M, 2, 2>(hp, table, hbp, n_k, need, lane, term, term_mine, alive_mine, live,
+                ok = sl_scan_shallow<RW, PW, SMALL_M, 2, 2>(hp, table, hbp, n_k, need, tm->pre_rounds, lane, term, term_mine, alive_mine, live,
                                                             acc, sectors);
             else
                 ok = sl_scan<RW, PW, SMALL_M>(hp, table, hbp, n_k, need, pre, lane, term, term_mine, alive_mine, live, acc,

@@ -26,6 +26,30 @@ sys.path.insert(0, ROOT)
 from phagefilter_b200 import accuracy as A  # noqa: E402
 
 BIN = os.path.join(ROOT, "phagefilter_b200", "bin", "phage_filter")
+# the command lines of the reference's own adapter (benchmarking/bench/tools/phage_filter.py:68-118), captured by importing
+# it (tests/golden/make_ref_adapter_vectors.py); only the binary path and the four placeholders are substituted
+import json  # noqa: E402
+ADAPTER = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_adapter_vectors.json")))["commands"]
+
+
+def adapter_cmd(which, k, theta, sub, filter_reads=True, depth=None):
+    tpl = next(c for c in ADAPTER if c["filter_reads"] == filter_reads and c["depth"] == depth)[which][0]
+    out, skip = [], False
+    for i, a in enumerate(tpl):
+        if skip:
+            skip = False
+            continue
+        if a == "./target/release/phage_filter":
+            out.append(BIN)
+        elif a == "--kmer-size":
+            out += [a, str(k)]
+            skip = True
+        elif a == "--filter-threshold":
+            out += [a, str(theta)]
+            skip = True
+        else:
+            out.append(sub.get(a, a))
+    return out
 COLUMNS = ["replicate", "kmer size", "theta", "error rate", "number of genomes", "read count", "time", "memory",
            "classification recall", "classification precision", "filter recall", "filter precision", "avg read count error"]
 
@@ -65,10 +89,9 @@ def main():
     try:
         for k in [int(x) for x in args.kmers.split(",")]:
             db = os.path.join(work, f"db_k{k}")
-            # the adapter's build line (phage_filter.py:79-88); seeds fixed so that the table is reproducible
-            t_build, _ = run([BIN, "build", "--genomes", genomes, "--db-path", db, "--kmer-size", str(k), "--cache-size", "100",
-                              "--false-pos-rate", "0.00001", "--largest-genome", "500000", "--threads", "1",
-                              "--seed-one", str(0x5EED0001), "--seed-two", str(0x5EED0002)])
+            # the adapter's build line (phage_filter.py:79-88) + fixed seeds so that the table is reproducible
+            t_build, _ = run(adapter_cmd("build", k, 0, {"{GENOMES}": genomes, "{DB}": db}) +
+                             ["--seed-one", str(0x5EED0001), "--seed-two", str(0x5EED0002)])
             print(f"build k={k}: {n_genomes} genome files in {t_build:.2f} s")
             for rf in read_files:
                 m = re.match(r"sim_reads_c(\d+)_n(\d+)_e([0-9.]+)\.fq", rf)
@@ -78,8 +101,7 @@ def main():
                 for theta in [float(x) for x in args.thetas.split(",")]:
                     out = os.path.join(work, "out")
                     # the adapter's query line (phage_filter.py:104-117)
-                    dt, rss = run([BIN, "query", "--reads", reads, "--db-path", db, "--filter-threshold", str(theta), "--cache-size", "1",
-                                   "--block-size-reads", "1000", "--out", out, "--threads", "1", "--pos-filter"])
+                    dt, rss = run(adapter_cmd("run", k, theta, {"{READS}": reads, "{DB}": db, "{OUT}": out}))
                     cls = A.parse_classification(os.path.join(out, "CLASSIFICATION.csv"))
                     c_rec, c_prec = A.get_classification_metrics(truth, cls)
                     diffs = A.get_readcount_metrics(truth, cls)
