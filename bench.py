@@ -55,6 +55,11 @@ CONFIGS = {
                  errors=(0.01,), background=0.9, seed_g=1003, seed_r=2003, steps=20, cpu_sample=20_000, lru_sample=500,
                  name="cfg3: 10000 synthetic phage genomes (35.9 GB gSBT) vs {reads} x 150 bp reads per step "
                       "(20 steps = 100 M reads), 10 % phage spike-in, -f 0.8"),
+    "cfg3s": dict(kind="synth", families=100, family_size=10, largest=1_000_000, theta=0.8, read_len=150, reads=5_000_000,
+                  errors=(0.01,), background=0.9, seed_g=1003, seed_r=2003, steps=5, cpu_sample=20_000, lru_sample=500,
+                  name="cfg3s (profiling stand-in for cfg3: same reads, filter geometry and tile-table size, a tenth of the "
+                       "genomes so that ncu's kernel replay can save and restore device memory): 1000 synthetic genomes "
+                       "(3.6 GB gSBT) vs {reads} x 150 bp reads per step, 10 % spike-in, -f 0.8"),
     "cfg4": dict(kind="synth", families=1000, family_size=10, largest=1_000_000, theta=0.9, read_len=10_000, reads=200_000,
                  errors=(0.001,), background=0.9, seed_g=1003, seed_r=2004, steps=5, cpu_sample=400, lru_sample=100,
                  name="cfg4: 10000-genome gSBT (35.9 GB) vs {reads} x 10 kb reads per step (5 steps = 1 M reads), "
@@ -207,7 +212,7 @@ def cpu_resident(db_dir, cfg, blob, offs, n_sample, steps, warmup, threads=0, ta
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return n_sample, times, res.probes_ref / max(n_sample, 1), res.pairs / max(n_sample, 1)
+    return n_sample, times, res.probes_ref / max(n_sample, 1), res.pairs / max(n_sample, 1), res.hits
 
 
 def cpu_faithful(db_dir, cfg, blob, offs, n_sample, threads, cache_size=10, block_size=100):
@@ -253,7 +258,7 @@ def run_reference(args, cfg):
     n_sample = cfg["cpu_sample"]
     blob, offs = make_reads(cfg, genomes, n_sample, cfg.get("seed_r", 0))
     warm = max(args.warmup, 1)
-    n_sample, times, p_ref, pairs_ref = cpu_resident(db_dir, cfg, blob, offs, n_sample, args.steps, warm, target_s=4.0)
+    n_sample, times, p_ref, pairs_ref, _ = cpu_resident(db_dir, cfg, blob, offs, n_sample, args.steps, warm, target_s=4.0)
     total = sum(times)
     v = n_sample * len(times) / total
     sample = (f"first {n_sample} reads of the workload per step, all {cores} host threads (OpenMP), every filter resident in "
@@ -391,6 +396,13 @@ def run_ours(args, cfg):
     last_off = np.ctypeslib.as_array(hits.read_off, shape=(args.reads + 1,)).copy()
     last_leaf = np.ctypeslib.as_array(hits.leaf, shape=(n_hits,)).copy() if n_hits else np.zeros(0, dtype=np.uint32)
     last_batch = (args.steps - 1) % n_batches
+    if last_batch == 0:
+        first_off, first_leaf = last_off, last_leaf
+    else:  # the CPU sample below is the head of batch 0
+        _lib.check(query_device(tree._h, dev_batches[0], C.c_float(theta), 1, C.byref(hits)))
+        first_off = np.ctypeslib.as_array(hits.read_off, shape=(args.reads + 1,)).copy()
+        first_leaf = (np.ctypeslib.as_array(hits.leaf, shape=(int(hits.n_hits),)).copy() if hits.n_hits
+                      else np.zeros(0, dtype=np.uint32))
     # ---- end-to-end through the C-ABI call with host buffers --------------------------------------
     run_e2e(2)
     if world > 1:
@@ -476,7 +488,8 @@ def run_ours(args, cfg):
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            tj = json.load(open(tpath)).get(args.config, {})
+            tj = json.load(open(tpath))
+            tj = tj.get(args.config) or tj.get({"cfg3": "cfg3s", "cfg4": "cfg3s"}.get(args.config, ""), {})
             key = "sliced_probe_kernel" if sliced else "probe_kernel"
             traffic, traffic_src = tj.get(key + "_dram_bytes_per_launch"), tj.get("source")
         rate = C.c_double(0)
@@ -531,8 +544,18 @@ def run_ours(args, cfg):
         cores = os.cpu_count() or 1
         blob, offs = host_batches[0]
         n_cpu = 500 if args.profile else cfg["cpu_sample"]
-        n_sample, times, p_ref, pairs_ref = cpu_resident(db_dir, cfg, blob, offs, n_cpu, 1, 0, target_s=10.0)
+        n_sample, times, p_ref, pairs_ref, cpu_hits = cpu_resident(db_dir, cfg, blob, offs, n_cpu, 1, 0, target_s=10.0)
         cpu_v = n_sample * len(times) / sum(times)
+        # parity guard at the full database size: the oracle's (read, leaf) hits for its sample are exactly the GPU's
+        order = np.lexsort((cpu_hits[:, 1], cpu_hits[:, 0])) if len(cpu_hits) else np.zeros(0, dtype=np.int64)
+        want_off = np.zeros(n_sample + 1, dtype=np.uint64)
+        if len(cpu_hits):
+            np.add.at(want_off, cpu_hits[:, 0].astype(np.int64) + 1, 1)
+        want_off = np.cumsum(want_off, dtype=np.uint64)
+        want_leaf = cpu_hits[order, 1] if len(cpu_hits) else np.zeros(0, dtype=np.uint32)
+        parity_ok = bool((first_off[: n_sample + 1] == want_off).all() and
+                         (first_leaf[: int(want_off[-1])] == want_leaf).all())
+        assert parity_ok, "GPU hit lists differ from the CPU oracle's on the sampled reads"
         modes = {"resident_all_cores": {"value": cpu_v, "reads": n_sample, "threads": cores}}
         if not args.profile:
             n_lru = cfg["lru_sample"]
@@ -575,6 +598,7 @@ def run_ours(args, cfg):
                      "reference_semantics_probes_per_step": int(p_ref * args.reads),
                      "reference_semantics_pairs_per_step": int(pairs_ref * args.reads),
                      "reference_semantics_sample": f"oracle on the first {n_sample} reads, scaled to the step",
+                     "parity_check": {"reads": n_sample, "hits": int(len(cpu_hits)), "identical_to_oracle": parity_ok},
                      "db_build_s": round(build_s, 2), "db_open_s": round(open_s, 2), "warmup_s": round(warm_s, 2)},
         }
         if shard:

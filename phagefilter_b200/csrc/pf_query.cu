@@ -259,8 +259,9 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     {   // L2 set-aside for persisting accesses: the filters a level is probing are pinned there with an access-policy
         // window on the stream (run_levels), everything streamed is loaded evict-first (pf_kernels.cuh)
         int persist = 0, window = 0;
-        const char *off = getenv("PF_L2_PERSIST");
-        if (!(off && off[0] == '0') && cudaDeviceGetAttribute(&persist, cudaDevAttrMaxPersistingL2CacheSize, db->device) == cudaSuccess &&
+        const char *off = getenv("PF_L2_PERSIST");  // 0: no window; 1 (default): levels whose filters fit the set-aside; 2: every level
+        db->l2_persist_policy = off ? atoi(off) : 1;
+        if (db->l2_persist_policy != 0 && cudaDeviceGetAttribute(&persist, cudaDevAttrMaxPersistingL2CacheSize, db->device) == cudaSuccess &&
             cudaDeviceGetAttribute(&window, cudaDevAttrMaxAccessPolicyWindowSize, db->device) == cudaSuccess && persist > 0 &&
             window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist) == cudaSuccess) {
             db->l2_persist_bytes = (uint64_t)persist;
@@ -818,7 +819,18 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
             a.order_span = (n_chunks + a.order_streams - 1) / a.order_streams;
         }
         if ((rc = ensure_events(db, st.n_ev + 2))) return rc;
-        if (db->l2_persist_bytes && db->level_slot_lo[l] != NONE32) {
+        const uint64_t level_filter_bytes =
+            db->level_slot_lo[l] == NONE32 ? 0 : (uint64_t)(db->level_slot_hi[l] - db->level_slot_lo[l] + 1) * db->wpf * 8;
+        const bool window = db->l2_persist_bytes && level_filter_bytes &&
+                            (db->l2_persist_policy >= 2 || level_filter_bytes <= std::min(db->l2_persist_bytes, db->l2_window_max));
+        if (db->l2_window_set && !window) {  // the previous level's persisting lines would only take L2 away from this one
+            cudaStreamAttrValue v{};
+            v.accessPolicyWindow.num_bytes = 0;
+            PF_CUDA_OK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v));
+            db->l2_window_set = false;
+        }
+        if (window) {
+            db->l2_window_set = true;
             // the level's filters as persisting lines: with more bytes than the set-aside, hitRatio makes that share of
             // the window's lines persisting and the rest ordinary, instead of thrashing the set-aside
             cudaStreamAttrValue v{};
@@ -867,10 +879,11 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         st.n = next_n;
         st.cur = nxt;
     }
-    if (db->l2_persist_bytes) {  // later kernels on this stream (CSR, the next block's hashing) use L2 normally
+    if (db->l2_window_set) {  // later kernels on this stream (CSR, the next block's hashing) use L2 normally
         cudaStreamAttrValue v{};
         v.accessPolicyWindow.num_bytes = 0;
         PF_CUDA_OK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v));
+        db->l2_window_set = false;
     }
     return PF_OK;
 }

@@ -28,6 +28,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CMD = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--profile"]
+CONFIG = "cfg2"
 TIMED_STEP = 4  # 1-based index of the timed step among the hash_kernel launches
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
@@ -62,17 +63,21 @@ def timed_step(rows):
     return [r for r in rows[lo:hi] if "pf::" in r[1] or "hash_kernel" in r[1] or "probe_kernel" in r[1]]
 
 
-def cmd_run(tag, no_bench=False):
+def cmd_run(tag, no_bench=False, launches_only=False):
     out = os.path.join(ROOT, "gpurun_out", tag)
     os.makedirs(out, exist_ok=True)
     if not no_bench:
         with open(os.path.join(out, "bench.json"), "w") as f:
-            subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3"], check=True, stdout=f)
+            subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", CONFIG, "--steps", "5", "--warmup", "3"],
+                           check=True, stdout=f)
     subprocess.run(CMD, check=True, stdout=subprocess.DEVNULL)  # must exit 0 without ncu first
     raw = os.path.join(out, "launches_raw.csv")
     subprocess.run(["ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "--csv", "--log-file", raw, *CMD],
                    check=True, stdout=subprocess.DEVNULL)
     rows = read_launch_list(raw)
+    if launches_only:
+        print("launch list only:", len(rows), "launches")
+        return
     sel = [r for r in rows if "hash_kernel" in r[1] or "probe_kernel" in r[1]]
     step = [r for r in timed_step(rows) if "hash_kernel" in r[1] or "probe_kernel" in r[1]]
     skip = sel.index(step[0])
@@ -103,7 +108,7 @@ def cmd_summarise(tag):
     print(f"{len(rows)} launches, {total / 1e6:.2f} ms of kernels in the timed step")
     for k, v in sorted(share.items(), key=lambda kv: -kv[1]):
         print(f"  {k:28s} {v / 1e6:7.3f} ms  {100 * v / total:5.1f} %")
-    probe = [r[2] / 1e6 for r in rows if "probe_kernel" in r[1]]
+    probe = [r[2] / 1e6 for r in rows if "probe_kernel" in r[1]]  # also matches sliced_probe_kernel
     print("  probe levels (ms):", ", ".join(f"{x:.2f}" for x in probe))
     # full-set summary: metrics as rows, launches as columns
     if not os.path.exists(os.path.join(src, "full_raw.csv")):
@@ -132,14 +137,23 @@ def cmd_summarise(tag):
     def as_bytes(r, m):
         v, u = float(r[col[m]].replace(",", "")), units[col[m]].lower()
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-    pl = [r for r in launches if "probe_kernel" in r[col["Kernel Name"]]]
-    if pl and "dram__bytes_read.sum" in col:
-        mean = sum(as_bytes(r, "dram__bytes_read.sum") + as_bytes(r, "dram__bytes_write.sum") for r in pl) / len(pl)
-        json.dump({"probe_kernel_dram_bytes_per_launch": mean, "launches": len(pl),
-                   "source": f"profiles/{tag}_ncu_full_summary.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
-                             f"mean over the {len(pl)} probe launches of one step)"},
-                  open(os.path.join(prof, "traffic.json"), "w"), indent=1)
-        print(f"  DRAM traffic per probe launch: {mean / 1e9:.2f} GB")
+    tpath = os.path.join(prof, "traffic.json")
+    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    if "probe_kernel_dram_bytes_per_launch" in tj:  # round-1 layout: one flat entry for cfg2
+        tj = {"cfg2": tj}
+    entry = {}
+    for key in ("sliced_probe_kernel", "probe_kernel"):
+        pl = [r for r in launches if key in r[col["Kernel Name"]] and (key != "probe_kernel" or "sliced" not in r[col["Kernel Name"]])]
+        if pl and "dram__bytes_read.sum" in col:
+            mean = sum(as_bytes(r, "dram__bytes_read.sum") + as_bytes(r, "dram__bytes_write.sum") for r in pl) / len(pl)
+            entry[key + "_dram_bytes_per_launch"] = mean
+            entry[key + "_launches"] = len(pl)
+            print(f"  DRAM traffic per {key} launch: {mean / 1e9:.2f} GB over {len(pl)} launches")
+    if entry:
+        entry["source"] = (f"profiles/{tag}_ncu_full_summary.csv (ncu --set full on bench.py --config {CONFIG}, dram__bytes_read.sum + "
+                           "dram__bytes_write.sum, mean over that kernel's launches of one step)")
+        tj[CONFIG] = entry
+        json.dump(tj, open(tpath, "w"), indent=1)
     if os.path.exists(os.path.join(src, "bench.json")):
         shutil.copy(os.path.join(src, "bench.json"), os.path.join(prof, f"bench_{tag}.json"))
 
@@ -149,8 +163,12 @@ if __name__ == "__main__":
     ap.add_argument("mode", choices=["run", "summarise"])
     ap.add_argument("--tag", required=True)
     ap.add_argument("--no-bench", action="store_true", help="run: skip the plain 5-step bench line")
+    ap.add_argument("--config", default="cfg2", help="bench.py --config to profile")
+    ap.add_argument("--launches-only", action="store_true", help="run: stop after the launch list (no full-set pass)")
     a = ap.parse_args()
+    CONFIG = a.config
+    CMD += ["--config", CONFIG]
     if a.mode == "run":
-        cmd_run(a.tag, a.no_bench)
+        cmd_run(a.tag, a.no_bench, a.launches_only)
     else:
         cmd_summarise(a.tag)

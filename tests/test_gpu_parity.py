@@ -372,5 +372,9 @@ def test_frontier_cap_splits_chunks(oracle, tmp_path):
             gt.reset_stats()
             assert gpu_query(gt, reads, theta) == want.hit_sets(len(reads)), (theta, mode)
             assert get_leaf_counts(gt) == ot.leaf_counts(), (theta, mode)
-            assert gt.stats().chunk_splits >= 1, (theta, mode)
+            st = gt.stats()
+            if mode == 1:
+                assert st.chunk_splits >= 1, theta  # a chunk outgrew the cap half-way down and was redone in halves
+            else:
+                assert st.probe_launches >= 3, theta  # (read, entry tile) pairs are bounded up front: several chunks
     gt.close()
