@@ -245,7 +245,7 @@ struct pf_db {
     // L2 residency (access-policy window on the stream): bytes of L2 set aside for persisting lines, largest window, and
     // per level the range of filter slots its nodes use
     uint64_t l2_persist_bytes = 0, l2_window_max = 0;
-    int l2_persist_policy = 1;
+    int l2_persist_policy = 0;
     bool l2_window_set = false;
     std::vector<uint32_t> level_slot_lo, level_slot_hi;
     double plan_cost = 0.0;            // expected bit probes PER K-MER of a read unrelated to the database under the current step plan

@@ -259,8 +259,12 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
     {   // L2 set-aside for persisting accesses: the filters a level is probing are pinned there with an access-policy
         // window on the stream (run_levels), everything streamed is loaded evict-first (pf_kernels.cuh)
         int persist = 0, window = 0;
-        const char *off = getenv("PF_L2_PERSIST");  // 0: no window; 1 (default): levels whose filters fit the set-aside; 2: every level
-        db->l2_persist_policy = off ? atoi(off) : 1;
+        // PF_L2_PERSIST: 0 (default) no window; 1: levels whose filters fit the set-aside; 2: every level (hitRatio < 1).
+        // Measured on BASELINE config 2 (profiles/r2h_*): the filters being probed are L2 hits already (the frontier is
+        // node-major; what misses is the compulsory streaming of frontier / index / hash arrays, loaded evict-first), so the
+        // window changes neither hit rate nor DRAM bytes, while the set-aside takes L2 from the leaf levels whose filters
+        // together exceed it: 4.40 ms per step without, 5.71 (policy 1) and 5.62 (policy 2) with.
+        db->l2_persist_policy = off ? atoi(off) : 0;
         if (db->l2_persist_policy != 0 && cudaDeviceGetAttribute(&persist, cudaDevAttrMaxPersistingL2CacheSize, db->device) == cudaSuccess &&
             cudaDeviceGetAttribute(&window, cudaDevAttrMaxAccessPolicyWindowSize, db->device) == cudaSuccess && persist > 0 &&
             window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist) == cudaSuccess) {
