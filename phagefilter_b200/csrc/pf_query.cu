@@ -264,6 +264,7 @@ int pf::db_open_impl(pf_db *db, const char *db_path, int64_t search_depth) {
         // node-major; what misses is the compulsory streaming of frontier / index / hash arrays, loaded evict-first), so the
         // window changes neither hit rate nor DRAM bytes, while the set-aside takes L2 from the leaf levels whose filters
         // together exceed it: 4.40 ms per step without, 5.71 (policy 1) and 5.62 (policy 2) with.
+        const char *off = getenv("PF_L2_PERSIST");
         db->l2_persist_policy = off ? atoi(off) : 0;
         if (db->l2_persist_policy != 0 && cudaDeviceGetAttribute(&persist, cudaDevAttrMaxPersistingL2CacheSize, db->device) == cudaSuccess &&
             cudaDeviceGetAttribute(&window, cudaDevAttrMaxAccessPolicyWindowSize, db->device) == cudaSuccess && persist > 0 &&
