@@ -248,6 +248,7 @@ struct pf_db {
     int l2_persist_policy = 0;
     bool l2_window_set = false;
     std::vector<uint32_t> level_slot_lo, level_slot_hi;
+    double related_share = -1.0;       // running estimate of the share of reads with at least one hit (-1: none yet)
     double plan_cost = 0.0;            // expected bit probes PER K-MER of a read unrelated to the database under the current step plan
     pf::SlicedState *sliced = nullptr;
     std::vector<uint8_t> nccl_id;      // ncclUniqueId handed to pf_db_open_sharded (the analysis at open is collective)

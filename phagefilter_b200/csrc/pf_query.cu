@@ -1057,6 +1057,10 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
     }
     account_stats(db, st, n_reads, d2h);
     if (sliced) db->stats.sliced_blocks++;
+    {   // feeds the choice between the two evaluation paths (sliced_prepare)
+        const double share = std::min(1.0, (double)st.hits_total / (double)n_reads);
+        db->related_share = db->related_share < 0 ? share : 0.7 * db->related_share + 0.3 * share;
+    }
     return PF_OK;
 }
 

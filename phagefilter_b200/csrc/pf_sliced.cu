@@ -41,12 +41,14 @@ struct SlicedState {
     unsigned long long *h_counters = nullptr;    // pinned [4]
     unsigned long long *h_tile_base = nullptr;   // pinned [n_tiles]
     bool tables_ready = false;
+    bool entry_lean = false;  // every entry tile is filter-only with a pre-test of at most 2 steps
     DevBuf<uint32_t> fr_read[2], fr_tile[2], fr_src[2], reach[2], alive;
     // what the plan was made for
     float theta = -1.f;
     uint64_t n_nominal = 0;
     int decided_mode = 0;  // 1 pair, 2 sliced (for theta / n_nominal above)
     int decided_under = -1;  // pf_db_set_mode value the decision was taken under
+    double decided_rho = 0.5; // related share the decision was taken for
     bool failed = false;   // tables could not be built (memory): stay with the node-at-a-time path
 };
 
@@ -380,8 +382,17 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
         }
         S.est_sectors_per_read = total_sectors;
         S.est_seconds_per_read = total_s;
-        // a read that belongs to a genome of the database walks one tile per tile-tree level with all its k-mers
-        S.est_seconds_related = (double)(max_depth + 1) * n * (double)K / sector_rate(1e12);
+        // a read that belongs to a genome of the database: the entry tile's pre-test (plus its exact pass unless the tile
+        // only filters), then one exactly evaluated tile per tile-tree level below
+        {
+            double worst_entry = 0.0;
+            for (uint32_t t : S.entry_tiles) {
+                const SlicedTileDev &tm = S.tiles[t];
+                const double bytes = (double)(64ULL * db->wpf) * tm.row_words * 4.0;
+                worst_entry += (n * (double)tm.pre_steps + (tm.filter_only ? 0.0 : n * (double)K)) / sector_rate(bytes);
+            }
+            S.est_seconds_related = worst_entry + (double)max_depth * n * (double)K / sector_rate(1e12);
+        }
     }
 }
 
@@ -503,7 +514,11 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
     if (!db->sliced) db->sliced = new SlicedState();
     SlicedState &S = *db->sliced;
     if (S.failed && db->mode != 2) return PF_OK;
-    if (S.decided_mode && S.theta == threshold && S.n_nominal == n_nominal && S.decided_under == db->mode) {
+    // the share of reads that belong to the database decides which path is cheaper; it is learnt from the blocks
+    // already answered (hits per read, capped at 1) and starts at 1/2
+    const double rho = db->related_share < 0 ? 0.5 : db->related_share;
+    if (S.decided_mode && S.theta == threshold && S.n_nominal == n_nominal && S.decided_under == db->mode &&
+        (db->mode != 0 || fabs(rho - S.decided_rho) <= 0.1)) {
         *use_sliced = S.decided_mode == 2;
         if (*use_sliced) {
             db->stats.sliced_tiles = S.tiles.size();
@@ -515,20 +530,41 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
     plan_tiles(db, threshold, n_nominal, P);
     bool sliced = db->mode == 2;
     if (db->mode == 0) {
-        const double t_pair = db->plan_cost * (double)n_nominal / 240e9;  // the step plan's cost is in probes per k-mer
-        // half of the reads are assumed to belong to the database (the planner cannot know the sample's composition)
-        const double t_sliced = 0.5 * P.est_seconds_per_read + 0.5 * P.est_seconds_related;
-        sliced = t_sliced < 0.8 * t_pair;
+        // Node-at-a-time: the step plan's expected probes per k-mer for an unrelated read (L2-resident filters, ~240 G
+        // probes/s measured); a related read walks root -> leaf, two cheap sampled tests per level and one exact leaf.
+        const double n = (double)n_nominal, K = (double)db->geom.num_hashes;
+        const double levels = (double)(db->level_start.size() - 1);
+        const double p_unrel = db->plan_cost * n / 240e9, p_rel = (n * K + 32.0 * levels) / 240e9;
+        const double t_pair = (1.0 - rho) * p_unrel + rho * p_rel;
+        const double t_sliced = (1.0 - rho) * P.est_seconds_per_read + rho * P.est_seconds_related;
+        // hysteresis: leave the current path only for a clear gain
+        sliced = S.decided_mode == 2 ? !(t_pair < 0.8 * t_sliced) : t_sliced < 0.8 * t_pair;
         if (getenv("PF_SLICED_DEBUG"))
-            fprintf(stderr, "[sliced plan] auto: node-at-a-time %.1f ns/read, sliced %.1f ns/read -> %s\n", t_pair * 1e9, t_sliced * 1e9,
-                    sliced ? "sliced" : "node-at-a-time");
+            fprintf(stderr, "[sliced plan] auto (related share %.2f): node-at-a-time %.1f ns/read (unrelated %.1f, related %.1f), "
+                            "sliced %.1f ns/read (unrelated %.1f, related %.1f) -> %s\n",
+                    rho, t_pair * 1e9, p_unrel * 1e9, p_rel * 1e9, t_sliced * 1e9, P.est_seconds_per_read * 1e9,
+                    P.est_seconds_related * 1e9, sliced ? "sliced" : "node-at-a-time");
     }
     S.theta = threshold;
     S.n_nominal = n_nominal;
     S.decided_mode = sliced ? 2 : 1;
     S.decided_under = db->mode;
+    S.decided_rho = rho;
     if (!sliced) return PF_OK;
     const bool same = S.tables_ready && S.skip == P.skip && S.tiles.size() == P.tiles.size();
+    if (same) {
+        // same tiling, possibly other pre-test depths (they follow the threshold and the read length): refresh the tile records
+        for (size_t t = 0; t < S.tiles.size(); ++t) {
+            S.tiles[t].pre_steps = P.tiles[t].pre_steps;
+            S.tiles[t].filter_only = P.tiles[t].filter_only;
+            S.tiles[t].pre_rounds = P.tiles[t].pre_rounds;
+        }
+        PF_CUDA_OK(cudaMemcpyAsync(S.d_tiles, S.tiles.data(), S.tiles.size() * sizeof(SlicedTileDev), cudaMemcpyHostToDevice, db->stream));
+        PF_CUDA_OK(cudaStreamSynchronize(db->stream));
+        S.est_sectors_per_read = P.est_sectors_per_read;
+        S.est_seconds_per_read = P.est_seconds_per_read;
+        S.est_seconds_related = P.est_seconds_related;
+    }
     if (!same) {
         S.skip = std::move(P.skip);
         S.tiles = std::move(P.tiles);
@@ -552,6 +588,10 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
             return PF_OK;                  // auto: stay with the node-at-a-time path
         }
     }
+    S.entry_lean = !S.entry_tiles.empty();
+    for (uint32_t t : S.entry_tiles)
+        S.entry_lean = S.entry_lean && S.tiles[t].filter_only && S.tiles[t].pre_steps >= 1 && S.tiles[t].pre_steps <= 2 &&
+                       S.tiles[t].pre_steps < db->geom.num_hashes;
     db->stats.sliced_tiles = S.tiles.size();
     db->stats.sliced_table_bytes = S.table_words * 4ULL;
     *use_sliced = true;
@@ -561,9 +601,14 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
 uint64_t sliced_entry_tiles(const pf_db *db) { return db->sliced ? db->sliced->entry_tiles.size() : 0; }
 
 template <int PW>
-static void launch_sliced(const SlicedArgs &a, int grid, cudaStream_t s) {
-    if (a.hp.small_m) sliced_probe_kernel<PW, true><<<grid, SL_THREADS, 0, s>>>(a);
-    else sliced_probe_kernel<PW, false><<<grid, SL_THREADS, 0, s>>>(a);
+static void launch_sliced(const SlicedArgs &a, int sm_count, bool lean, cudaStream_t s) {
+    if (lean) {
+        if (a.hp.small_m) sliced_probe_kernel<PW, true, true><<<sm_count * 3, SL_THREADS, 0, s>>>(a);
+        else sliced_probe_kernel<PW, false, true><<<sm_count * 3, SL_THREADS, 0, s>>>(a);
+    } else {
+        if (a.hp.small_m) sliced_probe_kernel<PW, true, false><<<sm_count * 2, SL_THREADS, 0, s>>>(a);
+        else sliced_probe_kernel<PW, false, false><<<sm_count * 2, SL_THREADS, 0, s>>>(a);
+    }
 }
 
 // The tile-level descent for reads [r0, r0 + n_chunk) of the batch whose hash values are cached in db->hb.
@@ -577,7 +622,6 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
     if (n > db->frontier_cap) return PF_SPLIT_CHUNK;
     int cur = 0;
     bool entry = true;
-    const int grid = db->sm_count * 2;
     while (n > 0) {
         if ((rc = S.reach[cur].ensure(n * 8)) || (rc = S.alive.ensure(n))) return rc;
         PF_CUDA_OK(cudaMemsetAsync(S.d_counters, 0, 3 * 8, s));
@@ -614,9 +658,11 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
             db->ev_probe.push_back(e);
         }
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev], s));
-        if (bt->max_kmers < 256) launch_sliced<8>(a, grid, s);
-        else if (bt->max_kmers < 65536) launch_sliced<16>(a, grid, s);
-        else launch_sliced<32>(a, grid, s);
+        // entry depth: every tile filter-only with a 1- or 2-step pre-test (the usual plan) -> the lean instantiation
+        const bool lean = entry && S.entry_lean && !getenv("PF_SLICED_NO_LEAN");
+        if (bt->max_kmers < 256) launch_sliced<8>(a, db->sm_count, lean, s);
+        else if (bt->max_kmers < 65536) launch_sliced<16>(a, db->sm_count, lean, s);
+        else launch_sliced<32>(a, db->sm_count, lean, s);
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev + 1], s));
         st.n_ev += 2;
         st.probe_launches++;

@@ -357,7 +357,9 @@ PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ tab
 
 // One (read, tile) pair.  Returns true when the pair has an output (a leaf hit or a successor tile); the columns
 // reached and passed are then in reach_out (replicated in every lane).  s_bits: 8 words of shared memory of this warp.
-template <int RW, int PW, bool SMALL_M>
+// LEAN: the instantiation for depths whose tiles are all filter-only with a shallow (1- or 2-step) pre-test -- the exact
+// pass and the deep scan are compiled out, which halves the registers and doubles the warps resident per SM.
+template <int RW, int PW, bool SMALL_M, bool LEAN>
 PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t r, uint32_t src, uint32_t lane,
                   uint32_t *s_bits, uint32_t (&reach_out)[RW], uint32_t &sectors) {
     const HashParams &hp = a.hp;
@@ -391,18 +393,20 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
             else if (pre == 2u)
                 ok = sl_scan_shallow<RW, PW, SMALL_M, 2, 2>(hp, table, hbp, n_k, need, tm->pre_rounds, lane, term, term_mine, alive_mine, live,
                                                             acc, sectors);
-            else
+            else if constexpr (!LEAN)
                 ok = sl_scan<RW, PW, SMALL_M>(hp, table, hbp, n_k, need, pre, lane, term, term_mine, alive_mine, live, acc,
                                               sectors);
+            else
+                ok = true;  // not reached: the host launches the lean kernel only where pre <= 2
             if (!ok) return false;
         }
-        if (pre != 0u && pre < hp.K && tm->filter_only) {
+        if (LEAN || (pre != 0u && pre < hp.K && tm->filter_only)) {
             // columns the pre-test could not rule out count as passed: the exact tiles below decide (see plan)
 #pragma unroll
             for (int pl = 0; pl < PW; ++pl) acc[pl] = 0xFFFFFFFFu;
-        } else if (!sl_scan<RW, PW, SMALL_M>(hp, table, hbp, n_k, need, hp.K, lane, term, term_mine, alive_mine, live, acc,
-                                             sectors)) {
-            return false;
+        } else if constexpr (!LEAN) {
+            if (!sl_scan<RW, PW, SMALL_M>(hp, table, hbp, n_k, need, hp.K, lane, term, term_mine, alive_mine, live, acc, sectors))
+                return false;
         }
     }
     // query_passes (query.rs:48): hits >= ceil(theta * n_k).  Columns ruled out earlier may hold stale counts (their
@@ -464,11 +468,11 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
     return t != 0u;
 }
 
-template <int RW, int PW, bool SMALL_M>
+template <int RW, int PW, bool SMALL_M, bool LEAN>
 PF_D void sl_pair_and_record(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t pair, uint32_t r,
                              uint32_t src, uint32_t lane, uint32_t *s_bits, uint32_t &sectors) {
     uint32_t reach[RW];
-    if (!sl_pair<RW, PW, SMALL_M>(a, tm, r, src, lane, s_bits, reach, sectors)) return;
+    if (!sl_pair<RW, PW, SMALL_M, LEAN>(a, tm, r, src, lane, s_bits, reach, sectors)) return;
     // record: reach vector, alive list, per-tile successor counts, hit count
     if (lane < 8u) {
         uint32_t v = 0u;
@@ -495,8 +499,8 @@ PF_D void sl_pair_and_record(const SlicedArgs &a, const SlicedTileDev *__restric
 }
 
 // Persistent grid; a warp takes `grab` consecutive pairs per ticket and works them one after the other.
-template <int PW, bool SMALL_M>
-static __global__ void __launch_bounds__(SL_THREADS, 2) sliced_probe_kernel(const SlicedArgs a) {
+template <int PW, bool SMALL_M, bool LEAN>
+static __global__ void __launch_bounds__(SL_THREADS, LEAN ? 3 : 2) sliced_probe_kernel(const SlicedArgs a) {
     __shared__ uint32_t s_bits_all[SL_THREADS / 32][8];
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t *const s_bits = s_bits_all[threadIdx.x >> 5];
@@ -521,10 +525,10 @@ static __global__ void __launch_bounds__(SL_THREADS, 2) sliced_probe_kernel(cons
             }
             const SlicedTileDev *tm = a.tiles + t;
             switch (tm->row_words) {
-                case 8: sl_pair_and_record<8, PW, SMALL_M>(a, tm, i, r, src, lane, s_bits, sectors); break;
-                case 4: sl_pair_and_record<4, PW, SMALL_M>(a, tm, i, r, src, lane, s_bits, sectors); break;
-                case 2: sl_pair_and_record<2, PW, SMALL_M>(a, tm, i, r, src, lane, s_bits, sectors); break;
-                default: sl_pair_and_record<1, PW, SMALL_M>(a, tm, i, r, src, lane, s_bits, sectors); break;
+                case 8: sl_pair_and_record<8, PW, SMALL_M, LEAN>(a, tm, i, r, src, lane, s_bits, sectors); break;
+                case 4: sl_pair_and_record<4, PW, SMALL_M, LEAN>(a, tm, i, r, src, lane, s_bits, sectors); break;
+                case 2: sl_pair_and_record<2, PW, SMALL_M, LEAN>(a, tm, i, r, src, lane, s_bits, sectors); break;
+                default: sl_pair_and_record<1, PW, SMALL_M, LEAN>(a, tm, i, r, src, lane, s_bits, sectors); break;
             }
         }
         sectors_total += __reduce_add_sync(0xFFFFFFFFu, sectors);
