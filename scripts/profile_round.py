@@ -68,7 +68,7 @@ def cmd_run(tag, no_bench=False, launches_only=False):
     os.makedirs(out, exist_ok=True)
     if not no_bench:
         with open(os.path.join(out, "bench.json"), "w") as f:
-            subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", CONFIG, "--steps", "5", "--warmup", "3"],
+            subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", *CMD[CMD.index("--profile") + 1:]],
                            check=True, stdout=f)
     subprocess.run(CMD, check=True, stdout=subprocess.DEVNULL)  # must exit 0 without ncu first
     raw = os.path.join(out, "launches_raw.csv")
@@ -165,9 +165,12 @@ if __name__ == "__main__":
     ap.add_argument("--no-bench", action="store_true", help="run: skip the plain 5-step bench line")
     ap.add_argument("--config", default="cfg2", help="bench.py --config to profile")
     ap.add_argument("--launches-only", action="store_true", help="run: stop after the launch list (no full-set pass)")
+    ap.add_argument("--mode", dest="mode_arg", type=int, default=None, help="bench.py --mode (pf_db_set_mode) for every run of this call")
     a = ap.parse_args()
     CONFIG = a.config
     CMD += ["--config", CONFIG]
+    if a.mode_arg is not None:
+        CMD += ["--mode", str(a.mode_arg)]
     if a.mode == "run":
         cmd_run(a.tag, a.no_bench, a.launches_only)
     else:
