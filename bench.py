@@ -484,6 +484,8 @@ def run_ours(args, cfg):
         memo_lookups, memo_hits = int(st.memo_lookups), int(st.memo_hits)
         probe_ms = float(st.probe_kernel_ms)
         n_launch = max(int(st.probe_launches), 1)
+        sectors, sliced_ms, sliced_pairs = int(st.sector_loads), float(st.sliced_kernel_ms), int(st.sliced_pairs)
+        n_sliced_launch = max(int(st.sliced_blocks), 1)  # one entry-depth launch per block on the hybrid path
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -496,26 +498,33 @@ def run_ours(args, cfg):
         if sliced:
             # one 32 B sector per row load (each answers one probe step for every node of the tile) + the
             # cached 8 B hash value per k-mer and pair
-            alg_bytes = 32 * probes
-            achieved = alg_bytes / (probe_ms * 1e-3) / 1e9 if probe_ms > 0 else 0.0
+            alg_bytes = 32 * sectors
+            achieved = alg_bytes / (sliced_ms * 1e-3) / 1e9 if sliced_ms > 0 else 0.0
             peaks = {}
             for name, nbytes in (("one_entry_table_460MB", int(info.words_per_filter) * 8 * 256),
-                                 ("all_tables", min(int(st.sliced_table_bytes), 48 << 30))):
+                                 ("all_tables", min(max(int(st.sliced_table_bytes), 1 << 20), 48 << 30))):
                 _lib.check(L.pf_microbench_sectors(local_rank, max(nbytes, 1 << 20), 60, C.byref(rate)))
                 peaks[name] = rate.value
             rs_peak = peaks["one_entry_table_460MB"]
+            sect_rate = sectors / (sliced_ms * 1e-3) if sliced_ms > 0 else 0.0
             roofline = {
                 "bound": "hbm", "kernel": "sliced_probe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "note": "random 32 B row gathers over tables far larger than L2: the binding roof is the random-sector rate "
                         "of HBM (micro-benchmark below, same footprint), about 1/5 of the streaming-copy peak in `peak`",
-                "algorithmic_bytes_per_launch": alg_bytes / n_launch, "launches_per_step": int(st.probe_launches) // steps,
-                "avg_launch_ms": probe_ms / n_launch,
-                "kernel_share_of_step": probe_ms / float(st.device_ms) if st.device_ms else None,
-                "sectors_per_s": probes / (probe_ms * 1e-3) if probe_ms > 0 else 0.0,
+                "algorithmic_bytes_per_launch": alg_bytes / n_sliced_launch, "launches_per_step": n_sliced_launch // steps,
+                "avg_launch_ms": sliced_ms / n_sliced_launch,
+                "kernel_share_of_step": sliced_ms / float(st.device_ms) if st.device_ms else None,
+                "sectors_per_s": sect_rate,
                 "random_sector_peak_per_s": peaks,
-                "frac_of_random_sector_peak": (probes / (probe_ms * 1e-3)) / rs_peak if probe_ms > 0 and rs_peak else None,
+                "frac_of_random_sector_peak": sect_rate / rs_peak if rs_peak else None,
                 "tiles": int(st.sliced_tiles), "table_bytes": int(st.sliced_table_bytes),
+                "handed_over_to_probe_kernel": {
+                    "note": "reads the tiles could not rule out continue node by node (probe_kernel, L2-resident filters)",
+                    "pairs_per_step": (pairs - sliced_pairs) // steps, "probes_per_step": probes // steps,
+                    "memo_lookups_per_step": memo_lookups // steps, "kernel_ms_per_step": probe_ms / steps,
+                    "share_of_step": probe_ms / float(st.device_ms) if st.device_ms else None,
+                    "probes_per_s": (probes + memo_lookups) / (probe_ms * 1e-3) if probe_ms > 0 else 0.0},
             }
         else:
             # one 32 B sector per probe issued (and per k-mer memo look-up) + the 2-bit read per pair
@@ -592,7 +601,8 @@ def run_ours(args, cfg):
                              if faithful else f"first {n_sample} reads, filters resident, all {cores} host threads",
                              "modes": modes},
             "work": {"pairs_per_step": pairs // steps,
-                     ("sector_loads_per_step" if sliced else "probes_issued_per_step"): probes // steps,
+                     "sector_loads_per_step": sectors // steps, "tile_pairs_per_step": sliced_pairs // steps,
+                     "probes_issued_per_step": probes // steps,
                      "memo_lookups_per_step": memo_lookups // steps, "memo_hits_per_step": memo_hits // steps,
                      "hits_last_step": n_hits,
                      "reference_semantics_probes_per_step": int(p_ref * args.reads),

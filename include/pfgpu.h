@@ -171,10 +171,13 @@ typedef struct pf_stats_t {
     uint64_t memo_hits;       /* k-mers answered by the k-mer memo instead of K - 1 probes (pf_db_set_memo) */
     uint64_t memo_lookups;    /* k-mers looked up in the memo (one 8-byte read each) */
     uint64_t sliced_blocks;   /* query calls evaluated on bit-sliced tiles (pf_db_set_mode); `pairs` are then (read, tile)
-                                 pairs and `probes_issued` the row (sector) loads, each answering a probe for a whole tile */
+                                 pairs (see sliced_pairs, sector_loads) */
     uint64_t sliced_tiles;    /* tiles of the current tiling */
     uint64_t sliced_table_bytes; /* HBM held by their tables */
     uint64_t chunk_splits;    /* times a chunk of reads was cut in half because its frontier outgrew the pair index */
+    uint64_t sector_loads;    /* row (32-byte sector) loads of the sliced kernel; `probes_issued` = bit probes of the node-at-a-time kernel */
+    uint64_t sliced_pairs;    /* (read, tile) pairs; `pairs` counts those and the (read, node) pairs */
+    double sliced_kernel_ms;  /* CUDA-event time of the sliced kernel's launches (`probe_kernel_ms`: the node-at-a-time kernel's) */
 } pf_stats_t;
 int pf_get_stats(pf_db *db, pf_stats_t *out);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can
@@ -197,6 +200,11 @@ int pf_db_set_lazy(pf_db *db, int on);
  * (about as much HBM again).  Results are identical in every mode.  The environment variable PF_MODE
  * (auto|pair|sliced) sets the initial value. */
 int pf_db_set_mode(pf_db *db, int mode);
+/* Sliced path, below the cut through the tree that every read is tested against.  0: tiles all the way down (about as much
+ * HBM again as the filters).  1: tiles for the cut only (a few hundred MB); the (read, node) pairs they cannot rule out are
+ * handed to the node-at-a-time descent.  -1 (default): 0 if the tables fit the free HBM, else 1.  Results are identical.
+ * Environment: PF_SLICED_HANDOVER=0|1. */
+int pf_db_set_handover(pf_db *db, int handover);
 /* 1 (default): k-mer memo at exact nodes.  BloomFilter::contains depends on a k-mer only through its 64-bit
  * hash_bytes value, so once a k-mer has passed all K probes at a node, every later occurrence of the same value at that
  * node within the block (sequencing depth: 30x in BASELINE config 2) is a hit after ONE table look-up instead of K - 1

@@ -111,6 +111,11 @@ class BloomTree:
         2 = bit-sliced tiles.  Results are identical in every mode."""
         _lib.check(_lib.lib().pf_db_set_mode(self._h, int(mode)))
 
+    def set_handover(self, handover: int) -> None:
+        """pf_db_set_handover: sliced path below the cut -- 0 tiles all the way down, 1 hand-over to the node-at-a-time
+        descent, -1 tiles if they fit the free HBM."""
+        _lib.check(_lib.lib().pf_db_set_handover(self._h, int(handover)))
+
     def set_frontier_cap(self, pairs: int) -> None:
         """pf_db_set_frontier_cap: chunks of reads whose frontier outgrows this many pairs are cut in half and redone."""
         _lib.check(_lib.lib().pf_db_set_frontier_cap(self._h, pairs))

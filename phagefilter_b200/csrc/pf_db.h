@@ -218,6 +218,7 @@ struct pf_db {
     DevBuf<uint8_t> pass;
     DevBuf<uint64_t> hb;                       // cached hash_bytes per k-mer of the current chunk
     DevBuf<uint32_t> idx0;                     // cached step-0 bit index per k-mer (m < 2^31)
+    DevBuf<uint8_t> read_flag;                 // hybrid hand-over: reads that go on node by node
     uint64_t hash_cache_bytes = 16ULL << 30;   // chunk reads so the cache stays below this
     pf_dev_batch own_batch;  // device copy used by pf_query_block
     // outputs: per-read hit lists as CSR, built on the device, returned through pinned host arrays
@@ -242,6 +243,7 @@ struct pf_db {
     // ---- bit-sliced tiles (pf_sliced.cu): 0 = choose per (threshold, read length) by cost model, 1 = node-at-a-time
     // descent only, 2 = sliced tiles only
     int mode = 0;
+    int handover = -1;  // sliced path below the cut: 0 tiles all the way down, 1 hand-over to the node-at-a-time descent, -1 tiles if they fit
     // L2 residency (access-policy window on the stream): bytes of L2 set aside for persisting lines, largest window, and
     // per level the range of filter slots its nodes use
     uint64_t l2_persist_bytes = 0, l2_window_max = 0;
@@ -251,6 +253,9 @@ struct pf_db {
     double related_share = -1.0;       // running estimate of the share of reads with at least one hit (-1: none yet)
     double plan_cost = 0.0;            // expected bit probes PER K-MER of a read unrelated to the database under the current step plan
     pf::SlicedState *sliced = nullptr;
+    // hand-over from the tiles to the node-at-a-time descent: (read, node) pairs, node-major, cut per level
+    const uint32_t *inj_read = nullptr, *inj_node = nullptr;
+    std::vector<uint64_t> inj_level_off;  // [n_levels + 1]; empty or all-equal: nothing to inject
     std::vector<uint8_t> nccl_id;      // ncclUniqueId handed to pf_db_open_sharded (the analysis at open is collective)
 };
 
@@ -262,7 +267,9 @@ struct Descent {
     int cur = 0;     // ping-pong buffer holding it
     uint64_t hits_total = 0, hits_before = 0, probes = 0, pairs = 0, levels = 0, probe_launches = 0, other_launches = 0;
     uint64_t memo_hits = 0, memo_lookups = 0;
+    uint64_t sectors = 0, sliced_pairs = 0;  // row loads and (read, tile) pairs of the sliced kernel
     size_t n_ev = 0;
+    std::vector<uint8_t> ev_sliced;          // per event pair: recorded around a sliced-kernel launch
 };
 int run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint32_t G, uint64_t kmer_base,
                size_t l_begin, size_t l_end, uint32_t inj_r0, uint32_t inj_n, Descent &st);
@@ -294,6 +301,7 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
 int sliced_begin_block(pf_db *db);
 int sliced_set_hit_cursor(pf_db *db, uint64_t hits);
 uint64_t sliced_entry_tiles(const pf_db *db);
+bool sliced_hybrid(const pf_db *db);
 int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint64_t kmer_base, uint32_t r0,
                uint32_t n_chunk, Descent &st);
 }  // namespace pf

@@ -902,6 +902,12 @@ static __global__ void csr_sort_kernel(const unsigned long long *__restrict__ of
     }
 }
 
+// flag[r] = 1 for every read that owns a pair of the list
+static __global__ void flag_reads_kernel(const uint32_t *__restrict__ reads, unsigned long long n, uint8_t *flag) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        flag[reads[i]] = 1;
+}
+
 static __global__ void zero_kernel(uint4 *p, size_t n16) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
         p[i] = make_uint4(0u, 0u, 0u, 0u);

@@ -105,6 +105,7 @@ void pf::db_free(pf_db *db) {
     db->pass.release();
     db->hb.release();
     db->idx0.release();
+    db->read_flag.release();
     db->read_hits.release();
     db->csr_leaf.release();
     db->csr_off.release();
@@ -738,8 +739,11 @@ void pf::account_stats(pf_db *db, const Descent &st, uint64_t n_reads, uint64_t 
     for (size_t e = 0; e + 1 < st.n_ev; e += 2) {
         float pm = 0.f;
         cudaEventElapsedTime(&pm, db->ev_probe[e], db->ev_probe[e + 1]);
-        db->stats.probe_kernel_ms += pm;
+        if (e / 2 < st.ev_sliced.size() && st.ev_sliced[e / 2]) db->stats.sliced_kernel_ms += pm;
+        else db->stats.probe_kernel_ms += pm;
     }
+    db->stats.sector_loads += st.sectors;
+    db->stats.sliced_pairs += st.sliced_pairs;
     db->stats.blocks++;
     db->stats.reads += n_reads;
     db->stats.pairs += st.pairs;
@@ -758,18 +762,29 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
                    size_t l_begin, size_t l_end, uint32_t inj_r0, uint32_t inj_n, Descent &st) {
     cudaStream_t s = db->stream;
     int rc;
+    // pairs handed over by the tiles (pf_sliced.cu) replace the plan's own entry nodes
+    const bool handed = !db->inj_level_off.empty() && db->inj_level_off.back() > db->inj_level_off.front();
     const size_t last_entry_level = [&] {
         size_t l = l_begin;
         for (size_t i = l_begin; i < l_end; ++i)
-            if (db->entry_start[i + 1] > db->entry_start[i]) l = i;
+            if (handed ? db->inj_level_off[i + 1] > db->inj_level_off[i] : db->entry_start[i + 1] > db->entry_start[i]) l = i;
         return l;
     }();
     for (size_t l = l_begin; l < l_end && (st.n > 0 || l <= last_entry_level); ++l) {
         const int cur = st.cur;
         uint64_t n = st.n;
         // entry nodes of this level: append (read, node) pairs for every read of the injected range
+        if (handed && db->inj_level_off[l + 1] > db->inj_level_off[l]) {
+            const uint64_t o = db->inj_level_off[l], add = db->inj_level_off[l + 1] - o;
+            if (n + add > db->frontier_cap) return PF_SPLIT_CHUNK;
+            if ((rc = db->fr_read[cur].grow_keep(n + add, n, s)) || (rc = db->fr_node[cur].grow_keep(n + add, n, s))) return rc;
+            PF_CUDA_OK(cudaMemcpyAsync(db->fr_read[cur].p + n, db->inj_read + o, add * 4, cudaMemcpyDeviceToDevice, s));
+            PF_CUDA_OK(cudaMemcpyAsync(db->fr_node[cur].p + n, db->inj_node + o, add * 4, cudaMemcpyDeviceToDevice, s));
+            n += add;
+            st.n = n;
+        }
         const uint32_t e0 = db->entry_start[l], n_entry = db->entry_start[l + 1] - e0;
-        if (n_entry && inj_n) {
+        if (n_entry && inj_n && !handed) {
             const uint64_t add = (uint64_t)inj_n * n_entry;
             if (n + add > db->frontier_cap) return PF_SPLIT_CHUNK;  // query_impl retries with fewer reads
             if ((rc = db->fr_read[cur].grow_keep(n + add, n, s)) || (rc = db->fr_node[cur].grow_keep(n + add, n, s)))
@@ -852,6 +867,7 @@ int pf::run_levels(pf_db *db, const pf_dev_batch *bt, float threshold, int want_
         launch_probe(a, G, db->sm_count, s);
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev + 1], s));
         st.n_ev += 2;
+        st.ev_sliced.push_back(0);
         st.probe_launches++;
         st.pairs += n;
         st.levels++;
@@ -921,6 +937,34 @@ int pf::finish_csr(pf_db *db, uint32_t n_reads, uint64_t hits_total, int want_hi
     if (hits_total) PF_CUDA_OK(cudaMemcpyAsync(db->pin_leaf.p, db->csr_leaf.p, hits_total * 4, cudaMemcpyDeviceToHost, s));
     *d2h += ((uint64_t)out_n + 1) * 8 + hits_total * 4;
     (void)out;
+    return PF_OK;
+}
+
+// Between the tiles and the node-at-a-time descent (hybrid evaluation): flag the reads that own a handed-over pair, give
+// them step-0 indices (hash kernel restricted to flagged reads), and make the running hit total the level scan continues
+// from equal to what the tiles have already emitted.
+static int hand_over(pf_db *db, const pf_dev_batch *bt, HashArgs h, uint64_t chunk_kmers, uint64_t kmer_base, uint32_t r0,
+                     uint32_t n_chunk, Descent &st) {
+    cudaStream_t s = db->stream;
+    int rc;
+    (void)kmer_base;
+    (void)n_chunk;
+    (void)r0;
+    const uint64_t n_inj = db->inj_level_off.back();
+    if (db->hp.small_m) {
+        if ((rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
+        if ((rc = db->read_flag.ensure(bt->n_reads))) return rc;
+        PF_CUDA_OK(cudaMemsetAsync(db->read_flag.p, 0, bt->n_reads, s));
+        flag_reads_kernel<<<(uint32_t)std::min<uint64_t>((n_inj + 255) / 256, 65535), 256, 0, s>>>(db->inj_read, n_inj, db->read_flag.p);
+        PF_CUDA_OK(cudaMemsetAsync(h.work_ctr, 0, 4, s));
+        h.idx0 = db->idx0.p;
+        h.flags = db->read_flag.p;
+        launch_hash(h, db->sm_count * 8, s);
+        st.other_launches += 2;
+    }
+    unsigned long long h64 = st.hits_total;
+    PF_CUDA_OK(cudaMemcpyAsync(&db->d_totals->hits_total, &h64, 8, cudaMemcpyHostToDevice, s));
+    PF_CUDA_OK(cudaStreamSynchronize(s));  // h64 lives on this stack frame
     return PF_OK;
 }
 
@@ -1015,8 +1059,22 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         }
         st.n = 0;
         st.cur = 0;
-        if (sliced) rc = run_sliced(db, bt, threshold, want_hits, kmer_base, r0, n_chunk, st);
-        else rc = run_levels(db, bt, threshold, want_hits, G, kmer_base, 0, n_levels, r0, n_chunk, st);
+        db->inj_level_off.clear();
+        if (sliced) {
+            // the tiles append hits through their own cursor: it continues where the block's hit list stands (earlier
+            // chunks may have added hits through the node-at-a-time descent after a hand-over)
+            if (r0 != 0 && (rc = sliced_set_hit_cursor(db, st.hits_total))) return rc;
+            rc = run_sliced(db, bt, threshold, want_hits, kmer_base, r0, n_chunk, st);
+            if (rc == PF_OK && sliced_hybrid(db) && !db->inj_level_off.empty() && db->inj_level_off.back() > 0) {
+                // the reads that survived the tiles go down the tree node by node.  That descent uses the step-0 bit indices
+                // next to the hash values; they are made now, for the surviving reads only.
+                rc = hand_over(db, bt, h, chunk_kmers, kmer_base, r0, n_chunk, st);
+                if (rc == PF_OK) rc = run_levels(db, bt, threshold, want_hits, G, kmer_base, 0, n_levels, r0, 0, st);
+                db->inj_level_off.clear();
+            }
+        } else {
+            rc = run_levels(db, bt, threshold, want_hits, G, kmer_base, 0, n_levels, r0, n_chunk, st);
+        }
         if (rc == PF_SPLIT_CHUNK) {
             if (n_chunk <= 1) {
                 set_error("one read alone produces a frontier beyond the 32-bit pair index");
@@ -1170,6 +1228,7 @@ int pf_db_open(const char *db_path, int device, int64_t search_depth, pf_db **ou
     pf_db *db = new pf_db();
     db->device = device;
     if (const char *m = getenv("PF_MODE")) db->mode = !strcmp(m, "pair") ? 1 : (!strcmp(m, "sliced") ? 2 : 0);
+    if (const char *m = getenv("PF_SLICED_HANDOVER")) db->handover = atoi(m) ? 1 : 0;
     int rc = db_open_impl(db, db_path, search_depth);
     if (rc != PF_OK) {
         std::string keep = g_error;
@@ -1250,6 +1309,14 @@ int pf_db_set_frontier_cap(pf_db *db, uint64_t pairs) {
         return PF_ERR_ARG;
     }
     db->frontier_cap = pairs;
+    return PF_OK;
+}
+int pf_db_set_handover(pf_db *db, int handover) {
+    if (!db || handover < -1 || handover > 1) {
+        set_error("pf_db_set_handover: -1, 0 or 1");
+        return PF_ERR_ARG;
+    }
+    db->handover = handover;
     return PF_OK;
 }
 int pf_db_set_mode(pf_db *db, int mode) {

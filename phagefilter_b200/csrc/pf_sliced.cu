@@ -42,6 +42,12 @@ struct SlicedState {
     unsigned long long *h_tile_base = nullptr;   // pinned [n_tiles]
     bool tables_ready = false;
     bool entry_lean = false;  // every entry tile is filter-only with a pre-test of at most 2 steps
+    // hybrid: tiles for the cut only; what survives them is handed to the node-at-a-time descent as (read, node) pairs
+    bool hybrid = true;
+    uint32_t *d_node_inj_count = nullptr, *d_node_inj_cursor = nullptr;  // contiguous [2 * n_nodes]
+    unsigned long long *d_node_inj_base = nullptr, *d_inj_bsum = nullptr;  // [n_nodes + 1], block sums of the scan
+    unsigned long long *h_node_inj_base = nullptr;                        // pinned copy
+    DevBuf<uint32_t> inj_read, inj_node;
     DevBuf<uint32_t> fr_read[2], fr_tile[2], fr_src[2], reach[2], alive;
     // what the plan was made for
     float theta = -1.f;
@@ -49,7 +55,9 @@ struct SlicedState {
     int decided_mode = 0;  // 1 pair, 2 sliced (for theta / n_nominal above)
     int decided_under = -1;  // pf_db_set_mode value the decision was taken under
     double decided_rho = 0.5; // related share the decision was taken for
+    int decided_handover = -2; // pf_db_set_handover value the decision was taken under
     bool failed = false;   // tables could not be built (memory): stay with the node-at-a-time path
+    bool deep_failed = false;  // the full set of tables did not fit: cut-only tiles with hand-over from now on
 };
 
 static void sliced_release_device(SlicedState *s) {
@@ -62,6 +70,13 @@ static void sliced_release_device(SlicedState *s) {
     cudaFree(s->d_tile_base);
     cudaFree(s->d_counters);
     cudaFree(s->d_work);
+    cudaFree(s->d_node_inj_count);
+    cudaFree(s->d_node_inj_base);
+    cudaFree(s->d_inj_bsum);
+    if (s->h_node_inj_base) cudaFreeHost(s->h_node_inj_base);
+    s->d_node_inj_count = s->d_node_inj_cursor = nullptr;
+    s->d_node_inj_base = s->d_inj_bsum = nullptr;
+    s->h_node_inj_base = nullptr;
     if (s->h_tile_count) cudaFreeHost(s->h_tile_count);
     if (s->h_counters) cudaFreeHost(s->h_counters);
     if (s->h_tile_base) cudaFreeHost(s->h_tile_base);
@@ -85,6 +100,8 @@ void sliced_free(pf_db *db) {
         s->reach[i].release();
     }
     s->alive.release();
+    s->inj_read.release();
+    s->inj_node.release();
     delete s;
     db->sliced = nullptr;
 }
@@ -171,7 +188,7 @@ static void tree_facts(const pf_db *db, float threshold, uint64_t n_nominal, Tre
 //    die there touch few tiles; sparse subtrees are packed whole, several per tile, so a read that survives needs one
 //    more tile.
 // Also fills the cost model: expected seconds of sector loads for a read unrelated to the database.
-static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
+static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool entry_only, double pair_related_s) {
     const size_t nn = db->n_nodes;
     const uint32_t K = db->geom.num_hashes;
     S.tiles.clear();
@@ -279,6 +296,7 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
                 tm.parent[c] = 0xFFFFu;
                 tm.leaf[c] = -1;
             }
+            for (size_t c = 0; c < (size_t)SL_MAX_COLS; ++c) tm.child_node[c][0] = tm.child_node[c][1] = NONE32;
             if (job.parent_tile >= 0) {
                 S.child_tile.push_back(t);
                 S.child_mask.insert(S.child_mask.end(), link_mask, link_mask + 8);
@@ -301,15 +319,18 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
             for (size_t c = 0; c < made[k].size(); ++c) {
                 const uint32_t u = made[k][c];
                 bool term = db->h_leaf[u] >= 0;
+                int k = 0;
+                S.tiles[t].child_node[c][0] = S.tiles[t].child_node[c][1] = NONE32;
                 for (uint32_t ch : {db->h_left[u], db->h_right[u]})
                     if (ch != NONE32 && node_tile[ch] != (int32_t)t) {
                         term = true;
                         nj.roots.push_back(ch);
+                        if (entry_only) S.tiles[t].child_node[c][k++] = ch;
                     }
                 if (term) S.tiles[t].terminal[c >> 5] |= 1u << (c & 31);
             }
             std::sort(nj.roots.begin(), nj.roots.end());
-            if (!nj.roots.empty()) jobs.push_back(std::move(nj));
+            if (!nj.roots.empty() && !entry_only) jobs.push_back(std::move(nj));
         }
     }
     // Cost model (steers choices only, never results).  A read unrelated to the database leaves a tile once every
@@ -339,9 +360,15 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
                 reach = 1.0 - none;
             }
             double fmax = 0.0;  // the terminal that holds out longest is the fullest one
+            std::vector<double> tf;
             for (uint32_t c = 0; c < tm.n_cols; ++c)
-                if ((tm.terminal[c >> 5] >> (c & 31)) & 1u) fmax = std::max(fmax, F.fill[S.tile_nodes[t][c]]);
+                if ((tm.terminal[c >> 5] >> (c & 31)) & 1u) {
+                    fmax = std::max(fmax, F.fill[S.tile_nodes[t][c]]);
+                    tf.push_back(F.fill[S.tile_nodes[t][c]]);
+                }
             fmax = std::min(fmax, 0.999999);
+            std::sort(tf.begin(), tf.end());
+            const double f90 = tf.empty() ? fmax : std::min(tf[(tf.size() * 9) / 10 == tf.size() ? tf.size() - 1 : (tf.size() * 9) / 10], 0.999999);
             auto kmers_to_die = [&](uint32_t s) {  // k-mers until the fullest terminal is ruled out, or -1: it survives
                 const double r = 1.0 - pow(fmax, (double)s);
                 const double j = (a1 + 2.0 * sqrt(a1 * (1.0 - r))) / r;
@@ -373,12 +400,37 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
             }
             tm.pre_steps = best_s;
             tm.filter_only = best_s != 0 && filt_ok;
-            tm.pre_rounds = (uint32_t)std::min(4.0, std::max(1.0, ceil(best_j / 32.0)));
+            {   // rounds in flight before the first look at the columns: when 90 % of the terminals are expected to be settled
+                double j90 = 0.0;
+                if (best_s) {
+                    const double r = 1.0 - pow(f90, (double)best_s);
+                    j90 = (a1 + sqrt(a1 * (1.0 - r))) / r;
+                }
+                tm.pre_rounds = (uint32_t)std::min(4.0, std::max(1.0, floor(j90 / 32.0 + 0.75)));
+            }
+            (void)best_j;
             const double bytes = (double)(64ULL * db->wpf) * tm.row_words * 4.0;
             // entry tiles are worked tile-major, one table hot at a time; deeper tiles are touched at random
             const double rate = tm.entry ? sector_rate(bytes) : sector_rate(1e12);
             total_s += reach * best_unrel / rate;
             total_sectors += reach * best_unrel;
+            if (entry_only) {
+                // what the tile cannot rule out goes to the node-at-a-time descent: two (read, child) pairs per surviving
+                // terminal column, each a cheap sampled test there (~32 probes at the L2 rate)
+                const double r_s = best_s ? 1.0 : 0.0;
+                for (uint32_t c = 0; c < tm.n_cols; ++c) {
+                    if (!((tm.terminal[c >> 5] >> (c & 31)) & 1u)) continue;
+                    const uint32_t u = S.tile_nodes[t][c];
+                    double surv = F.q[u];
+                    if (r_s > 0.0) {
+                        const double r = 1.0 - pow(std::min(F.fill[u], 0.999999), (double)best_s);
+                        const double mean = n * r, var = n * r * (1.0 - r);
+                        surv = var < 1e-9 ? (mean > F.allowed ? 0.0 : 1.0) : phi_tab((F.allowed + 0.5 - mean) / sqrt(var));
+                        if (!tm.filter_only) surv = std::min(surv, F.q[u]);
+                    }
+                    total_s += reach * surv * 2.0 * 32.0 / 240e9;
+                }
+            }
         }
         S.est_sectors_per_read = total_sectors;
         S.est_seconds_per_read = total_s;
@@ -391,7 +443,7 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
                 const double bytes = (double)(64ULL * db->wpf) * tm.row_words * 4.0;
                 worst_entry += (n * (double)tm.pre_steps + (tm.filter_only ? 0.0 : n * (double)K)) / sector_rate(bytes);
             }
-            S.est_seconds_related = worst_entry + (double)max_depth * n * (double)K / sector_rate(1e12);
+            S.est_seconds_related = worst_entry + (entry_only ? pair_related_s : (double)max_depth * n * (double)K / sector_rate(1e12));
         }
     }
 }
@@ -403,6 +455,8 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S) {
 static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, SlicedState &S) {
     TreeFacts F;
     tree_facts(db, threshold, n_nominal, F);
+    // a related read in the node-at-a-time descent: one exact leaf plus two cheap sampled tests per level
+    const double pair_related_s = ((double)n_nominal * (double)db->geom.num_hashes + 32.0 * (double)(db->level_start.size() - 1)) / 240e9;
     const size_t nn = db->n_nodes;
     std::vector<uint64_t> cand{~0ULL};
     for (double g = (double)std::max<uint64_t>(db->n_leaves, 1); g >= 1.0; g /= 1.4142135623730951) {
@@ -421,7 +475,8 @@ static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, Sli
         }
         if (have && T.skip == prev_skip) continue;
         prev_skip = T.skip;
-        tile_tree(db, F, T);
+        T.hybrid = S.hybrid;
+        tile_tree(db, F, T, S.hybrid, pair_related_s);
         if (getenv("PF_SLICED_DEBUG"))
             fprintf(stderr, "[sliced plan] G=%llu skipped=%zu entry_tiles=%zu tiles=%zu est=%.2f ns/read (%.0f sectors)\n",
                     (unsigned long long)G, (size_t)std::count(T.skip.begin(), T.skip.end(), 1), T.entry_tiles.size(),
@@ -476,6 +531,14 @@ static int build_tables(pf_db *db, SlicedState &S) {
     PF_CUDA_OK(cudaMalloc(&S.d_counters, 4 * 8));
     S.d_hit_cursor = S.d_counters + 3;
     PF_CUDA_OK(cudaMalloc(&S.d_work, 4));
+    {
+        const size_t nn = db->n_nodes;
+        PF_CUDA_OK(cudaMalloc(&S.d_node_inj_count, 2 * nn * 4));
+        S.d_node_inj_cursor = S.d_node_inj_count + nn;
+        PF_CUDA_OK(cudaMalloc(&S.d_node_inj_base, (nn + 1) * 8));
+        PF_CUDA_OK(cudaMalloc(&S.d_inj_bsum, ((nn + 1023) / 1024 + 1) * 8));
+        PF_CUDA_OK(cudaMallocHost(&S.h_node_inj_base, (nn + 1) * 8));
+    }
     PF_CUDA_OK(cudaMallocHost(&S.h_tile_count, nt * 4));
     PF_CUDA_OK(cudaMallocHost(&S.h_counters, 4 * 8));
     PF_CUDA_OK(cudaMallocHost(&S.h_tile_base, nt * 8));
@@ -518,6 +581,7 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
     // already answered (hits per read, capped at 1) and starts at 1/2
     const double rho = db->related_share < 0 ? 0.5 : db->related_share;
     if (S.decided_mode && S.theta == threshold && S.n_nominal == n_nominal && S.decided_under == db->mode &&
+        S.decided_handover == db->handover &&
         (db->mode != 0 || fabs(rho - S.decided_rho) <= 0.1)) {
         *use_sliced = S.decided_mode == 2;
         if (*use_sliced) {
@@ -527,6 +591,11 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
         return PF_OK;
     }
     SlicedState P;  // plan into a scratch state first: the tables are rebuilt only if the tiling changed
+    // Below the cut: tiles all the way down (default), or -- pf_db_set_handover / PF_SLICED_HANDOVER=1, and automatically
+    // when the full set of tables does not fit the free HBM -- tiles for the cut only, whose survivors are handed to the
+    // node-at-a-time descent.  Measured equal on cfg3 (47 ms either way: a read that belongs touches a cold 1.8 MB leaf
+    // filter or a cold table, HBM-bound both ways) and slower on 10 kb reads (114 vs 79 ms), at 1 GB instead of 36 GB.
+    P.hybrid = db->handover == 1 || S.deep_failed;
     plan_tiles(db, threshold, n_nominal, P);
     bool sliced = db->mode == 2;
     if (db->mode == 0) {
@@ -550,8 +619,9 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
     S.decided_mode = sliced ? 2 : 1;
     S.decided_under = db->mode;
     S.decided_rho = rho;
+    S.decided_handover = db->handover;
     if (!sliced) return PF_OK;
-    const bool same = S.tables_ready && S.skip == P.skip && S.tiles.size() == P.tiles.size();
+    const bool same = S.tables_ready && S.skip == P.skip && S.tiles.size() == P.tiles.size() && S.hybrid == P.hybrid;
     if (same) {
         // same tiling, possibly other pre-test depths (they follow the threshold and the read length): refresh the tile records
         for (size_t t = 0; t < S.tiles.size(); ++t) {
@@ -574,12 +644,20 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
         S.entry_tiles = std::move(P.entry_tiles);
         S.tile_parent = std::move(P.tile_parent);
         S.tile_nodes = std::move(P.tile_nodes);
+        S.hybrid = P.hybrid;
         S.table_words = P.table_words;
         S.entry_bytes = P.entry_bytes;
         S.est_sectors_per_read = P.est_sectors_per_read;
         S.est_seconds_per_read = P.est_seconds_per_read;
         S.est_seconds_related = P.est_seconds_related;
         int rc = build_tables(db, S);
+        if (rc == PF_ERR_NOMEM && !S.hybrid && db->handover != 0) {
+            // not enough HBM for tiles all the way down: keep the tiles of the cut only and hand their survivors over
+            sliced_release_device(&S);
+            S.deep_failed = true;
+            S.decided_mode = 0;
+            return sliced_prepare(db, threshold, n_nominal, use_sliced);
+        }
         if (rc != PF_OK) {
             sliced_release_device(&S);
             S.failed = true;
@@ -599,6 +677,7 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
 }
 
 uint64_t sliced_entry_tiles(const pf_db *db) { return db->sliced ? db->sliced->entry_tiles.size() : 0; }
+bool sliced_hybrid(const pf_db *db) { return db->sliced && db->sliced->hybrid; }
 
 template <int PW>
 static void launch_sliced(const SlicedArgs &a, int sm_count, bool lean, cudaStream_t s) {
@@ -652,6 +731,10 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
         a.hp = db->hp;
         a.threshold = threshold;
         a.grab = bt->max_kmers <= 256 ? 4u : 1u;
+        if (S.hybrid) {
+            PF_CUDA_OK(cudaMemsetAsync(S.d_node_inj_count, 0, 2 * db->n_nodes * 4, s));
+            a.node_inj_count = S.d_node_inj_count;
+        }
         while (db->ev_probe.size() < st.n_ev + 2) {
             cudaEvent_t e;
             PF_CUDA_OK(cudaEventCreate(&e));
@@ -665,13 +748,15 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
         else launch_sliced<32>(a, db->sm_count, lean, s);
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev + 1], s));
         st.n_ev += 2;
+        st.ev_sliced.push_back(1);
         st.probe_launches++;
         st.pairs += n;
+        st.sliced_pairs += n;
         st.levels++;
         PF_CUDA_OK(cudaMemcpyAsync(S.h_counters, S.d_counters, 3 * 8, cudaMemcpyDeviceToHost, s));
         PF_CUDA_OK(cudaMemcpyAsync(S.h_tile_count, S.d_tile_count, nt * 4, cudaMemcpyDeviceToHost, s));
         PF_CUDA_OK(cudaStreamSynchronize(s));
-        st.probes += S.h_counters[0];
+        st.sectors += S.h_counters[0];
         const uint64_t n_alive = S.h_counters[1], hits = S.h_counters[2];
         uint64_t next_n = 0;
         for (size_t t = 0; t < nt; ++t) {
@@ -680,6 +765,27 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
         }
         if (next_n > db->frontier_cap) return PF_SPLIT_CHUNK;
         const int nxt = cur ^ 1;
+        uint64_t n_inj = 0;
+        if (S.hybrid && n_alive) {
+            // exclusive scan of the per-node hand-over counts: nodes are numbered level by level, so the offsets at the
+            // level boundaries cut the (read, node) list into per-level, node-major slices
+            const uint32_t nn = (uint32_t)db->n_nodes, nb = (nn + 1023u) / 1024u;
+            csr_block_sums_kernel<<<nb, 1024, 0, s>>>(S.d_node_inj_count, nn, S.d_inj_bsum);
+            csr_scan_sums_kernel<<<1, 1024, 0, s>>>(S.d_inj_bsum, nb);
+            csr_offsets_kernel<<<nb, 1024, 0, s>>>(S.d_node_inj_count, nn, S.d_inj_bsum, S.d_node_inj_base);
+            st.other_launches += 3;
+            PF_CUDA_OK(cudaMemcpyAsync(S.h_node_inj_base, S.d_node_inj_base, ((size_t)nn + 1) * 8, cudaMemcpyDeviceToHost, s));
+            PF_CUDA_OK(cudaStreamSynchronize(s));
+            n_inj = S.h_node_inj_base[nn];
+            if (n_inj > db->frontier_cap) return PF_SPLIT_CHUNK;
+            if (n_inj && ((rc = S.inj_read.ensure(n_inj)) || (rc = S.inj_node.ensure(n_inj)))) return rc;
+        }
+        db->inj_level_off.assign(db->level_start.size(), 0);
+        if (n_inj) {
+            for (size_t l = 0; l < db->level_start.size(); ++l) db->inj_level_off[l] = S.h_node_inj_base[db->level_start[l]];
+            db->inj_read = S.inj_read.p;
+            db->inj_node = S.inj_node.p;
+        }
         if (n_alive) {
             if (next_n && ((rc = S.fr_read[nxt].ensure(next_n)) || (rc = S.fr_tile[nxt].ensure(next_n)) ||
                            (rc = S.fr_src[nxt].ensure(next_n))))
@@ -712,6 +818,12 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
             e.hit_cursor = S.d_hit_cursor;
             e.blk_counts = db->d_blk_counts;
             e.want_hits = want_hits;
+            if (n_inj) {
+                e.node_inj_base = S.d_node_inj_base;
+                e.node_inj_cursor = S.d_node_inj_cursor;
+                e.inj_read = S.inj_read.p;
+                e.inj_node = S.inj_node.p;
+            }
             const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_alive + 7) / 8, (uint64_t)db->sm_count * 8);
             sliced_emit_kernel<<<blocks, 256, 0, s>>>(e);
             st.other_launches++;

@@ -35,6 +35,7 @@ struct SlicedTileDev {
     uint32_t leafmask[8]; // columns that are tree leaves
     uint16_t parent[SL_MAX_COLS];  // in-tile parent column; roots: 0x8000 | column in the parent tile (entry: 0xFFFF)
     int32_t leaf[SL_MAX_COLS];     // left-first DFS leaf index (query.rs:197-218) or -1
+    uint32_t child_node[SL_MAX_COLS][2];  // tree nodes below a column that are NOT in this tile (node-at-a-time hand-over), or NONE
 };
 
 struct SlicedArgs {
@@ -58,6 +59,7 @@ struct SlicedArgs {
     uint32_t *reach;             // [n_pairs][8] columns reached AND passed (written for pairs listed in `alive`)
     uint32_t *alive;             // indices of the pairs with a hit or a successor, any order
     uint32_t *tile_count;        // per tile: pairs the next depth will hold
+    uint32_t *node_inj_count;    // hand-over to the node-at-a-time descent: per tree node, (read, node) pairs to inject; or null
     unsigned long long *counters;  // [0] sectors loaded, [1] alive pairs, [2] leaf hits
     unsigned int *work_ctr;
     HashParams hp;
@@ -271,12 +273,14 @@ PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ tab
                           uint32_t n_k, uint32_t need, uint32_t rounds, uint32_t lane, const uint32_t (&term)[RW],
                           uint32_t term_mine, uint32_t &alive_mine, uint32_t (&live)[RW], uint32_t (&acc)[PW],
                           uint32_t &sectors) {
-    rounds = min(max(rounds, 1u), (uint32_t)RB);  // the plan expects reads to be settled after about this many rounds
+    // the plan expects a typical unrelated read to be settled after `rounds` rounds: that many are in flight first, then
+    // the columns are re-examined after every further round (the gather is throughput-bound, not latency-bound)
+    rounds = min(max(rounds, 1u), (uint32_t)RB);
     const bool allowed0 = need == n_k;
     const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
 #pragma unroll
     for (int pl = 0; pl < PW; ++pl) acc[pl] = 0u;
-    for (uint32_t base = 0; base < n_k; base += 32u * rounds) {
+    for (uint32_t base = 0; base < n_k; base += 32u * rounds, rounds = 1u) {
         uint64_t hbv[RB];
         bool have[RB];
 #pragma unroll
@@ -496,6 +500,18 @@ PF_D void sl_pair_and_record(const SlicedArgs &a, const SlicedTileDev *__restric
         for (int w = 0; w < RW; ++w) t |= reach[w] & ldg32(cm + w);
         if (t) atomicAdd(a.tile_count + ldg32(a.child_tile + tm->first_child + c), 1u);
     }
+    if (a.node_inj_count) {
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            if (!((reach[w] & tm->terminal[w]) >> lane & 1u)) continue;
+            const uint32_t c = 32u * w + lane;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t ch = tm->child_node[c][k];
+                if (ch != NONE32_D) atomicAdd(a.node_inj_count + ch, 1u);
+            }
+        }
+    }
 }
 
 // Persistent grid; a warp takes `grab` consecutive pairs per ticket and works them one after the other.
@@ -556,6 +572,10 @@ struct SlicedEmitArgs {
     unsigned long long *hit_cursor;  // next free slot of the hit list
     unsigned long long *blk_counts;
     int want_hits;
+    // hand-over to the node-at-a-time descent: (read, node) pairs, node-major (null: tiles all the way down)
+    const unsigned long long *node_inj_base;
+    uint32_t *node_inj_cursor;
+    uint32_t *inj_read, *inj_node;
 };
 static __global__ void sliced_emit_kernel(const SlicedEmitArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -606,6 +626,21 @@ static __global__ void sliced_emit_kernel(const SlicedEmitArgs a) {
                 a.nx_read[p] = r;
                 a.nx_tile[p] = ct;
                 a.nx_src[p] = i;
+            }
+        }
+        if (a.node_inj_base) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                if (!((reach[w] & tm->terminal[w]) >> lane & 1u)) continue;
+                const uint32_t c = 32u * w + lane;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint32_t ch = tm->child_node[c][k];
+                    if (ch == NONE32_D) continue;
+                    const unsigned long long p = a.node_inj_base[ch] + atomicAdd(a.node_inj_cursor + ch, 1u);
+                    a.inj_read[p] = r;
+                    a.inj_node[p] = ch;
+                }
             }
         }
     }

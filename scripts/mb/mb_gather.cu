@@ -74,6 +74,16 @@ int main(int argc, char **argv) {
     if (argc > 1) { mbs.clear(); for (int i = 1; i < argc; ++i) mbs.push_back(atof(argv[i])); }
     double maxmb = 0;
     for (double m : mbs) if (m > maxmb) maxmb = m;
+    if (const char *g = getenv("MB_L2_FETCH")) {  // cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "L2 fetch granularity: asked %s, %s, now %zu\n", g, cudaGetErrorString(e), got);
+    } else {
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "L2 fetch granularity (default): %zu\n", got);
+    }
     uint32_t *buf = nullptr, *sink = nullptr;
     const uint64_t cap = (uint64_t)(maxmb * 1048576.0) + 4096;
     if (cudaMalloc(&buf, cap) != cudaSuccess || cudaMalloc(&sink, 4) != cudaSuccess) { fprintf(stderr, "alloc failed\n"); return 1; }

@@ -81,7 +81,9 @@ def main():
                  "build_s": round(t_build, 1), "save_s": round(t_save, 1), "open_s": round(t_open, 1),
                  "wall_ms": round(wall * 1e3, 1), "device_ms": round(st.device_ms, 1), "probe_ms": round(st.probe_kernel_ms, 1),
                  "reads_per_s_wall": round(a.reads / wall), "pairs": int(st.pairs), "probes": int(st.probes_issued),
-                 "probes_per_s": round(st.probes_issued / (st.probe_kernel_ms * 1e-3)), "hits": int(len(leaf)),
+                 "probes_per_s": round(st.probes_issued / max(st.probe_kernel_ms * 1e-3, 1e-9)), "hits": int(len(leaf)),
+                 "sectors": int(st.sector_loads), "sliced_ms": round(st.sliced_kernel_ms, 1), "tile_pairs": int(st.sliced_pairs),
+                 "sectors_per_s": round(st.sector_loads / max(st.sliced_kernel_ms * 1e-3, 1e-9)),
                  "group_rounds": int(st.group_rounds), "lazy": not a.exact, "mode": mode,
                  "sliced_blocks": int(st.sliced_blocks), "tiles": int(st.sliced_tiles), "table_gb": round(st.sliced_table_bytes / 1e9, 2),
                  "levels_run": int(st.levels)}

@@ -17,11 +17,12 @@ def _check(oracle, ot, gt, reads, theta):
     want = ot.query_batch(reads, theta)
     sched = ot.query_sched(reads, theta, lazy=True)
     # bit-sliced tiles, then whatever the cost model picks
-    for mode in (2, 0):
+    for mode, handover in ((2, 0), (2, 1), (0, -1)):
         gt.set_mode(mode)
+        gt.set_handover(handover)
         gt.reset_counts()
-        assert gpu_query(gt, reads, theta) == want.hit_sets(len(reads)), mode
-        assert get_leaf_counts(gt) == ot.leaf_counts(), mode
+        assert gpu_query(gt, reads, theta) == want.hit_sets(len(reads)), (mode, handover)
+        assert get_leaf_counts(gt) == ot.leaf_counts(), (mode, handover)
     gt.set_mode(1)  # node-at-a-time descent: work counts are predicted by the oracle's restatement of its schedule
     gt.reset_counts()
     gt.reset_stats()

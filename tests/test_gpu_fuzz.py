@@ -64,11 +64,12 @@ def test_fuzz(oracle, tmp_path, seed):
         ot.reset_counts()
         ref = ot.query_batch(reads, theta)
         want = ref.hit_sets(len(reads))
-        for mode in (2, 0):  # bit-sliced tiles; the cost model's choice
+        for mode, handover in ((2, 0), (2, 1), (0, -1)):  # tiles all the way down; tiles + hand-over; the cost model's choice
             gt.set_mode(mode)
+            gt.set_handover(handover)
             gt.reset_counts()
-            assert gpu_query(gt, reads, theta) == want, (seed, theta, "mode", mode)
-            assert get_leaf_counts(gt) == ot.leaf_counts(), (seed, theta, "mode", mode)
+            assert gpu_query(gt, reads, theta) == want, (seed, theta, "mode", mode, handover)
+            assert get_leaf_counts(gt) == ot.leaf_counts(), (seed, theta, "mode", mode, handover)
         gt.set_mode(1)  # node-at-a-time descent: the work counts below are its schedule's
         for lazy in (True, False):
             sched = ot.query_sched(reads, theta, lazy=lazy)

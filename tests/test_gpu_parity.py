@@ -35,6 +35,12 @@ def _compare(oracle, otree, gtree, reads, theta, check_probes=True):
     assert gpu_query(gtree, reads, theta) == want, "sliced"
     assert get_leaf_counts(gtree) == otree.leaf_counts(), "sliced"
     assert gtree.stats().sliced_blocks == 1
+    # the same with tiles for the cut only and the survivors handed to the node-at-a-time descent
+    gtree.set_handover(1)
+    gtree.reset_counts()
+    assert gpu_query(gtree, reads, theta) == want, "sliced + hand-over"
+    assert get_leaf_counts(gtree) == otree.leaf_counts(), "sliced + hand-over"
+    gtree.set_handover(-1)
     # whatever the cost model picks
     gtree.set_mode(0)
     gtree.reset_counts()
@@ -328,6 +334,7 @@ def test_kmer_memo_deep_coverage(oracle, tmp_path):
     d = str(tmp_path / "db")
     ot = oracle_build_db(oracle, genomes, 20, d, largest=8000)
     gt = BloomTree.load(d)
+    gt.set_mode(1)  # the memo belongs to the node-at-a-time descent (with 3.7 MB tables the cost model would pick tiles here)
     reads, _ = simulate_reads(genomes, 12000, 150, seed=7, error_rates=(0.0, 0.01))
     rl = [r.tobytes() for r in reads] + [genomes[0][1][10:160].lower(), genomes[1][1][:150].replace(b"C", b"N", 2)]
     for theta in (1.0, 0.8):
@@ -362,8 +369,9 @@ def test_frontier_cap_splits_chunks(oracle, tmp_path):
     for theta in (1.0, 0.6):
         ot.reset_counts()
         want = ot.query_batch(reads, theta)
-        for mode in (1, 2):
+        for mode, handover in ((1, -1), (2, 0), (2, 1)):
             gt.set_mode(mode)
+            gt.set_handover(handover)
             gt.set_frontier_cap(0xFF000000)
             gt.reset_counts()
             assert gpu_query(gt, reads, theta) == want.hit_sets(len(reads))
