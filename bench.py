@@ -418,7 +418,9 @@ def run_ours(args, cfg):
         L.pf_batch_free(tree._h, b)
 
     tmax = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    per_rank = [tmax.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, tmax)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_all, e2e_ms_all = float(tmax[0]), float(tmax[1])
     total_reads = args.reads * world * args.steps
@@ -456,8 +458,16 @@ def run_ours(args, cfg):
         torch.cuda.synchronize()
         sq = time.perf_counter() - t0
         same = bool((soff == last_off[: n_sl + 1]).all() and (sleaf == last_leaf[: int(last_off[n_sl])]).all())
+        # and at -f 1.0, where the top of the tree is not skipped by the step plan, so that (read, node) pairs really cross
+        # between ranks at the cut: against the replicated tree's answer for the same reads at that threshold
+        from phagefilter_b200.query import query_packed
+        tree.set_mode(1)  # no new tiling for one cross-check block
+        roff, rleaf = query_packed(tree, sp, 1.0)
+        tree.set_mode(0 if args.mode is None else args.mode)
+        s1off, s1leaf = query_sharded(stree, sp, 1.0)
+        same = same and bool((s1off == roff).all() and (s1leaf == rleaf).all())
         si, ss = stree.shard_info(), stree.shard_stats()
-        flag = torch.tensor([1 if same else 0, int(ss.pairs_sent), int(ss.pairs_received)], dtype=torch.int64, device="cuda")
+        flag = torch.tensor([1 if same else 0, int(ss.pairs_sent), int(ss.pairs_received), int(ss.hits_sent)], dtype=torch.int64, device="cuda")
         mn = flag.clone()
         dist.all_reduce(mn, op=dist.ReduceOp.MIN)
         sm = flag.clone()
@@ -467,7 +477,8 @@ def run_ours(args, cfg):
         sharded_check = {"reads_per_rank": n_sl, "identical_to_replicated_on_every_rank": bool(int(mn[0]) == 1),
                          "cut_level": int(si.cut_level), "top_nodes": int(si.top_nodes),
                          "resident_filter_bytes_rank0": int(si.resident_bytes),
-                         "pairs_sent_all_ranks": int(sm[1]), "pairs_received_all_ranks": int(sm[2]),
+                         "thresholds": [theta, 1.0],
+                         "pairs_sent_all_ranks": int(sm[1]), "pairs_received_all_ranks": int(sm[2]), "hits_sent_all_ranks": int(sm[3]),
                          "reads_per_s_all_ranks": n_sl * world / float(tq[0]), "open_s_rank0": round(sopen, 2),
                          "note": "subtree-shard path (pf_db_open_sharded / pf_query_sharded): replicated top, subtrees owned "
                                  "by ranks, frontier and hits exchanged with NCCL; node-at-a-time descent"}
@@ -574,7 +585,8 @@ def run_ours(args, cfg):
         faithful = modes.get("faithful_lru10_block100_all_cores")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
-            "ms_per_step": ms_all / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_all / steps, "ms_per_step_by_rank": [float(t[0]) / steps for t in per_rank],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": cfg["name"].format(reads=args.reads), "config": args.config,
                        "reads_per_gpu_per_step": args.reads, "theta": theta,
