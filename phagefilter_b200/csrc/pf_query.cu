@@ -1019,7 +1019,10 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
             if (r1 <= r0) r1 = r0 + 1;
         }
         if (sliced) {  // (read, entry tile) pairs of a chunk are indexed with 32 bits
-            const uint64_t cap = std::max<uint64_t>(1, db->frontier_cap / std::max<uint64_t>(sliced_entry_tiles(db), 1));
+            // ... and every pair owns 32 B of column bits and a slot in the list of pairs with an output: 64 M pairs
+            // per chunk keep that at ~2.3 GB whatever the block size
+            const uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>(db->frontier_cap, 1ULL << 26) /
+                                                           std::max<uint64_t>(sliced_entry_tiles(db), 1));
             if (r1 - r0 > cap) r1 = r0 + (uint32_t)cap;
         }
         if (r1 - r0 > max_chunk_reads) r1 = r0 + max_chunk_reads;  // an earlier attempt overflowed the frontier
@@ -1217,7 +1220,7 @@ int pf::batch_upload_impl(pf_db *db, const pf_read_batch *in, pf_dev_batch *b, c
 extern "C" {
 
 const char *pf_last_error(void) { return g_error.c_str(); }
-const char *pf_version(void) { return "pfgpu 0.1 sm_100a"; }
+const char *pf_version(void) { return "pfgpu 0.2 sm_100a"; }
 
 int pf_db_open(const char *db_path, int device, int64_t search_depth, pf_db **out) {
     if (!db_path || !out) {

@@ -466,11 +466,19 @@ static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, Sli
     SlicedState best;
     bool have = false;
     std::vector<uint8_t> prev_skip;
-    for (uint64_t G : cand) {
+    // second family of cuts: by fill instead of by leaf count ("skip while the filter is fuller than phi") -- the fullest
+    // node of the cut decides how many k-mers an unrelated read needs, and subtrees of equal size differ in fill
+    const size_t n_by_leaves = cand.size();
+    for (int i = 19; i >= 2; --i) cand.push_back((uint64_t)i);  // phi = i / 20
+    for (size_t ci = 0; ci < cand.size(); ++ci) {
+        const uint64_t G = cand[ci];
+        const bool by_fill = ci >= n_by_leaves;
+        const double phi = by_fill ? (double)G / 20.0 : 0.0;
         SlicedState T;
         T.skip.assign(nn, 0);
         for (size_t u = 0; u < nn; ++u) {
-            if (db->h_leaf[u] >= 0 || !F.vb[u] || (uint64_t)F.leaves[u] <= G) continue;
+            if (db->h_leaf[u] >= 0 || !F.vb[u]) continue;
+            if (by_fill ? F.fill[u] <= phi : (uint64_t)F.leaves[u] <= G) continue;
             if (u == 0 || T.skip[F.parent[u]]) T.skip[u] = 1;
         }
         if (have && T.skip == prev_skip) continue;
@@ -478,8 +486,8 @@ static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, Sli
         T.hybrid = S.hybrid;
         tile_tree(db, F, T, S.hybrid, pair_related_s);
         if (getenv("PF_SLICED_DEBUG"))
-            fprintf(stderr, "[sliced plan] G=%llu skipped=%zu entry_tiles=%zu tiles=%zu est=%.2f ns/read (%.0f sectors)\n",
-                    (unsigned long long)G, (size_t)std::count(T.skip.begin(), T.skip.end(), 1), T.entry_tiles.size(),
+            fprintf(stderr, "[sliced plan] %s=%llu skipped=%zu entry_tiles=%zu tiles=%zu est=%.2f ns/read (%.0f sectors)\n",
+                    by_fill ? "G=phi*20" : "G", (unsigned long long)G, (size_t)std::count(T.skip.begin(), T.skip.end(), 1), T.entry_tiles.size(),
                     T.tiles.size(), T.est_seconds_per_read * 1e9, T.est_sectors_per_read);
         if (!have || T.est_seconds_per_read < best.est_seconds_per_read) {
             best = std::move(T);
@@ -503,8 +511,8 @@ static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, Sli
         fprintf(stderr, "[sliced plan] chosen: %zu tiles, %zu entry, tables %.2f GB, est %.2f ns/read\n", S.tiles.size(),
                 S.entry_tiles.size(), S.table_words * 4.0 / 1e9, S.est_seconds_per_read * 1e9);
         for (uint32_t t : S.entry_tiles)
-            fprintf(stderr, "[sliced plan]   entry tile %u: %u columns, row %u B, %u children, pre-test %u steps%s\n", t,
-                    S.tiles[t].n_cols, S.tiles[t].row_words * 4, S.tiles[t].n_children, S.tiles[t].pre_steps,
+            fprintf(stderr, "[sliced plan]   entry tile %u: %u columns, row %u B, %u children, pre-test %u steps, %u rounds first%s\n", t,
+                    S.tiles[t].n_cols, S.tiles[t].row_words * 4, S.tiles[t].n_children, S.tiles[t].pre_steps, S.tiles[t].pre_rounds,
                     S.tiles[t].filter_only ? " (filter only)" : "");
     }
 }
@@ -681,12 +689,16 @@ bool sliced_hybrid(const pf_db *db) { return db->sliced && db->sliced->hybrid; }
 
 template <int PW>
 static void launch_sliced(const SlicedArgs &a, int sm_count, bool lean, cudaStream_t s) {
-    if (lean) {
-        if (a.hp.small_m) sliced_probe_kernel<PW, true, true><<<sm_count * 3, SL_THREADS, 0, s>>>(a);
-        else sliced_probe_kernel<PW, false, true><<<sm_count * 3, SL_THREADS, 0, s>>>(a);
+    static const int lean_ctas = getenv("PF_SLICED_LEAN_CTAS") ? atoi(getenv("PF_SLICED_LEAN_CTAS")) : 3;
+    if (lean && lean_ctas == 3) {
+        if (a.hp.small_m) sliced_probe_kernel<PW, true, true, 3><<<sm_count * 3, SL_THREADS, 0, s>>>(a);
+        else sliced_probe_kernel<PW, false, true, 3><<<sm_count * 3, SL_THREADS, 0, s>>>(a);
+    } else if (lean) {
+        if (a.hp.small_m) sliced_probe_kernel<PW, true, true, 2><<<sm_count * 2, SL_THREADS, 0, s>>>(a);
+        else sliced_probe_kernel<PW, false, true, 2><<<sm_count * 2, SL_THREADS, 0, s>>>(a);
     } else {
-        if (a.hp.small_m) sliced_probe_kernel<PW, true, false><<<sm_count * 2, SL_THREADS, 0, s>>>(a);
-        else sliced_probe_kernel<PW, false, false><<<sm_count * 2, SL_THREADS, 0, s>>>(a);
+        if (a.hp.small_m) sliced_probe_kernel<PW, true, false, 2><<<sm_count * 2, SL_THREADS, 0, s>>>(a);
+        else sliced_probe_kernel<PW, false, false, 2><<<sm_count * 2, SL_THREADS, 0, s>>>(a);
     }
 }
 

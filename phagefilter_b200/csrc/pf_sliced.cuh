@@ -280,13 +280,15 @@ PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ tab
     const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
 #pragma unroll
     for (int pl = 0; pl < PW; ++pl) acc[pl] = 0u;
+    uint64_t hb_pre = 0ULL;  // hash value of the NEXT round, fetched while this batch's rows are in flight
+    bool pre_valid = false;
     for (uint32_t base = 0; base < n_k; base += 32u * rounds, rounds = 1u) {
         uint64_t hbv[RB];
         bool have[RB];
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             have[j] = (uint32_t)j < rounds && base + 32u * j + lane < n_k;
-            hbv[j] = have[j] ? sl_ld_stream(hbp + base + 32u * j + lane) : 0ULL;
+            hbv[j] = (j == 0 && pre_valid) ? hb_pre : (have[j] ? sl_ld_stream(hbp + base + 32u * j + lane) : 0ULL);
         }
         uint32_t rows[RB][ST][RW];
 #pragma unroll
@@ -305,6 +307,11 @@ PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ tab
                     ++sectors;
                 }
             }
+        }
+        {
+            const uint32_t nb = base + 32u * rounds;  // the batches after the first hold one round
+            hb_pre = nb + lane < n_k ? sl_ld_stream(hbp + nb + lane) : 0ULL;
+            pre_valid = true;
         }
         if (allowed0) {
             uint32_t t = 0u;
@@ -515,8 +522,8 @@ PF_D void sl_pair_and_record(const SlicedArgs &a, const SlicedTileDev *__restric
 }
 
 // Persistent grid; a warp takes `grab` consecutive pairs per ticket and works them one after the other.
-template <int PW, bool SMALL_M, bool LEAN>
-static __global__ void __launch_bounds__(SL_THREADS, LEAN ? 3 : 2) sliced_probe_kernel(const SlicedArgs a) {
+template <int PW, bool SMALL_M, bool LEAN, int CTAS>
+static __global__ void __launch_bounds__(SL_THREADS, CTAS) sliced_probe_kernel(const SlicedArgs a) {
     __shared__ uint32_t s_bits_all[SL_THREADS / 32][8];
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t *const s_bits = s_bits_all[threadIdx.x >> 5];
