@@ -11,6 +11,7 @@ largest configuration one GPU holds:
         the configuration), 10 % phage spike-in, 90 % background, -f 0.8
   cfg4  the cfg3 database vs 200,000 x 10 kb reads per step (5 steps = 1 M reads), -f 0.9
   cfg5  100,000 genomes, --largest-genome 450000 (162 GB replica): explicit only, hours of database build
+  cfg5s a fifth of cfg5 (20,000 genomes, 32 GB), same geometry, reads and threshold (-f 1.0)
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfgN] [--reads R]
 
@@ -64,6 +65,11 @@ CONFIGS = {
                  errors=(0.001,), background=0.9, seed_g=1003, seed_r=2004, steps=5, cpu_sample=400, lru_sample=100,
                  name="cfg4: 10000-genome gSBT (35.9 GB) vs {reads} x 10 kb reads per step (5 steps = 1 M reads), "
                       "10 % spike-in, -f 0.9"),
+    "cfg5s": dict(kind="synth", families=2_000, family_size=10, largest=450_000, theta=1.0, read_len=150, reads=5_000_000,
+                  errors=(0.0, 0.01), background=0.9, seed_g=1005, seed_r=2005, steps=10, cpu_sample=5_000, lru_sample=200,
+                  name="cfg5s (a fifth of cfg5: the same geometry, reads and threshold, 20000 genomes -- the greedy build of all "
+                       "100000 takes hours): 20000 synthetic genomes (--largest-genome 450000, 32 GB gSBT) vs {reads} x 150 bp "
+                       "reads per GPU per step, 10 % spike-in, -f 1.0"),
     "cfg5": dict(kind="synth", families=10_000, family_size=10, largest=450_000, theta=1.0, read_len=150, reads=5_000_000,
                  errors=(0.0, 0.01), background=0.9, seed_g=1005, seed_r=2005, steps=20, cpu_sample=5_000, lru_sample=200,
                  name="cfg5: 100000 synthetic genomes (--largest-genome 450000, 162 GB gSBT) vs {reads} x 150 bp reads "
@@ -496,7 +502,7 @@ def run_ours(args, cfg):
         probe_ms = float(st.probe_kernel_ms)
         n_launch = max(int(st.probe_launches), 1)
         sectors, sliced_ms, sliced_pairs = int(st.sector_loads), float(st.sliced_kernel_ms), int(st.sliced_pairs)
-        n_sliced_launch = max(int(st.sliced_blocks), 1)  # one entry-depth launch per block on the hybrid path
+        n_sliced_launch = max(int(st.sliced_launches), 1)  # one timed launch per tile-tree depth
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")

@@ -178,6 +178,7 @@ typedef struct pf_stats_t {
     uint64_t sector_loads;    /* row (32-byte sector) loads of the sliced kernel; `probes_issued` = bit probes of the node-at-a-time kernel */
     uint64_t sliced_pairs;    /* (read, tile) pairs; `pairs` counts those and the (read, node) pairs */
     double sliced_kernel_ms;  /* CUDA-event time of the sliced kernel's launches (`probe_kernel_ms`: the node-at-a-time kernel's) */
+    uint64_t sliced_launches; /* timed launches of the sliced kernels (one per tile-tree depth; the entry depth may be two kernels timed as one) */
 } pf_stats_t;
 int pf_get_stats(pf_db *db, pf_stats_t *out);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can

@@ -739,8 +739,13 @@ void pf::account_stats(pf_db *db, const Descent &st, uint64_t n_reads, uint64_t 
     for (size_t e = 0; e + 1 < st.n_ev; e += 2) {
         float pm = 0.f;
         cudaEventElapsedTime(&pm, db->ev_probe[e], db->ev_probe[e + 1]);
-        if (e / 2 < st.ev_sliced.size() && st.ev_sliced[e / 2]) db->stats.sliced_kernel_ms += pm;
-        else db->stats.probe_kernel_ms += pm;
+        if (e / 2 < st.ev_sliced.size() && st.ev_sliced[e / 2]) {
+            db->stats.sliced_kernel_ms += pm;
+            db->stats.sliced_launches++;
+        }
+        else {
+            db->stats.probe_kernel_ms += pm;
+        }
     }
     db->stats.sector_loads += st.sectors;
     db->stats.sliced_pairs += st.sliced_pairs;

@@ -42,6 +42,7 @@ struct SlicedState {
     unsigned long long *h_tile_base = nullptr;   // pinned [n_tiles]
     bool tables_ready = false;
     bool entry_lean = false;  // every entry tile is filter-only with a pre-test of at most 2 steps
+    uint32_t n_groupable = 0; // leading entry tiles of that kind (S.entry_tiles is ordered so that they come first)
     // hybrid: tiles for the cut only; what survives them is handed to the node-at-a-time descent as (read, node) pairs
     bool hybrid = true;
     uint32_t *d_node_inj_count = nullptr, *d_node_inj_cursor = nullptr;  // contiguous [2 * n_nodes]
@@ -538,7 +539,7 @@ static int build_tables(pf_db *db, SlicedState &S) {
     PF_CUDA_OK(cudaMalloc(&S.d_tile_base, nt * 8));
     PF_CUDA_OK(cudaMalloc(&S.d_counters, 4 * 8));
     S.d_hit_cursor = S.d_counters + 3;
-    PF_CUDA_OK(cudaMalloc(&S.d_work, 4));
+    PF_CUDA_OK(cudaMalloc(&S.d_work, 8));
     {
         const size_t nn = db->n_nodes;
         PF_CUDA_OK(cudaMalloc(&S.d_node_inj_count, 2 * nn * 4));
@@ -674,10 +675,19 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
             return PF_OK;                  // auto: stay with the node-at-a-time path
         }
     }
-    S.entry_lean = !S.entry_tiles.empty();
-    for (uint32_t t : S.entry_tiles)
-        S.entry_lean = S.entry_lean && S.tiles[t].filter_only && S.tiles[t].pre_steps >= 1 && S.tiles[t].pre_steps <= 2 &&
-                       S.tiles[t].pre_steps < db->geom.num_hashes;
+    // entry tiles that only filter with a 1- or 2-step pre-test come first: they can share one pass per read
+    {
+        auto groupable = [&](uint32_t t) {
+            return S.tiles[t].filter_only && S.tiles[t].pre_steps >= 1 && S.tiles[t].pre_steps <= 2 &&
+                   S.tiles[t].pre_steps < db->geom.num_hashes;
+        };
+        std::stable_partition(S.entry_tiles.begin(), S.entry_tiles.end(), groupable);
+        S.n_groupable = 0;
+        for (uint32_t t : S.entry_tiles) S.n_groupable += groupable(t) ? 1u : 0u;
+        S.entry_lean = !S.entry_tiles.empty() && S.n_groupable == S.entry_tiles.size();
+        PF_CUDA_OK(cudaMemcpyAsync(S.d_entry, S.entry_tiles.data(), S.entry_tiles.size() * 4, cudaMemcpyHostToDevice, db->stream));
+        PF_CUDA_OK(cudaStreamSynchronize(db->stream));
+    }
     db->stats.sliced_tiles = S.tiles.size();
     db->stats.sliced_table_bytes = S.table_words * 4ULL;
     *use_sliced = true;
@@ -716,7 +726,7 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
     while (n > 0) {
         if ((rc = S.reach[cur].ensure(n * 8)) || (rc = S.alive.ensure(n))) return rc;
         PF_CUDA_OK(cudaMemsetAsync(S.d_counters, 0, 3 * 8, s));
-        PF_CUDA_OK(cudaMemsetAsync(S.d_work, 0, 4, s));
+        PF_CUDA_OK(cudaMemsetAsync(S.d_work, 0, 8, s));
         PF_CUDA_OK(cudaMemsetAsync(S.d_tile_count, 0, 2 * nt * 4, s));
         SlicedArgs a{};
         a.fr_read = entry ? nullptr : S.fr_read[cur].p;
@@ -753,15 +763,34 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
             db->ev_probe.push_back(e);
         }
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev], s));
-        // entry depth: every tile filter-only with a 1- or 2-step pre-test (the usual plan) -> the lean instantiation
+        // Entry depth.  Tiles that only filter with a 1- or 2-step pre-test (the usual plan) share one pass per read, up to
+        // SL_GROUP tiles at a time (sliced_entry_group_kernel; short reads, two or more such tiles); the rest of the depth --
+        // or all of it -- goes pair by pair, with the lean instantiation when every tile is of that kind.
         const bool lean = entry && S.entry_lean && !getenv("PF_SLICED_NO_LEAN");
-        if (bt->max_kmers < 256) launch_sliced<8>(a, db->sm_count, lean, s);
-        else if (bt->max_kmers < 65536) launch_sliced<16>(a, db->sm_count, lean, s);
-        else launch_sliced<32>(a, db->sm_count, lean, s);
+        uint32_t n_grouped = 0;
+        if (entry && bt->max_kmers < 256 && S.n_groupable >= 2 && !getenv("PF_SLICED_NO_GROUP")) {
+            n_grouped = S.n_groupable;
+            const uint32_t n_groups = (n_grouped + SL_GROUP - 1) / SL_GROUP;
+            SlicedArgs g = a;
+            g.grab = 4u;
+            if (g.hp.small_m) sliced_entry_group_kernel<true><<<db->sm_count * 2, SL_THREADS, 0, s>>>(g, n_grouped, n_groups);
+            else sliced_entry_group_kernel<false><<<db->sm_count * 2, SL_THREADS, 0, s>>>(g, n_grouped, n_groups);
+            st.probe_launches++;
+        }
+        if (!entry || n_grouped < S.entry_tiles.size()) {
+            if (n_grouped) {
+                a.pair0 = n_grouped * n_chunk;
+                a.n_pairs = (uint32_t)(n - (uint64_t)n_grouped * n_chunk);
+                a.work_ctr = S.d_work + 1;
+            }
+            if (bt->max_kmers < 256) launch_sliced<8>(a, db->sm_count, lean, s);
+            else if (bt->max_kmers < 65536) launch_sliced<16>(a, db->sm_count, lean, s);
+            else launch_sliced<32>(a, db->sm_count, lean, s);
+            st.probe_launches++;
+        }
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev + 1], s));
         st.n_ev += 2;
         st.ev_sliced.push_back(1);
-        st.probe_launches++;
         st.pairs += n;
         st.sliced_pairs += n;
         st.levels++;

@@ -42,6 +42,7 @@ struct SlicedArgs {
     // frontier of (read, tile) pairs; entry depth (fr_read == null): pair i = (read0 + i % n_chunk, entry_tiles[i / n_chunk])
     const uint32_t *fr_read, *fr_tile, *fr_src;
     uint32_t n_pairs;
+    uint32_t pair0;              // entry depth: index of the first pair this launch works on (the depth may be split in two launches)
     const uint32_t *entry_tiles;
     uint32_t read0, n_chunk;
     // reads
@@ -366,6 +367,72 @@ PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ tab
     return true;
 }
 
+// From the pass bits of one (read, tile) pair (this lane's row word) to the columns REACHED and passed, replicated in
+// every lane.  _query_batch (query.rs:99-158): a column is reached iff its parent was reached and passed.  Roots take
+// that from the pair one tile up (or unconditionally in an entry tile); inside the tile the bits are relaxed prop_iters
+// times.  Returns false when no terminal column is left (nothing to emit).
+template <int RW>
+PF_D bool sl_reach(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t src, uint32_t lane, uint32_t *s_bits,
+                   uint32_t pass_mine, uint32_t (&reach_out)[RW]) {
+    uint32_t term[RW];
+#pragma unroll
+    for (int w = 0; w < RW; ++w) term[w] = tm->terminal[w];
+    uint32_t pass[RW], t = 0u;
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        pass[w] = __shfl_sync(0xFFFFFFFFu, pass_mine, sl_lane_of_word<RW>(w));
+        t |= pass[w] & term[w];
+    }
+    if (t == 0u) return false;
+    // _query_batch (query.rs:99-158): a column is reached iff its parent was reached and passed.  Roots take that from
+    // the pair one tile up (or unconditionally in an entry tile); inside the tile the bits are relaxed prop_iters times.
+    uint32_t par[RW];
+    uint32_t reach[RW];
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        const uint32_t c = 32u * w + lane;
+        par[w] = tm->parent[c];
+        bool bit = (pass[w] >> lane) & 1u;
+        if (bit && (par[w] & 0x8000u)) {
+            if (par[w] != 0xFFFFu) {
+                const uint32_t pc = par[w] & 0x7FFFu;
+                bit = (ldg32(a.src_reach + (size_t)src * 8u + (pc >> 5)) >> (pc & 31u)) & 1u;
+            }
+        } else if (bit) {
+            bit = false;  // decided by the relaxation below
+        }
+        reach[w] = __ballot_sync(0xFFFFFFFFu, bit);
+    }
+    const uint32_t iters = tm->prop_iters;
+    for (uint32_t it = 0; it < iters; ++it) {
+        __syncwarp();
+        if (lane < RW) {
+#pragma unroll
+            for (int w = 0; w < RW; ++w)
+                if (lane == (uint32_t)w) s_bits[w] = reach[w];
+        }
+        __syncwarp();
+        uint32_t changed = 0u;
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            bool bit = (reach[w] >> lane) & 1u;
+            if (!bit && ((pass[w] >> lane) & 1u) && !(par[w] & 0x8000u))
+                bit = (s_bits[par[w] >> 5] >> (par[w] & 31u)) & 1u;
+            const uint32_t nw = __ballot_sync(0xFFFFFFFFu, bit);
+            changed |= nw ^ reach[w];
+            reach[w] = nw;
+        }
+        if (!changed) break;
+    }
+    t = 0u;
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        reach_out[w] = reach[w];
+        t |= reach[w] & term[w];
+    }
+    return t != 0u;
+}
+
 // One (read, tile) pair.  Returns true when the pair has an output (a leaf hit or a successor tile); the columns
 // reached and passed are then in reach_out (replicated in every lane).  s_bits: 8 words of shared memory of this warp.
 // LEAN: the instantiation for depths whose tiles are all filter-only with a shallow (1- or 2-step) pre-test -- the exact
@@ -423,68 +490,26 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
     // query_passes (query.rs:48): hits >= ceil(theta * n_k).  Columns ruled out earlier may hold stale counts (their
     // k-mers stop being probed), hence the mask.
     const uint32_t pass_mine = sl_ge<PW>(acc, need) & alive_mine;
-    uint32_t pass[RW], t = 0u;
-#pragma unroll
-    for (int w = 0; w < RW; ++w) {
-        pass[w] = __shfl_sync(0xFFFFFFFFu, pass_mine, sl_lane_of_word<RW>(w));
-        t |= pass[w] & term[w];
-    }
-    if (t == 0u) return false;
-    // _query_batch (query.rs:99-158): a column is reached iff its parent was reached and passed.  Roots take that from
-    // the pair one tile up (or unconditionally in an entry tile); inside the tile the bits are relaxed prop_iters times.
-    uint32_t par[RW];
-    uint32_t reach[RW];
-#pragma unroll
-    for (int w = 0; w < RW; ++w) {
-        const uint32_t c = 32u * w + lane;
-        par[w] = tm->parent[c];
-        bool bit = (pass[w] >> lane) & 1u;
-        if (bit && (par[w] & 0x8000u)) {
-            if (par[w] != 0xFFFFu) {
-                const uint32_t pc = par[w] & 0x7FFFu;
-                bit = (ldg32(a.src_reach + (size_t)src * 8u + (pc >> 5)) >> (pc & 31u)) & 1u;
-            }
-        } else if (bit) {
-            bit = false;  // decided by the relaxation below
-        }
-        reach[w] = __ballot_sync(0xFFFFFFFFu, bit);
-    }
-    const uint32_t iters = tm->prop_iters;
-    for (uint32_t it = 0; it < iters; ++it) {
-        __syncwarp();
-        if (lane < RW) {
-#pragma unroll
-            for (int w = 0; w < RW; ++w)
-                if (lane == (uint32_t)w) s_bits[w] = reach[w];
-        }
-        __syncwarp();
-        uint32_t changed = 0u;
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            bool bit = (reach[w] >> lane) & 1u;
-            if (!bit && ((pass[w] >> lane) & 1u) && !(par[w] & 0x8000u))
-                bit = (s_bits[par[w] >> 5] >> (par[w] & 31u)) & 1u;
-            const uint32_t nw = __ballot_sync(0xFFFFFFFFu, bit);
-            changed |= nw ^ reach[w];
-            reach[w] = nw;
-        }
-        if (!changed) break;
-    }
-    t = 0u;
-#pragma unroll
-    for (int w = 0; w < RW; ++w) {
-        reach_out[w] = reach[w];
-        t |= reach[w] & term[w];
-    }
-    return t != 0u;
+    return sl_reach<RW>(a, tm, src, lane, s_bits, pass_mine, reach_out);
 }
+
+template <int RW>
+PF_D void sl_record(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t pair, uint32_t lane,
+                    const uint32_t (&reach)[RW]);
 
 template <int RW, int PW, bool SMALL_M, bool LEAN>
 PF_D void sl_pair_and_record(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t pair, uint32_t r,
                              uint32_t src, uint32_t lane, uint32_t *s_bits, uint32_t &sectors) {
     uint32_t reach[RW];
     if (!sl_pair<RW, PW, SMALL_M, LEAN>(a, tm, r, src, lane, s_bits, reach, sectors)) return;
-    // record: reach vector, alive list, per-tile successor counts, hit count
+    sl_record<RW>(a, tm, pair, lane, reach);
+}
+
+// A pair with an output: its reach vector, its place in the list of such pairs, the pairs it makes one depth down (counted
+// per tile here, written by sliced_emit_kernel) and its leaf hits.
+template <int RW>
+PF_D void sl_record(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uint32_t pair, uint32_t lane,
+                    const uint32_t (&reach)[RW]) {
     if (lane < 8u) {
         uint32_t v = 0u;
 #pragma unroll
@@ -535,7 +560,8 @@ static __global__ void __launch_bounds__(SL_THREADS, CTAS) sliced_probe_kernel(c
         g0 = __shfl_sync(0xFFFFFFFFu, g0, 0);
         if (g0 >= a.n_pairs) break;
         const uint32_t g1 = min(g0 + a.grab, a.n_pairs);
-        for (uint32_t i = g0; i < g1; ++i) {
+        for (uint32_t ii = g0; ii < g1; ++ii) {
+            const uint32_t i = a.pair0 + ii;
             uint32_t r, t, src = NONE32_D;
             if (a.fr_read) {
                 r = ldg32(a.fr_read + i);
@@ -552,6 +578,158 @@ static __global__ void __launch_bounds__(SL_THREADS, CTAS) sliced_probe_kernel(c
                 case 4: sl_pair_and_record<4, PW, SMALL_M, LEAN>(a, tm, i, r, src, lane, s_bits, sectors); break;
                 case 2: sl_pair_and_record<2, PW, SMALL_M, LEAN>(a, tm, i, r, src, lane, s_bits, sectors); break;
                 default: sl_pair_and_record<1, PW, SMALL_M, LEAN>(a, tm, i, r, src, lane, s_bits, sectors); break;
+            }
+        }
+        sectors_total += __reduce_add_sync(0xFFFFFFFFu, sectors);
+        sectors = 0u;
+    }
+    if (lane == 0 && sectors_total) atomicAdd(a.counters, sectors_total);
+}
+
+// ---- entry depth, several tiles per pass -------------------------------------------------------------------------------
+// Every read meets every entry tile.  When those tiles only filter (filter_only, pre-test of 1 or 2 steps -- the usual plan)
+// a warp takes one read through up to SL_GROUP of them at once: the cached hash values are streamed and the row indices
+// derived ONCE per round (seeds and m are tree-global, so a k-mer's row index is the same in every table), and the rows of
+// all tables are in flight together.  Per tile the state is what sl_scan_shallow keeps: the bit-sliced count of possibly
+// present k-mers per column and the columns not yet ruled out; a tile drops out once none of its terminal columns is left,
+// the read once every tile has dropped out.  Outputs are those of the per-tile pairs (pair index = entry tile * n_chunk +
+// read), so everything downstream is unchanged.  Reads of up to 255 k-mers (8 count planes).
+constexpr int SL_GROUP = 4;
+
+template <int RW, bool SMALL_M>
+PF_D void sl_group_round(const HashParams &hp, const uint32_t *__restrict__ table, uint64_t i0, uint64_t i1, uint32_t steps,
+                         bool have, uint32_t lane, uint32_t (&acc)[8], uint32_t &sectors) {
+    uint32_t m[RW];
+#pragma unroll
+    for (int w = 0; w < RW; ++w) m[w] = 0u;
+    if (have) {
+        uint32_t r0[RW], r1[RW];
+        sl_load_row<RW>(table + i0 * RW, r0);
+#pragma unroll
+        for (int w = 0; w < RW; ++w) r1[w] = 0xFFFFFFFFu;
+        if (steps > 1u) sl_load_row<RW>(table + i1 * RW, r1);
+        sectors += steps;
+#pragma unroll
+        for (int w = 0; w < RW; ++w) m[w] = r0[w] & r1[w];
+    }
+    uint32_t cnt[6];
+    sl_count_columns<RW>(m, lane, cnt);
+    uint32_t carry = 0u;
+#pragma unroll
+    for (int pl = 0; pl < 8; ++pl) {
+        const uint32_t x = pl < 6 ? cnt[pl] : 0u;
+        const uint32_t sum = sl_xor3(acc[pl], x, carry);
+        carry = sl_maj(acc[pl], x, carry);
+        acc[pl] = sum;
+    }
+}
+
+template <bool SMALL_M>
+static __global__ void __launch_bounds__(SL_THREADS, 2) sliced_entry_group_kernel(const SlicedArgs a, uint32_t n_entry,
+                                                                                   uint32_t n_groups) {
+    __shared__ uint32_t s_bits_all[SL_THREADS / 32][8];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t *const s_bits = s_bits_all[threadIdx.x >> 5];
+    const HashParams &hp = a.hp;
+    const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
+    uint32_t sectors = 0u;
+    unsigned long long sectors_total = 0ULL;
+    const uint32_t n_items = a.n_chunk * n_groups;  // item = group * n_chunk + read: group-major like the tile-major pairs
+    for (;;) {
+        uint32_t g0 = 0;
+        if (lane == 0) g0 = atomicAdd(a.work_ctr, a.grab);
+        g0 = __shfl_sync(0xFFFFFFFFu, g0, 0);
+        if (g0 >= n_items) break;
+        const uint32_t g1 = min(g0 + a.grab, n_items);
+        for (uint32_t item = g0; item < g1; ++item) {
+            const uint32_t grp = item / a.n_chunk, ri = item - grp * a.n_chunk, r = a.read0 + ri;
+            const uint32_t e0 = grp * SL_GROUP, ne = min((uint32_t)SL_GROUP, n_entry - e0);
+            const uint32_t n_k = kmers_of(ldg32(a.lengths + r), hp.k);
+            const uint32_t need = need_of(a.threshold, n_k);
+            if (need > n_k) continue;  // theta > 1: nothing can pass
+            const uint64_t *__restrict__ hbp = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
+            const SlicedTileDev *tms[SL_GROUP];
+            uint32_t acc[SL_GROUP][8], alive[SL_GROUP], term_mine[SL_GROUP], rw[SL_GROUP], steps[SL_GROUP];
+            uint32_t live_tiles = 0u, any_two = 0u;
+#pragma unroll
+            for (int t = 0; t < SL_GROUP; ++t) {
+                tms[t] = a.tiles + ldg32(a.entry_tiles + min(e0 + (uint32_t)t, n_entry - 1u));
+                rw[t] = tms[t]->row_words;
+                steps[t] = tms[t]->pre_steps;
+                uint32_t w_mine = 0u;
+                switch (rw[t]) {
+                    case 8: w_mine = sl_word_of_lane<8>(lane); break;
+                    case 4: w_mine = sl_word_of_lane<4>(lane); break;
+                    case 2: w_mine = sl_word_of_lane<2>(lane); break;
+                    default: w_mine = 0u; break;
+                }
+                alive[t] = tms[t]->valid[w_mine];
+                term_mine[t] = tms[t]->terminal[w_mine];
+#pragma unroll
+                for (int pl = 0; pl < 8; ++pl) acc[t][pl] = 0u;
+                if ((uint32_t)t < ne) {
+                    live_tiles |= 1u << t;
+                    any_two |= steps[t] > 1u;
+                }
+            }
+            if (n_k != 0u && need != 0u) {  // need == 0: every column passes (query.rs:48)
+                for (uint32_t base = 0; base < n_k && live_tiles; base += 32u) {
+                    const bool have = base + lane < n_k;
+                    const uint64_t hbv = have ? sl_ld_stream(hbp + base + lane) : 0ULL;
+                    const uint64_t h1 = fx_finish(hp.c1, hbv, hp.rot);
+                    uint64_t i0, i1 = 0ULL;
+                    if (SMALL_M) i0 = mod_small(h1, M0, M1, m32);
+                    else i0 = mod_any(h1, hp.m, hp.M);
+                    if (any_two) {
+                        const uint64_t h2 = fx_finish(hp.c2, hbv, hp.rot);
+                        if (SMALL_M) i1 = mod_small(h2, M0, M1, m32);
+                        else i1 = mod_any(h2, hp.m, hp.M);
+                    }
+                    const uint32_t done = min(base + 32u, n_k), rest = n_k - done;
+#pragma unroll
+                    for (int t = 0; t < SL_GROUP; ++t) {
+                        if (!((live_tiles >> t) & 1u)) continue;  // warp-uniform
+                        const uint32_t *__restrict__ table = a.tables + tms[t]->table_off;
+                        switch (rw[t]) {
+                            case 8: sl_group_round<8, SMALL_M>(hp, table, i0, i1, steps[t], have, lane, acc[t], sectors); break;
+                            case 4: sl_group_round<4, SMALL_M>(hp, table, i0, i1, steps[t], have, lane, acc[t], sectors); break;
+                            case 2: sl_group_round<2, SMALL_M>(hp, table, i0, i1, steps[t], have, lane, acc[t], sectors); break;
+                            default: sl_group_round<1, SMALL_M>(hp, table, i0, i1, steps[t], have, lane, acc[t], sectors); break;
+                        }
+                        if (need > rest) {
+                            alive[t] &= sl_ge<8>(acc[t], need - rest);
+                            if (!__any_sync(0xFFFFFFFFu, (alive[t] & term_mine[t]) != 0u)) live_tiles &= ~(1u << t);
+                        }
+                    }
+                }
+            }
+            // columns the pre-test could not rule out count as passed (filter-only tiles: the exact tiles below decide)
+#pragma unroll
+            for (int t = 0; t < SL_GROUP; ++t) {
+                if (!((live_tiles >> t) & 1u)) continue;
+                const uint32_t pair = (e0 + (uint32_t)t) * a.n_chunk + ri;
+                switch (rw[t]) {
+                    case 8: {
+                        uint32_t reach[8];
+                        if (sl_reach<8>(a, tms[t], NONE32_D, lane, s_bits, alive[t], reach)) sl_record<8>(a, tms[t], pair, lane, reach);
+                        break;
+                    }
+                    case 4: {
+                        uint32_t reach[4];
+                        if (sl_reach<4>(a, tms[t], NONE32_D, lane, s_bits, alive[t], reach)) sl_record<4>(a, tms[t], pair, lane, reach);
+                        break;
+                    }
+                    case 2: {
+                        uint32_t reach[2];
+                        if (sl_reach<2>(a, tms[t], NONE32_D, lane, s_bits, alive[t], reach)) sl_record<2>(a, tms[t], pair, lane, reach);
+                        break;
+                    }
+                    default: {
+                        uint32_t reach[1];
+                        if (sl_reach<1>(a, tms[t], NONE32_D, lane, s_bits, alive[t], reach)) sl_record<1>(a, tms[t], pair, lane, reach);
+                        break;
+                    }
+                }
             }
         }
         sectors_total += __reduce_add_sync(0xFFFFFFFFu, sectors);
