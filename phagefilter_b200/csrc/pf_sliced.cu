@@ -133,7 +133,7 @@ static uint32_t width_for(size_t cols) { return cols <= 32 ? 32u : (cols <= 64 ?
 // Per-node facts the tiling works from (host only).
 struct TreeFacts {
     std::vector<uint32_t> parent, sz, leaves;  // subtree size in nodes / in tree leaves
-    std::vector<uint8_t> vb, inA;              // vb: every (node, child) pair below was verified a bitwise superset
+    std::vector<uint8_t> vb;                   // every (node, child) pair below was verified a bitwise superset
     std::vector<double> fill, p, q;            // p: a k-mer unrelated to the node passes it; q: an unrelated read passes it
     double n = 0, allowed = 0;
     uint64_t need = 0;
@@ -151,7 +151,6 @@ static void tree_facts(const pf_db *db, float threshold, uint64_t n_nominal, Tre
     F.n = (double)n_nominal;
     F.allowed = F.need > n_nominal ? 0.0 : (double)(n_nominal - F.need);
     F.vb.assign(nn, 1);
-    F.inA.assign(nn, 0);
     F.sz.assign(nn, 1);
     F.leaves.assign(nn, 0);
     F.p.assign(nn, 0.0);
@@ -163,7 +162,6 @@ static void tree_facts(const pf_db *db, float threshold, uint64_t n_nominal, Tre
         F.p[u] = p;
         F.fill[u] = fill;
         F.q[u] = var < 1e-9 ? (mean + 0.5 >= (double)F.need ? 1.0 : 0.0) : phi_tab((mean - (double)F.need + 0.5) / sqrt(var));
-        F.inA[u] = fill > 0.5;
         if (db->h_leaf[u] >= 0) {
             F.leaves[u] = 1;
             continue;
@@ -172,7 +170,6 @@ static void tree_facts(const pf_db *db, float threshold, uint64_t n_nominal, Tre
         for (uint32_t c : {db->h_left[u], db->h_right[u]})
             if (c != NONE32) {
                 F.vb[u] = F.vb[u] && F.vb[c];
-                F.inA[u] = F.inA[u] || F.inA[c];
                 F.sz[u] += F.sz[c];
                 F.leaves[u] += F.leaves[c];
             }
@@ -184,10 +181,11 @@ static void tree_facts(const pf_db *db, float threshold, uint64_t n_nominal, Tre
 //    to be a bitwise superset (analyse_tree), so whatever passes a leaf below them passes them too: evaluating the
 //    nodes of the cut exactly selects exactly the reads the reference's descent would let through.
 //  * Every other node gets a column in exactly one tile.  A tile's roots all hang below columns of ONE parent tile (or
-//    below skipped nodes: entry tiles, evaluated for every read).  Where filters are still dense (fill > 1/2, in the
-//    node or below it) tiles are wide and shallow -- as many sibling subtrees side by side as fit, so the reads that
-//    die there touch few tiles; sparse subtrees are packed whole, several per tile, so a read that survives needs one
-//    more tile.
+//    below skipped nodes: entry tiles, evaluated for every read).  Entry tiles hold the nodes of the cut side by side,
+//    256 per tile (the rest in the narrowest width that fits, free columns filled with the next level), so that every
+//    read touches as few tiles as possible; below them whole subtrees are packed, several per tile, so that a read that
+//    survives needs one more tile, not one per level.  entry_only: no tiles below the cut -- the children of the
+//    entry tiles' terminal columns are recorded for the hand-over to the node-at-a-time descent instead.
 // Also fills the cost model: expected seconds of sector loads for a read unrelated to the database.
 static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool entry_only, double pair_related_s) {
     const size_t nn = db->n_nodes;
@@ -386,7 +384,6 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
             const double exact_unrel = (jK < 0 ? n : jK) * (double)K, exact_rel = n * (double)K;
             double best = 0.5 * exact_unrel + 0.5 * exact_rel, best_unrel = exact_unrel;
             uint32_t best_s = 0;
-            double best_j = 0.0;
             const bool pretest_useful = tm.entry || reach > 0.5;
             for (uint32_t s = 1; pretest_useful && s < K && s <= (uint32_t)SL_STEP_BATCH; ++s) {
                 const double j = kmers_to_die(s);
@@ -396,7 +393,6 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
                     best = c;
                     best_unrel = unrel;
                     best_s = s;
-                    best_j = j;
                 }
             }
             tm.pre_steps = best_s;
@@ -409,7 +405,6 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
                 }
                 tm.pre_rounds = (uint32_t)std::min(4.0, std::max(1.0, floor(j90 / 32.0 + 0.75)));
             }
-            (void)best_j;
             const double bytes = (double)(64ULL * db->wpf) * tm.row_words * 4.0;
             // entry tiles are worked tile-major, one table hot at a time; deeper tiles are touched at random
             const double rate = tm.entry ? sector_rate(bytes) : sector_rate(1e12);

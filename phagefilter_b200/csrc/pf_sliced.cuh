@@ -8,8 +8,11 @@
 // g_i mod m (hash_iter.rs:13-27): K sector loads instead of K per node.  query_passes (query.rs:38-49) for all
 // columns is a bit-sliced count of those masks over the read's k-mers compared with ceil(theta * n_k), and
 // _query_batch's descent (query.rs:99-158: a node is reached iff every ancestor passed) is applied to the
-// resulting pass bits inside the tile and across tiles.  Every node is evaluated exactly with its own filter, so the
-// result is the reference's for any tree (including the non-superset filters its u16 name collisions produce).
+// resulting pass bits inside the tile and across tiles.  A node that is evaluated is tested exactly, with its own
+// filter, so the result is the reference's for any tree (including the non-superset filters its u16 name collisions
+// produce).  Two shortcuts leave nodes out, both only where the load-time analysis VERIFIED that every (node, child)
+// pair below is a bitwise superset, i.e. "a leaf below passes => this node passes" (pf_sliced.cu: the skipped top of the
+// tree, and filter-only tiles whose sound pre-test is all they do).
 #pragma once
 #include "pf_kernels.cuh"
 
