@@ -3,16 +3,20 @@
 //   BloomTree::new            bloom_tree.rs:100-119     pf_builder_create
 //   BloomTree::insert         bloom_tree.rs:128-145     pf_builder_insert
 //     init_leaf_node          bloom_tree.rs:154-170     insert_kernel (canonical k-mers -> atomicOr)
-//     add_to_tree             bloom_tree.rs:187-214     greedy descent: union + two Hamming distances
-//     init_internal_node      bloom_tree.rs:226-246
+//     add_to_tree             bloom_tree.rs:187-214     descend_kernel: one cooperative launch walks root -> leaf on the
+//     init_internal_node      bloom_tree.rs:226-246     device (union + two Hamming distances per level, grid barrier)
 //   BloomFilter::union        bloom_filter.rs:275-278   union_kernel
 //   BloomFilter::distance     bloom_filter.rs:142-150   distance2_kernel (popcount of xor)
 //   BloomTree::save           bloom_tree.rs:339-355     pf_builder_save (tree.bin + one .bf per node)
 #include <sys/stat.h>
 
+#include <cooperative_groups.h>
+
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pf_common.h"
@@ -58,6 +62,88 @@ __global__ void distance2_kernel(const uint64_t *__restrict__ a, const uint64_t 
     if ((threadIdx.x & 31) == 0) {
         if (da) atomicAdd(out, da);
         if (db) atomicAdd(out + 1, db);
+    }
+}
+
+// add_to_tree + init_internal_node (bloom_tree.rs:187-246) for one new leaf, entirely on the device: one cooperative
+// launch walks from the root to the leaf the new genome is paired with.  At a two-child node the new leaf's filter is
+// OR-ed into the node (:194) while its Hamming distances to both children are summed (:197-199); after a grid-wide
+// barrier every thread reads the two sums and steps right iff right < left (:200-206, ties go left).  At the leaf it
+// stops at, the fresh internal node `in` becomes union(new leaf, that leaf) (:237-238) with the existing node as its
+// left and the new one as its right child (:242-243), and takes the old node's place under its parent (or as root).
+// The tree lives in device arrays (left / right / filter pointer per node, node 0.. in creation order), so the host
+// neither waits for a distance nor launches per level: ~50 launches and ~15 round trips per insert became one launch.
+struct DescendArgs {
+    int32_t *left, *right;       // children per node, -1 = none
+    uint64_t *const *fptr;       // filter per node
+    int32_t *root;               // device copy of the root index
+    unsigned long long *dist;    // [2 * MAX_LEVELS], zeroed before the launch: (right, left) distance sums per level
+    int32_t leaf, in;            // the new leaf and the internal node created above the leaf it is paired with
+    uint64_t wpf;
+    int32_t *err;                // set to 1 on a one-child node ("should not happen", bloom_tree.rs:209-213)
+};
+constexpr int BUILD_MAX_LEVELS = 4096;
+
+__global__ void __launch_bounds__(256) descend_kernel(const DescendArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t *__restrict__ x = a.fptr[a.leaf];
+    int32_t cur = *a.root, parent = -1;
+    bool parent_left = false;
+    for (int level = 0;; ++level) {
+        const int32_t l = a.left[cur], r = a.right[cur];
+        if (l < 0 && r < 0) break;
+        if (l < 0 || r < 0 || level >= BUILD_MAX_LEVELS) {
+            if (tid == 0) *a.err = 1;
+            return;  // uniform: every thread sees the same tree
+        }
+        uint64_t *__restrict__ c = a.fptr[cur];
+        const uint64_t *__restrict__ fl = a.fptr[l], *__restrict__ fr = a.fptr[r];
+        unsigned long long dr = 0, dl = 0;
+        for (uint64_t i = tid; i < a.wpf; i += nthr) {
+            const uint64_t v = x[i];
+            c[i] |= v;
+            dr += __popcll(fr[i] ^ v);
+            dl += __popcll(fl[i] ^ v);
+        }
+        for (int o = 16; o; o >>= 1) {
+            dr += __shfl_xor_sync(0xFFFFFFFFu, dr, o);
+            dl += __shfl_xor_sync(0xFFFFFFFFu, dl, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (dr) atomicAdd(a.dist + 2 * level, dr);
+            if (dl) atomicAdd(a.dist + 2 * level + 1, dl);
+        }
+        grid.sync();
+        const unsigned long long right_d = __ldcg(a.dist + 2 * level), left_d = __ldcg(a.dist + 2 * level + 1);
+        parent = cur;
+        if (right_d < left_d) {
+            parent_left = false;
+            cur = r;
+        } else {
+            parent_left = true;
+            cur = l;
+        }
+    }
+    uint64_t *__restrict__ fin = a.fptr[a.in];
+    const uint64_t *__restrict__ fc = a.fptr[cur];
+    for (uint64_t i = tid; i < a.wpf; i += nthr) fin[i] = x[i] | fc[i];
+    if (tid == 0) {
+        a.left[a.in] = cur;
+        a.right[a.in] = a.leaf;
+        if (parent < 0) *a.root = a.in;
+        else if (parent_left) a.left[parent] = a.in;
+        else a.right[parent] = a.in;
+    }
+}
+
+__global__ void init_nodes_kernel(int32_t *left, int32_t *right, uint64_t **fptr, int32_t i0, uint64_t *p0, int32_t i1, uint64_t *p1) {
+    left[i0] = right[i0] = -1;
+    fptr[i0] = p0;
+    if (i1 >= 0) {
+        left[i1] = right[i1] = -1;
+        fptr[i1] = p1;
     }
 }
 
@@ -138,26 +224,106 @@ using namespace pf;
 struct pf_builder {
     int device = 0;
     cudaStream_t stream = nullptr;
-    HostTree tree;                    // nodes in creation order; root tracked in tree.root
-    std::vector<uint64_t *> filters;  // device filter per node (index = node index)
+    HostTree tree;                    // nodes in creation order; links are refreshed from the device before saving
+    std::vector<uint64_t *> filters;  // device filter per node (index = node index), carved out of `chunks`
+    std::vector<uint64_t *> chunks;   // filter pool: one allocation per POOL_FILTERS filters instead of one per node
+    size_t pool_used = 0;             // filters handed out of the last chunk
     uint64_t m = 0, n_words = 0, wpf = 0;
     uint32_t K = 0;
     HashParams hp{};
     int name_mode = 0;
     uint64_t name_state = 0, name_counter = 0;
     std::vector<uint8_t> name_used;
-    unsigned long long *d_dist = nullptr, *h_dist = nullptr;
+    // device copy of the tree the descent kernel walks and updates
+    int32_t *d_left = nullptr, *d_right = nullptr, *d_root = nullptr, *d_err = nullptr;
+    uint64_t **d_fptr = nullptr;
+    size_t dev_cap = 0;
+    unsigned long long *d_dist = nullptr;
+    bool links_on_device = false;     // host links are stale
+    int coop_grid = 0;
+    // genome staging: two pinned buffers alternate so that the copy of genome i+1 overlaps the descent of genome i
+    uint8_t *h_seq[2] = {nullptr, nullptr}, *d_seq[2] = {nullptr, nullptr};
+    size_t seq_cap[2] = {0, 0};
+    cudaEvent_t seq_done[2] = {nullptr, nullptr};
+    int ring = 0;
 };
+constexpr size_t POOL_FILTERS = 256;
+
+static int ensure_dev_tree(pf_builder *b, size_t n_nodes) {
+    if (n_nodes <= b->dev_cap) return PF_OK;
+    const size_t cap = std::max<size_t>(n_nodes, std::max<size_t>(1024, b->dev_cap * 2));
+    int32_t *l = nullptr, *r = nullptr;
+    uint64_t **f = nullptr;
+    PF_CUDA_OK(cudaMalloc(&l, cap * 4));
+    PF_CUDA_OK(cudaMalloc(&r, cap * 4));
+    PF_CUDA_OK(cudaMalloc(&f, cap * 8));
+    if (b->dev_cap) {
+        PF_CUDA_OK(cudaMemcpyAsync(l, b->d_left, b->dev_cap * 4, cudaMemcpyDeviceToDevice, b->stream));
+        PF_CUDA_OK(cudaMemcpyAsync(r, b->d_right, b->dev_cap * 4, cudaMemcpyDeviceToDevice, b->stream));
+        PF_CUDA_OK(cudaMemcpyAsync(f, b->d_fptr, b->dev_cap * 8, cudaMemcpyDeviceToDevice, b->stream));
+        PF_CUDA_OK(cudaStreamSynchronize(b->stream));
+        cudaFree(b->d_left);
+        cudaFree(b->d_right);
+        cudaFree(b->d_fptr);
+    }
+    b->d_left = l;
+    b->d_right = r;
+    b->d_fptr = f;
+    b->dev_cap = cap;
+    return PF_OK;
+}
+
+// host links <- device (after inserts the descent kernel is the only one who knows where the leaves went)
+static int pull_links(pf_builder *b) {
+    if (!b->links_on_device) return PF_OK;
+    const size_t n = b->tree.nodes.size();
+    std::vector<int32_t> l(n), r(n);
+    int32_t root = -1, err = 0;
+    PF_CUDA_OK(cudaMemcpyAsync(l.data(), b->d_left, n * 4, cudaMemcpyDeviceToHost, b->stream));
+    PF_CUDA_OK(cudaMemcpyAsync(r.data(), b->d_right, n * 4, cudaMemcpyDeviceToHost, b->stream));
+    PF_CUDA_OK(cudaMemcpyAsync(&root, b->d_root, 4, cudaMemcpyDeviceToHost, b->stream));
+    PF_CUDA_OK(cudaMemcpyAsync(&err, b->d_err, 4, cudaMemcpyDeviceToHost, b->stream));
+    PF_CUDA_OK(cudaStreamSynchronize(b->stream));
+    PF_CUDA_OK(cudaGetLastError());
+    if (err) {
+        set_error("Node with only one child encountered - should not happen.");
+        return PF_ERR_STATE;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        b->tree.nodes[i].left = l[i];
+        b->tree.nodes[i].right = r[i];
+    }
+    b->tree.root = root;
+    b->links_on_device = false;
+    return PF_OK;
+}
+
+static int builder_device_state(pf_builder *b) {
+    PF_CUDA_OK(cudaMalloc(&b->d_root, 4));
+    PF_CUDA_OK(cudaMalloc(&b->d_err, 4));
+    PF_CUDA_OK(cudaMemsetAsync(b->d_err, 0, 4, b->stream));
+    PF_CUDA_OK(cudaMalloc(&b->d_dist, 2 * BUILD_MAX_LEVELS * 8));
+    for (int i = 0; i < 2; ++i) PF_CUDA_OK(cudaEventCreateWithFlags(&b->seq_done[i], cudaEventDisableTiming));
+    int per_sm = 0, sms = 0;
+    PF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descend_kernel, 256, 0));
+    PF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+    b->coop_grid = sms * std::max(1, std::min(per_sm, 4));
+    return PF_OK;
+}
 
 static int new_node(pf_builder *b, const std::string &id, int32_t *out) {
-    uint64_t *f = nullptr;
-    cudaError_t e = cudaMalloc(&f, b->wpf * 8);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        set_error("cannot allocate filter %zu (%.1f MB each)", b->filters.size(), b->wpf * 8 / 1e6);
-        return PF_ERR_NOMEM;
+    if (b->chunks.empty() || b->pool_used == POOL_FILTERS) {
+        uint64_t *c = nullptr;
+        cudaError_t e = cudaMalloc(&c, POOL_FILTERS * b->wpf * 8);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cannot allocate filters beyond %zu (%.1f MB each)", b->filters.size(), b->wpf * 8 / 1e6);
+            return PF_ERR_NOMEM;
+        }
+        b->chunks.push_back(c);
+        b->pool_used = 0;
     }
-    PF_CUDA_OK(cudaMemsetAsync(f, 0, b->wpf * 8, b->stream));
+    uint64_t *f = b->chunks.back() + b->pool_used++ * b->wpf;
     HostNode n;
     n.bf_path = id + ".bf";  // make_bloom_node, bloom_tree.rs:281
     n.has_tax = true;
@@ -165,7 +331,7 @@ static int new_node(pf_builder *b, const std::string &id, int32_t *out) {
     b->tree.nodes.push_back(n);
     b->filters.push_back(f);
     *out = (int32_t)b->tree.nodes.size() - 1;
-    return PF_OK;
+    return ensure_dev_tree(b, b->tree.nodes.size());
 }
 
 extern "C" {
@@ -208,10 +374,9 @@ int pf_builder_create(uint64_t kmer_size, float fpr, uint32_t largest_genome, ui
     b->name_state = name_seed;
     if (name_mode == 1) b->name_used.assign(65536, 0);
     cudaSetDevice(device);
-    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&b->d_dist, 16) != cudaSuccess || cudaMallocHost(&b->h_dist, 16) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || builder_device_state(b) != PF_OK) {
         set_error("CUDA error creating builder: %s", cudaGetErrorString(cudaGetLastError()));
-        delete b;
+        pf_builder_free(b);
         return PF_ERR_CUDA;
     }
     *out = b;
@@ -263,8 +428,7 @@ int pf_builder_open(const char *db_path, int device, pf_builder **out) {
     b->name_used.assign(65536, 0);
     cudaSetDevice(device);
     uint64_t *stage = nullptr;
-    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&b->d_dist, 16) != cudaSuccess || cudaMallocHost(&b->h_dist, 16) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || builder_device_state(b) != PF_OK ||
         cudaMallocHost(&stage, b->wpf * 8) != cudaSuccess) {
         set_error("CUDA error opening builder: %s", cudaGetErrorString(cudaGetLastError()));
         pf_builder_free(b);
@@ -278,13 +442,18 @@ int pf_builder_open(const char *db_path, int device, pf_builder **out) {
             if (v < 65536) b->name_used[v] = 1;
             b->name_counter++;
         }
-        uint64_t *f = nullptr;
-        if (cudaMalloc(&f, b->wpf * 8) != cudaSuccess) {
-            cudaGetLastError();
-            set_error("cannot allocate filter %zu", i);
-            rc = PF_ERR_NOMEM;
-            break;
+        if (b->chunks.empty() || b->pool_used == POOL_FILTERS) {
+            uint64_t *c = nullptr;
+            if (cudaMalloc(&c, POOL_FILTERS * b->wpf * 8) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("cannot allocate filter %zu", i);
+                rc = PF_ERR_NOMEM;
+                break;
+            }
+            b->chunks.push_back(c);
+            b->pool_used = 0;
         }
+        uint64_t *f = b->chunks.back() + b->pool_used++ * b->wpf;
         b->filters.push_back(f);
         memset(stage, 0, b->wpf * 8);
         BfHeader hh;
@@ -297,6 +466,23 @@ int pf_builder_open(const char *db_path, int device, pf_builder **out) {
         cudaStreamSynchronize(b->stream);
     }
     cudaFreeHost(stage);
+    if (rc == PF_OK && (rc = ensure_dev_tree(b, b->tree.nodes.size())) == PF_OK) {
+        // the tree the descent kernel walks: links and filter pointers of the loaded nodes
+        const size_t n = b->tree.nodes.size();
+        std::vector<int32_t> l(n), r(n);
+        for (size_t i = 0; i < n; ++i) {
+            l[i] = b->tree.nodes[i].left;
+            r[i] = b->tree.nodes[i].right;
+        }
+        const int32_t root = b->tree.root;
+        if (cudaMemcpy(b->d_left, l.data(), n * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(b->d_right, r.data(), n * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(b->d_fptr, b->filters.data(), n * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(b->d_root, &root, 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("CUDA error uploading the tree: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = PF_ERR_CUDA;
+        }
+    }
     if (rc != PF_OK) {
         pf_builder_free(b);
         return rc;
@@ -318,77 +504,86 @@ int pf_builder_insert(pf_builder *b, const char *id, const uint8_t *seq, uint64_
     }
     PF_CUDA_OK(cudaSetDevice(b->device));
     cudaStream_t s = b->stream;
-    int32_t leaf;
+    int32_t leaf, in = -1;
     int rc = new_node(b, id, &leaf);
     if (rc != PF_OK) return rc;
-    if ((rc = build_leaf_filter(seq, len, b->hp, b->filters[leaf], b->wpf, s))) return rc;
-    if (b->tree.root < 0) {
+    const bool first = b->tree.nodes.size() == 1;
+    if (!first) {
+        // init_internal_node (bloom_tree.rs:226-246): every insert but the first creates exactly one internal node
+        char name[64];
+        if (b->name_mode == 1 && b->name_counter < 65536) {
+            // a random u16 like the reference (bloom_tree.rs:232-234), redrawn until unused; once all 65,536
+            // are taken the names continue above the u16 range instead of colliding
+            uint16_t n2;
+            do {
+                n2 = (uint16_t)splitmix64(b->name_state);
+            } while (b->name_used[n2]);
+            b->name_used[n2] = 1;
+            snprintf(name, sizeof name, "Internal_Node_%u", (unsigned)n2);
+        } else {
+            snprintf(name, sizeof name, "Internal_Node_%llu", (unsigned long long)b->name_counter);
+        }
+        b->name_counter++;
+        if ((rc = new_node(b, name, &in))) return rc;
+    }
+    init_nodes_kernel<<<1, 1, 0, s>>>(b->d_left, b->d_right, b->d_fptr, leaf, b->filters[leaf], in, in >= 0 ? b->filters[in] : nullptr);
+    // init_leaf_node (bloom_tree.rs:154-170): the genome goes up through one of two pinned buffers, so that this copy
+    // overlaps the previous genome's descent
+    const int slot = b->ring;
+    b->ring ^= 1;
+    PF_CUDA_OK(cudaEventSynchronize(b->seq_done[slot]));
+    if (len > b->seq_cap[slot]) {
+        if (b->h_seq[slot]) cudaFreeHost(b->h_seq[slot]);
+        if (b->d_seq[slot]) cudaFree(b->d_seq[slot]);
+        b->h_seq[slot] = nullptr;
+        b->d_seq[slot] = nullptr;
+        const size_t cap = std::max<size_t>(len + len / 4, 1 << 16);
+        PF_CUDA_OK(cudaMallocHost(&b->h_seq[slot], cap));
+        PF_CUDA_OK(cudaMalloc(&b->d_seq[slot], cap));
+        b->seq_cap[slot] = cap;
+    }
+    PF_CUDA_OK(cudaMemsetAsync(b->filters[leaf], 0, b->wpf * 8, s));
+    const uint64_t k = b->hp.k;
+    const uint64_t n_k = (k == 0 || k > len) ? 0 : len - k + 1;  // file_parser.rs:136-139
+    if (n_k) {
+        memcpy(b->h_seq[slot], seq, len);
+        PF_CUDA_OK(cudaMemcpyAsync(b->d_seq[slot], b->h_seq[slot], len, cudaMemcpyHostToDevice, s));
+        const int grid = (int)std::min<uint64_t>((n_k + 255) / 256, 148 * 16);
+        insert_kernel<<<grid, 256, 0, s>>>(b->d_seq[slot], n_k, b->hp, reinterpret_cast<uint32_t *>(b->filters[leaf]));
+    }
+    PF_CUDA_OK(cudaEventRecord(b->seq_done[slot], s));
+    if (first) {
+        const int32_t root = leaf;
+        PF_CUDA_OK(cudaMemcpyAsync(b->d_root, &root, 4, cudaMemcpyHostToDevice, s));
+        PF_CUDA_OK(cudaStreamSynchronize(s));
         b->tree.root = leaf;
         return PF_OK;
     }
-    const int grid = 148 * 4;
-    // add_to_tree (bloom_tree.rs:187-214), iteratively: `link` is where the current subtree hangs
-    int32_t cur = b->tree.root, parent = -1;
-    bool parent_left = false;
-    for (;;) {
-        HostNode &cn = b->tree.nodes[cur];
-        if (cn.left >= 0 && cn.right >= 0) {
-            union_kernel<<<grid, 256, 0, s>>>(b->filters[cur], b->filters[leaf], b->wpf);  // :194
-            PF_CUDA_OK(cudaMemsetAsync(b->d_dist, 0, 16, s));
-            distance2_kernel<<<grid, 256, 0, s>>>(b->filters[cn.right], b->filters[cn.left], b->filters[leaf], b->wpf,
-                                                  b->d_dist);
-            PF_CUDA_OK(cudaMemcpyAsync(b->h_dist, b->d_dist, 16, cudaMemcpyDeviceToHost, s));
-            PF_CUDA_OK(cudaStreamSynchronize(s));
-            const unsigned long long right_d = b->h_dist[0], left_d = b->h_dist[1];
-            parent = cur;
-            if (right_d < left_d) {  // :200-202
-                parent_left = false;
-                cur = cn.right;
-            } else {  // :203-206 (ties go left)
-                parent_left = true;
-                cur = cn.left;
-            }
-        } else if (cn.left < 0 && cn.right < 0) {
-            // init_internal_node (bloom_tree.rs:226-246)
-            char name[64];
-            if (b->name_mode == 1 && b->name_counter < 65536) {
-                // a random u16 like the reference (bloom_tree.rs:232-234), redrawn until unused; once all 65,536
-                // are taken the names continue above the u16 range instead of colliding
-                uint16_t n2;
-                do {
-                    n2 = (uint16_t)splitmix64(b->name_state);
-                } while (b->name_used[n2]);
-                b->name_used[n2] = 1;
-                snprintf(name, sizeof name, "Internal_Node_%u", (unsigned)n2);
-            } else if (b->name_mode == 1) {
-                snprintf(name, sizeof name, "Internal_Node_%llu", (unsigned long long)b->name_counter);
-            } else {
-                snprintf(name, sizeof name, "Internal_Node_%llu", (unsigned long long)b->name_counter);
-            }
-            b->name_counter++;
-            int32_t in;
-            if ((rc = new_node(b, name, &in))) return rc;
-            union_kernel<<<grid, 256, 0, s>>>(b->filters[in], b->filters[leaf], b->wpf);  // :237
-            union_kernel<<<grid, 256, 0, s>>>(b->filters[in], b->filters[cur], b->wpf);   // :238
-            b->tree.nodes[in].left = cur;    // :242 existing node on the left
-            b->tree.nodes[in].right = leaf;  // :243 new node on the right
-            if (parent < 0) b->tree.root = in;
-            else if (parent_left) b->tree.nodes[parent].left = in;
-            else b->tree.nodes[parent].right = in;
-            break;
-        } else {
-            set_error("Node with only one child encountered - should not happen.");
-            return PF_ERR_STATE;
-        }
-    }
-    PF_CUDA_OK(cudaStreamSynchronize(s));
-    PF_CUDA_OK(cudaGetLastError());
+    // add_to_tree (bloom_tree.rs:187-214) + init_internal_node: one cooperative launch, no host round trip
+    PF_CUDA_OK(cudaMemsetAsync(b->d_dist, 0, 2 * BUILD_MAX_LEVELS * 8, s));
+    DescendArgs a{};
+    a.left = b->d_left;
+    a.right = b->d_right;
+    a.fptr = b->d_fptr;
+    a.root = b->d_root;
+    a.dist = b->d_dist;
+    a.leaf = leaf;
+    a.in = in;
+    a.wpf = b->wpf;
+    a.err = b->d_err;
+    void *args[] = {&a};
+    PF_CUDA_OK(cudaLaunchCooperativeKernel((const void *)descend_kernel, dim3(b->coop_grid), dim3(256), args, 0, s));
+    b->links_on_device = true;
     return PF_OK;
 }
 
 int pf_builder_save(pf_builder *b, const char *db_path) {
     if (!b || !db_path) return PF_ERR_ARG;
     PF_CUDA_OK(cudaSetDevice(b->device));
+    {
+        int prc = pull_links(b);
+        if (prc != PF_OK) return prc;
+    }
     mkdir(db_path, 0777);
     std::string dir(db_path), err;
     // tree.bin wants pre-order with inline children: re-index from creation order
@@ -418,39 +613,76 @@ int pf_builder_save(pf_builder *b, const char *db_path) {
         set_error("%s", err.c_str());
         return PF_ERR_IO;
     }
-    uint64_t *stage = nullptr;
-    PF_CUDA_OK(cudaMallocHost(&stage, b->wpf * 8));
     BfHeader h;
     h.num_bits = b->m;
     h.n_words = b->n_words;
     h.num_hashes = b->K;
     h.seed1 = b->tree.seed1;
     h.seed2 = b->tree.seed2;
-    int rc = PF_OK;
-    for (size_t i = 0; i < b->tree.nodes.size() && rc == PF_OK; ++i) {
-        if (cudaMemcpyAsync(stage, b->filters[i], b->wpf * 8, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess ||
-            cudaStreamSynchronize(b->stream) != cudaSuccess) {
-            set_error("CUDA error copying filter: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = PF_ERR_CUDA;
-            break;
+    // one .bf per node: several writer threads, each with its own pinned buffer and stream (device -> host copy of one
+    // filter overlaps the file writes of the others)
+    PF_CUDA_OK(cudaStreamSynchronize(b->stream));
+    const size_t n = b->tree.nodes.size();
+    const unsigned hc = std::thread::hardware_concurrency();
+    const size_t n_thr = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(hc ? hc : 4, 8), n));
+    std::atomic<size_t> next{0};
+    std::atomic<int> status{PF_OK};
+    std::vector<std::string> errs(n_thr);
+    auto worker = [&](size_t t) {
+        cudaSetDevice(b->device);
+        uint64_t *stage = nullptr;
+        cudaStream_t ws = nullptr;
+        if (cudaMallocHost(&stage, b->wpf * 8) != cudaSuccess || cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking) != cudaSuccess) {
+            errs[t] = std::string("CUDA error preparing a writer: ") + cudaGetErrorString(cudaGetLastError());
+            status = PF_ERR_CUDA;
         }
-        const std::string p = join_path(dir, b->tree.nodes[i].bf_path);
-        // Drop writes each filter with file_path = directory.join(name) (bloom_filter.rs:105-117, bloom_tree.rs:282)
-        if (!write_bf(p, h, stage, p, err)) {
-            set_error("%s", err.c_str());
-            rc = PF_ERR_IO;
+        for (size_t i; status == PF_OK && (i = next.fetch_add(1)) < n;) {
+            if (cudaMemcpyAsync(stage, b->filters[i], b->wpf * 8, cudaMemcpyDeviceToHost, ws) != cudaSuccess ||
+                cudaStreamSynchronize(ws) != cudaSuccess) {
+                errs[t] = std::string("CUDA error copying filter: ") + cudaGetErrorString(cudaGetLastError());
+                status = PF_ERR_CUDA;
+                break;
+            }
+            const std::string p = join_path(dir, b->tree.nodes[i].bf_path);
+            // Drop writes each filter with file_path = directory.join(name) (bloom_filter.rs:105-117, bloom_tree.rs:282)
+            std::string e;
+            if (!write_bf(p, h, stage, p, e)) {
+                errs[t] = e;
+                status = PF_ERR_IO;
+            }
         }
-    }
-    cudaFreeHost(stage);
-    return rc;
+        if (ws) cudaStreamDestroy(ws);
+        if (stage) cudaFreeHost(stage);
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < n_thr; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &t : th) t.join();
+    if (status != PF_OK)
+        for (auto &e : errs)
+            if (!e.empty()) {
+                set_error("%s", e.c_str());
+                break;
+            }
+    return status;
 }
 
 void pf_builder_free(pf_builder *b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    for (auto f : b->filters) cudaFree(f);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (auto c : b->chunks) cudaFree(c);
+    cudaFree(b->d_left);
+    cudaFree(b->d_right);
+    cudaFree(b->d_fptr);
+    cudaFree(b->d_root);
+    cudaFree(b->d_err);
     cudaFree(b->d_dist);
-    if (b->h_dist) cudaFreeHost(b->h_dist);
+    for (int i = 0; i < 2; ++i) {
+        if (b->h_seq[i]) cudaFreeHost(b->h_seq[i]);
+        if (b->d_seq[i]) cudaFree(b->d_seq[i]);
+        if (b->seq_done[i]) cudaEventDestroy(b->seq_done[i]);
+    }
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
