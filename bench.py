@@ -533,10 +533,14 @@ def run_ours(args, cfg):
             rs_peak = peaks["one_entry_table_460MB"]
             sect_rate = sectors / (sliced_ms * 1e-3) if sliced_ms > 0 else 0.0
             roofline = {
-                "bound": "hbm", "kernel": "sliced_probe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "bound": "hbm", "kernel": "sliced_probe_kernel (+ sliced_entry_group_kernel at the entry depth: same row gathers)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "note": "random 32 B row gathers over tables far larger than L2: the binding roof is the random-sector rate "
-                        "of HBM (micro-benchmark below, same footprint), about 1/5 of the streaming-copy peak in `peak`",
+                        "of HBM (micro-benchmark below, same footprint), about 1/5 of the streaming-copy peak in `peak`; ncu "
+                        "(profiles/r2r_cfg3s_*) shows the DRAM pipe 77 % busy on the HBM-bound launch, each missed 32 B sector "
+                        "costing ~105 B of DRAM traffic -- `traffic` is that capture's dram bytes per launch (stand-in config "
+                        "cfg3s for cfg3/cfg4: ncu cannot replay kernels over 72 GB of device memory)",
                 "algorithmic_bytes_per_launch": alg_bytes / n_sliced_launch, "launches_per_step": n_sliced_launch // steps,
                 "avg_launch_ms": sliced_ms / n_sliced_launch,
                 "kernel_share_of_step": sliced_ms / float(st.device_ms) if st.device_ms else None,

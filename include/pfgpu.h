@@ -299,6 +299,17 @@ uint64_t pf_needed_bits(float false_pos_rate, uint32_t num_items);
 uint32_t pf_optimal_num_hashes(uint64_t num_bits, uint32_t num_items);
 
 /* ------------------------------------------------------------------------------------------
+ * Host-only view of the tiling of the sliced path (no device needed; used by the CPU tests).  The tree is given as
+ * level-ordered arrays (children 0xFFFFFFFF = none, leaf[u] = DFS leaf index or -1, pop[u] = set bits of the node's
+ * filter, mono[u] = filter verified a superset of both children's).  Per node: skipped or (tile, column); per tile: parent
+ * tile (-1 = entry tile) and width in columns.  handover 1: tiles for the cut only.
+ * ---------------------------------------------------------------------------------------- */
+int pf_plan_tiles(uint64_t n_nodes, const uint32_t *left, const uint32_t *right, const int32_t *leaf, const uint64_t *pop,
+                  const uint8_t *mono, uint64_t num_bits, uint32_t num_hashes, float threshold, uint64_t nominal_kmers,
+                  int handover, uint8_t *skip_out, int32_t *node_tile_out, uint32_t *node_col_out, int32_t *tile_parent_out,
+                  uint32_t *tile_width_out, uint64_t tile_cap, uint64_t *n_tiles_out, uint64_t *n_entry_out);
+
+/* ------------------------------------------------------------------------------------------
  * Roofline micro-benchmark: all SMs issue independent random 32-byte-sector loads over a
  * working set of `bytes` (1.8 MB -> L2-resident filter; >= L2 size -> HBM).  Reports sectors/s.
  * ---------------------------------------------------------------------------------------- */

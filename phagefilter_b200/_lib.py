@@ -132,6 +132,11 @@ SYMBOLS = {
     "pf_needed_bits": (C.c_uint64, [C.c_float, C.c_uint32]),
     "pf_optimal_num_hashes": (C.c_uint32, [C.c_uint64, C.c_uint32]),
     "pf_microbench_sectors": (C.c_int, [C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
+    "pf_plan_tiles": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32),
+                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.c_uint64, C.c_uint32, C.c_float, C.c_uint64,
+                                C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_uint32),
+                                C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(C.c_uint64),
+                                C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

@@ -448,7 +448,7 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
 // makes an unrelated read cheapest under the cost model (deeper cuts have emptier filters, so reads die after fewer
 // k-mers, but need more columns and hence more tiles).  G = infinity (nothing skipped) is always a candidate and the
 // only one when the top of the tree holds an unverified node.
-static void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, SlicedState &S) {
+void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, SlicedState &S) {
     TreeFacts F;
     tree_facts(db, threshold, n_nominal, F);
     // a related read in the node-at-a-time descent: one exact leaf plus two cheap sampled tests per level
@@ -888,3 +888,59 @@ int sliced_set_hit_cursor(pf_db *db, uint64_t hits) {  // a chunk starts over (q
 }
 
 }  // namespace pf
+
+// Host-only view of the tiling for tests (no device needed): the tree is given as level-ordered arrays.
+extern "C" int pf_plan_tiles(uint64_t n_nodes, const uint32_t *left, const uint32_t *right, const int32_t *leaf,
+                             const uint64_t *pop, const uint8_t *mono, uint64_t num_bits, uint32_t num_hashes,
+                             float threshold, uint64_t nominal_kmers, int handover, uint8_t *skip_out, int32_t *node_tile_out,
+                             uint32_t *node_col_out, int32_t *tile_parent_out, uint32_t *tile_width_out, uint64_t tile_cap,
+                             uint64_t *n_tiles_out, uint64_t *n_entry_out) {
+    if (!left || !right || !leaf || !pop || !mono || !n_tiles_out || n_nodes == 0 || num_bits == 0) {
+        pf::set_error("pf_plan_tiles: bad argument");
+        return PF_ERR_ARG;
+    }
+    pf_db db;
+    db.n_nodes = n_nodes;
+    db.h_left.assign(left, left + n_nodes);
+    db.h_right.assign(right, right + n_nodes);
+    db.h_leaf.assign(leaf, leaf + n_nodes);
+    db.h_pop.assign(pop, pop + n_nodes);
+    db.h_mono.assign(mono, mono + n_nodes);
+    db.h_slot.resize(n_nodes);
+    db.n_leaves = 0;
+    for (uint64_t u = 0; u < n_nodes; ++u) {
+        db.h_slot[u] = (uint32_t)u;
+        db.n_leaves += leaf[u] >= 0;
+    }
+    db.geom.num_bits = num_bits;
+    db.geom.num_hashes = num_hashes;
+    db.wpf = ((num_bits + 63) / 64 + 15) / 16 * 16;
+    // level boundaries from the child links (nodes are level-ordered: children of level l form level l + 1)
+    db.level_start.assign(1, 0);
+    for (uint32_t lo = 0, hi = 1; lo < hi && hi <= n_nodes;) {
+        uint32_t nh = hi;
+        for (uint32_t u = lo; u < hi; ++u) nh += (left[u] != NONE32) + (right[u] != NONE32);
+        db.level_start.push_back(hi);
+        lo = hi;
+        hi = nh;
+    }
+    pf::SlicedState S;
+    S.hybrid = handover == 1;
+    pf::plan_tiles(&db, threshold, nominal_kmers ? nominal_kmers : 1, S);
+    if (skip_out) memcpy(skip_out, S.skip.data(), n_nodes);
+    if (node_tile_out)
+        for (uint64_t u = 0; u < n_nodes; ++u) node_tile_out[u] = -1;
+    for (size_t t = 0; t < S.tiles.size(); ++t) {
+        for (size_t c = 0; c < S.tile_nodes[t].size(); ++c) {
+            if (node_tile_out) node_tile_out[S.tile_nodes[t][c]] = (int32_t)t;
+            if (node_col_out) node_col_out[S.tile_nodes[t][c]] = (uint32_t)c;
+        }
+        if (t < tile_cap) {
+            if (tile_parent_out) tile_parent_out[t] = S.tile_parent[t];
+            if (tile_width_out) tile_width_out[t] = S.tiles[t].row_words * 32u;
+        }
+    }
+    *n_tiles_out = S.tiles.size();
+    if (n_entry_out) *n_entry_out = S.entry_tiles.size();
+    return PF_OK;
+}
