@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) descend_kernel(const DescendArgs a) {
         const int32_t l = a.left[cur], r = a.right[cur];
         if (l < 0 && r < 0) break;
         if (l < 0 || r < 0 || level >= BUILD_MAX_LEVELS) {
-            if (tid == 0) *a.err = 1;
+            if (tid == 0) *a.err = (l < 0 || r < 0) ? 1 : 2;
             return;  // uniform: every thread sees the same tree
         }
         uint64_t *__restrict__ c = a.fptr[cur];
@@ -286,7 +286,8 @@ static int pull_links(pf_builder *b) {
     PF_CUDA_OK(cudaStreamSynchronize(b->stream));
     PF_CUDA_OK(cudaGetLastError());
     if (err) {
-        set_error("Node with only one child encountered - should not happen.");
+        set_error(err == 1 ? "Node with only one child encountered - should not happen."
+                           : "tree deeper than 4096 levels: not supported by the device-side insert");
         return PF_ERR_STATE;
     }
     for (size_t i = 0; i < n; ++i) {

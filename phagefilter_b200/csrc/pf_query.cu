@@ -948,13 +948,9 @@ int pf::finish_csr(pf_db *db, uint32_t n_reads, uint64_t hits_total, int want_hi
 // Between the tiles and the node-at-a-time descent (hybrid evaluation): flag the reads that own a handed-over pair, give
 // them step-0 indices (hash kernel restricted to flagged reads), and make the running hit total the level scan continues
 // from equal to what the tiles have already emitted.
-static int hand_over(pf_db *db, const pf_dev_batch *bt, HashArgs h, uint64_t chunk_kmers, uint64_t kmer_base, uint32_t r0,
-                     uint32_t n_chunk, Descent &st) {
+static int hand_over(pf_db *db, const pf_dev_batch *bt, HashArgs h, uint64_t chunk_kmers, Descent &st) {
     cudaStream_t s = db->stream;
     int rc;
-    (void)kmer_base;
-    (void)n_chunk;
-    (void)r0;
     const uint64_t n_inj = db->inj_level_off.back();
     if (db->hp.small_m) {
         if ((rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
@@ -1076,7 +1072,7 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
             if (rc == PF_OK && sliced_hybrid(db) && !db->inj_level_off.empty() && db->inj_level_off.back() > 0) {
                 // the reads that survived the tiles go down the tree node by node.  That descent uses the step-0 bit indices
                 // next to the hash values; they are made now, for the surviving reads only.
-                rc = hand_over(db, bt, h, chunk_kmers, kmer_base, r0, n_chunk, st);
+                rc = hand_over(db, bt, h, chunk_kmers, st);
                 if (rc == PF_OK) rc = run_levels(db, bt, threshold, want_hits, G, kmer_base, 0, n_levels, r0, 0, st);
                 db->inj_level_off.clear();
             }
