@@ -510,6 +510,7 @@ def run_ours(args, cfg):
         probe_ms = float(st.probe_kernel_ms)
         n_launch = max(int(st.probe_launches), 1)
         sectors, sliced_ms, sliced_pairs = int(st.sector_loads), float(st.sliced_kernel_ms), int(st.sliced_pairs)
+        lines = int(st.line_loads)  # 128-byte line loads of the entry line kernel (a row of up to four entry tiles each)
         n_sliced_launch = max(int(st.sliced_launches), 1)  # one timed launch per tile-tree depth
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
         traffic, traffic_src = None, None
@@ -523,7 +524,7 @@ def run_ours(args, cfg):
         if sliced:
             # one 32 B sector per row load (each answers one probe step for every node of the tile) + the
             # cached 8 B hash value per k-mer and pair
-            alg_bytes = 32 * sectors
+            alg_bytes = 32 * sectors + 128 * lines
             achieved = alg_bytes / (sliced_ms * 1e-3) / 1e9 if sliced_ms > 0 else 0.0
             peaks = {}
             for name, nbytes in (("one_entry_table_460MB", int(info.words_per_filter) * 8 * 256),
@@ -531,7 +532,7 @@ def run_ours(args, cfg):
                 _lib.check(L.pf_microbench_sectors(local_rank, max(nbytes, 1 << 20), 60, C.byref(rate)))
                 peaks[name] = rate.value
             rs_peak = peaks["one_entry_table_460MB"]
-            sect_rate = sectors / (sliced_ms * 1e-3) if sliced_ms > 0 else 0.0
+            sect_rate = (sectors + lines) / (sliced_ms * 1e-3) if sliced_ms > 0 else 0.0  # random accesses (sector or line)
             roofline = {
                 "bound": "hbm", "kernel": "sliced_probe_kernel (+ sliced_entry_group_kernel at the entry depth: same row gathers)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -631,7 +632,8 @@ def run_ours(args, cfg):
                              if faithful else f"first {n_sample} reads, filters resident, all {cores} host threads",
                              "modes": modes},
             "work": {"pairs_per_step": pairs // steps,
-                     "sector_loads_per_step": sectors // steps, "tile_pairs_per_step": sliced_pairs // steps,
+                     "sector_loads_per_step": sectors // steps, "line_loads_per_step": lines // steps,
+                     "tile_pairs_per_step": sliced_pairs // steps,
                      "probes_issued_per_step": probes // steps,
                      "memo_lookups_per_step": memo_lookups // steps, "memo_hits_per_step": memo_hits // steps,
                      "hits_last_step": n_hits,

@@ -179,6 +179,7 @@ typedef struct pf_stats_t {
     uint64_t sliced_pairs;    /* (read, tile) pairs; `pairs` counts those and the (read, node) pairs */
     double sliced_kernel_ms;  /* CUDA-event time of the sliced kernel's launches (`probe_kernel_ms`: the node-at-a-time kernel's) */
     uint64_t sliced_launches; /* timed launches of the sliced kernels (one per tile-tree depth; the entry depth may be two kernels timed as one) */
+    uint64_t line_loads;      /* 128-byte line loads of the entry line kernel (one line = one row of up to four entry tiles); not in sector_loads */
 } pf_stats_t;
 int pf_get_stats(pf_db *db, pf_stats_t *out);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can
@@ -206,6 +207,10 @@ int pf_db_set_mode(pf_db *db, int mode);
  * handed to the node-at-a-time descent.  -1 (default): 0 if the tables fit the free HBM, else 1.  Results are identical.
  * Environment: PF_SLICED_HANDOVER=0|1. */
 int pf_db_set_handover(pf_db *db, int handover);
+/* Sliced path: most columns (tree nodes) a tile may hold -- 32, 64, 128 or 256 (default).  Narrower tiles only make the
+ * tiling finer (more entry tiles, more tile-tree depths); the tests use it to drive small trees through the multi-tile
+ * code paths (entry tiles sharing 128-byte lines, several groups of them).  Results are identical. */
+int pf_db_set_tile_cols(pf_db *db, int cols);
 /* 1 (default): k-mer memo at exact nodes.  BloomFilter::contains depends on a k-mer only through its 64-bit
  * hash_bytes value, so once a k-mer has passed all K probes at a node, every later occurrence of the same value at that
  * node within the block (sequencing depth: 30x in BASELINE config 2) is a hit after ONE table look-up instead of K - 1

@@ -58,7 +58,7 @@ class Stats(C.Structure):
         ("memo_hits", C.c_uint64), ("memo_lookups", C.c_uint64),
         ("sliced_blocks", C.c_uint64), ("sliced_tiles", C.c_uint64), ("sliced_table_bytes", C.c_uint64),
         ("chunk_splits", C.c_uint64), ("sector_loads", C.c_uint64), ("sliced_pairs", C.c_uint64),
-        ("sliced_kernel_ms", C.c_double), ("sliced_launches", C.c_uint64),
+        ("sliced_kernel_ms", C.c_double), ("sliced_launches", C.c_uint64), ("line_loads", C.c_uint64),
     ]
 
 
@@ -107,6 +107,7 @@ SYMBOLS = {
     "pf_db_set_lazy": (C.c_int, [_VP, C.c_int]),
     "pf_db_set_mode": (C.c_int, [_VP, C.c_int]),
     "pf_db_set_handover": (C.c_int, [_VP, C.c_int]),
+    "pf_db_set_tile_cols": (C.c_int, [_VP, C.c_int]),
     "pf_db_set_frontier_cap": (C.c_int, [_VP, C.c_uint64]),
     "pf_db_set_memo": (C.c_int, [_VP, C.c_int, C.c_uint64]),
     "pf_db_set_hash_cache_bytes": (C.c_int, [_VP, C.c_uint64]),

@@ -116,6 +116,10 @@ class BloomTree:
         descent, -1 tiles if they fit the free HBM."""
         _lib.check(_lib.lib().pf_db_set_handover(self._h, int(handover)))
 
+    def set_tile_cols(self, cols: int) -> None:
+        """pf_db_set_tile_cols: most columns per tile of the sliced path (32, 64, 128 or 256)."""
+        _lib.check(_lib.lib().pf_db_set_tile_cols(self._h, int(cols)))
+
     def set_frontier_cap(self, pairs: int) -> None:
         """pf_db_set_frontier_cap: chunks of reads whose frontier outgrows this many pairs are cut in half and redone."""
         _lib.check(_lib.lib().pf_db_set_frontier_cap(self._h, pairs))

@@ -243,6 +243,7 @@ struct pf_db {
     // ---- bit-sliced tiles (pf_sliced.cu): 0 = choose per (threshold, read length) by cost model, 1 = node-at-a-time
     // descent only, 2 = sliced tiles only
     int mode = 0;
+    uint32_t tile_cols = 256;  // sliced path: most columns per tile (pf_db_set_tile_cols)
     int handover = -1;  // sliced path below the cut: 0 tiles all the way down, 1 hand-over to the node-at-a-time descent, -1 tiles if they fit
     // L2 residency (access-policy window on the stream): bytes of L2 set aside for persisting lines, largest window, and
     // per level the range of filter slots its nodes use
@@ -268,6 +269,7 @@ struct Descent {
     uint64_t hits_total = 0, hits_before = 0, probes = 0, pairs = 0, levels = 0, probe_launches = 0, other_launches = 0;
     uint64_t memo_hits = 0, memo_lookups = 0;
     uint64_t sectors = 0, sliced_pairs = 0;  // row loads and (read, tile) pairs of the sliced kernel
+    uint64_t lines = 0;                      // 128-byte line loads of the entry line kernel (not in `sectors`)
     size_t n_ev = 0;
     std::vector<uint8_t> ev_sliced;          // per event pair: recorded around a sliced-kernel launch
 };

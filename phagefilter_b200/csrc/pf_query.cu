@@ -748,6 +748,7 @@ void pf::account_stats(pf_db *db, const Descent &st, uint64_t n_reads, uint64_t 
         }
     }
     db->stats.sector_loads += st.sectors;
+    db->stats.line_loads += st.lines;
     db->stats.sliced_pairs += st.sliced_pairs;
     db->stats.blocks++;
     db->stats.reads += n_reads;
@@ -1321,6 +1322,14 @@ int pf_db_set_handover(pf_db *db, int handover) {
         return PF_ERR_ARG;
     }
     db->handover = handover;
+    return PF_OK;
+}
+int pf_db_set_tile_cols(pf_db *db, int cols) {
+    if (!db || (cols != 32 && cols != 64 && cols != 128 && cols != 256)) {
+        set_error("pf_db_set_tile_cols: 32, 64, 128 or 256");
+        return PF_ERR_ARG;
+    }
+    db->tile_cols = (uint32_t)cols;
     return PF_OK;
 }
 int pf_db_set_mode(pf_db *db, int mode) {

@@ -26,6 +26,8 @@ struct SlicedState {
     std::vector<uint32_t> entry_tiles;
     std::vector<int32_t> tile_parent;
     std::vector<std::vector<uint32_t>> tile_nodes;  // node of every column
+    std::vector<int32_t> tile_group;       // per tile: the group of entry tiles it shares 128-byte lines with, or -1
+    uint32_t n_line_tiles = 0;             // leading entries of entry_tiles laid out that way (SL_QUAD per group)
     uint64_t table_words = 0;
     uint64_t entry_bytes = 0;
     double est_sectors_per_read = 0.0;     // cost model: expected sector loads of a read unrelated to the database
@@ -38,11 +40,11 @@ struct SlicedState {
     unsigned long long *d_tile_base = nullptr, *d_counters = nullptr, *d_hit_cursor = nullptr;
     unsigned int *d_work = nullptr;
     uint32_t *h_tile_count = nullptr;            // pinned [n_tiles]
-    unsigned long long *h_counters = nullptr;    // pinned [4]
+    unsigned long long *h_counters = nullptr;    // pinned [5]
     unsigned long long *h_tile_base = nullptr;   // pinned [n_tiles]
     bool tables_ready = false;
     bool entry_lean = false;  // every entry tile is filter-only with a pre-test of at most 2 steps
-    uint32_t n_groupable = 0; // leading entry tiles of that kind (S.entry_tiles is ordered so that they come first)
+    uint32_t n_quad_now = 0;  // leading entry positions the line kernel takes under the current threshold (whole groups)
     // hybrid: tiles for the cut only; what survives them is handed to the node-at-a-time descent as (read, node) pairs
     bool hybrid = true;
     uint32_t *d_node_inj_count = nullptr, *d_node_inj_cursor = nullptr;  // contiguous [2 * n_nodes]
@@ -57,6 +59,7 @@ struct SlicedState {
     int decided_under = -1;  // pf_db_set_mode value the decision was taken under
     double decided_rho = 0.5; // related share the decision was taken for
     int decided_handover = -2; // pf_db_set_handover value the decision was taken under
+    uint32_t tile_cols = 0;    // pf_db_set_tile_cols value the tiling was made with
     bool failed = false;   // tables could not be built (memory): stay with the node-at-a-time path
     bool deep_failed = false;  // the full set of tables did not fit: cut-only tiles with hand-over from now on
 };
@@ -176,6 +179,48 @@ static void tree_facts(const pf_db *db, float threshold, uint64_t n_nominal, Tre
     }
 }
 
+// Where the tiles' tables lie.  Entry tiles that can serve as pure filters for some threshold (no leaf column, every
+// column's subtree verified -- a property of the tiling, not of the threshold) come first in entry order and, SL_QUAD at a
+// time, share one table whose rows are 128-byte lines: 32 bytes (one sector, 256 columns) per tile, so that one line load
+// answers a probe step for all of them (sliced_entry_quad_kernel).  A group needs at least two tiles; every other tile
+// keeps a table of its own with rows of row_words words.
+static void layout_tables(const pf_db *db, const TreeFacts &F, SlicedState &S) {
+    const uint64_t rows = 64ULL * db->wpf;
+    const size_t nt = S.tiles.size();
+    std::vector<uint8_t> filt_ok(nt, 0);
+    for (uint32_t t : S.entry_tiles) {
+        bool ok = true;
+        for (uint32_t u : S.tile_nodes[t]) ok = ok && F.vb[u] && db->h_leaf[u] < 0;
+        filt_ok[t] = ok;
+    }
+    std::stable_partition(S.entry_tiles.begin(), S.entry_tiles.end(), [&](uint32_t t) { return filt_ok[t] != 0; });
+    size_t n_ok = 0;
+    while (n_ok < S.entry_tiles.size() && filt_ok[S.entry_tiles[n_ok]]) ++n_ok;
+    if (n_ok % SL_QUAD == 1) --n_ok;  // a tile alone in its group gains nothing from a 128-byte row
+    static const bool no_lines = getenv("PF_SLICED_NO_LINES") != nullptr;
+    if (no_lines) n_ok = 0;
+    S.n_line_tiles = (uint32_t)n_ok;
+    S.tile_group.assign(nt, -1);
+    S.table_words = 0;
+    S.entry_bytes = 0;
+    for (size_t e = 0; e < n_ok; ++e) {
+        SlicedTileDev &tm = S.tiles[S.entry_tiles[e]];
+        S.tile_group[S.entry_tiles[e]] = (int32_t)(e / SL_QUAD);
+        tm.table_off = S.table_words + 8ULL * (e % SL_QUAD);
+        tm.row_stride = 32u;
+        if (e % SL_QUAD == SL_QUAD - 1 || e + 1 == n_ok) S.table_words += rows * 32ULL;
+    }
+    S.entry_bytes = S.table_words * 4ULL;
+    for (size_t t = 0; t < nt; ++t) {
+        SlicedTileDev &tm = S.tiles[t];
+        if (S.tile_group[t] >= 0) continue;
+        tm.table_off = S.table_words;
+        tm.row_stride = tm.row_words;
+        S.table_words += rows * tm.row_words;
+        if (tm.entry) S.entry_bytes += rows * tm.row_words * 4ULL;
+    }
+}
+
 // Cuts the (pruned, level-ordered) tree into tiles given the set of nodes that are not evaluated.
 //  * Skipped nodes: interior, connected to the root, and every (node, child) pair below them was verified at load time
 //    to be a bitwise superset (analyse_tree), so whatever passes a leaf below them passes them too: evaluating the
@@ -190,6 +235,7 @@ static void tree_facts(const pf_db *db, float threshold, uint64_t n_nominal, Tre
 static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool entry_only, double pair_related_s) {
     const size_t nn = db->n_nodes;
     const uint32_t K = db->geom.num_hashes;
+    const size_t MAXC = std::min<size_t>(std::max<uint32_t>(db->tile_cols, 32u), SL_MAX_COLS);  // columns per tile
     S.tiles.clear();
     S.col_slot.clear();
     S.child_tile.clear();
@@ -217,9 +263,6 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
             for (uint32_t c : {db->h_left[out[i]], db->h_right[out[i]]})
                 if (c != NONE32 && out.size() - b < cap) out.push_back(c);
     };
-    const uint64_t rows = 64ULL * db->wpf;
-    S.table_words = 0;
-    S.entry_bytes = 0;
     while (!jobs.empty()) {
         Job job = std::move(jobs.front());
         jobs.pop_front();
@@ -228,9 +271,9 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
         // entry tiles see every read: roots side by side, as few tiles as possible.  Below them come the reads that
         // (mostly) belong there: whole subtrees, several per tile, so that such a read needs one more tile only.
         for (uint32_t r : job.roots) (job.parent_tile < 0 ? RA : RB).push_back(r);
-        for (size_t c0 = 0; c0 < RA.size(); c0 += SL_MAX_COLS) {
-            std::vector<uint32_t> cols(RA.begin() + c0, RA.begin() + std::min(RA.size(), c0 + SL_MAX_COLS));
-            const size_t cap = width_for(cols.size());
+        for (size_t c0 = 0; c0 < RA.size(); c0 += MAXC) {
+            std::vector<uint32_t> cols(RA.begin() + c0, RA.begin() + std::min(RA.size(), c0 + MAXC));
+            const size_t cap = std::min<size_t>(width_for(cols.size()), MAXC);
             for (size_t i = 0; i < cols.size() && cols.size() < cap; ++i)
                 for (uint32_t c : {db->h_left[cols[i]], db->h_right[cols[i]]})
                     if (c != NONE32 && cols.size() < cap) cols.push_back(c);
@@ -238,19 +281,19 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
         }
         std::vector<uint32_t> cur;
         for (uint32_t r : RB) {
-            if (F.sz[r] <= (uint32_t)SL_MAX_COLS) {
-                if (cur.size() + F.sz[r] > (size_t)SL_MAX_COLS) {
+            if (F.sz[r] <= (uint32_t)MAXC) {
+                if (cur.size() + F.sz[r] > MAXC) {
                     made.push_back(std::move(cur));
                     cur.clear();
                 }
-                bfs_subtree(r, SL_MAX_COLS, cur);
+                bfs_subtree(r, MAXC, cur);
             } else {
                 if (!cur.empty()) {
                     made.push_back(std::move(cur));
                     cur.clear();
                 }
                 std::vector<uint32_t> cols;
-                bfs_subtree(r, SL_MAX_COLS, cols);
+                bfs_subtree(r, MAXC, cols);
                 made.push_back(std::move(cols));
             }
         }
@@ -262,10 +305,7 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
             memset(&tm, 0, sizeof tm);
             tm.n_cols = (uint32_t)cols.size();
             tm.row_words = width_for(cols.size()) / 32u;
-            tm.table_off = S.table_words;
-            S.table_words += rows * tm.row_words;
             tm.entry = job.parent_tile < 0;
-            if (tm.entry) S.entry_bytes += rows * tm.row_words * 4ULL;
             S.col_slot.resize((size_t)(t + 1) * SL_MAX_COLS, NONE32);
             for (size_t c = 0; c < cols.size(); ++c) {
                 node_tile[cols[c]] = (int32_t)t;
@@ -332,6 +372,7 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
             if (!nj.roots.empty() && !entry_only) jobs.push_back(std::move(nj));
         }
     }
+    layout_tables(db, F, S);
     // Cost model (steers choices only, never results).  A read unrelated to the database leaves a tile once every
     // terminal column has more than `allowed` k-mers proven absent.  With s probe steps per k-mer, a terminal of fill f
     // proves an unrelated k-mer absent with probability r = 1 - f^s, so it needs about (allowed + 1) / r k-mers (plus two
@@ -344,6 +385,8 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
         std::vector<double> pr(nn, 0.0);  // per node: probability that an unrelated read reaches and passes it
         for (size_t u = 0; u < nn; ++u) pr[u] = S.skip[u] ? 1.0 : (u == 0 ? 1.0 : pr[F.parent[u]]) * F.q[u];
         double total_s = 0.0, total_sectors = 0.0;
+        std::vector<double> group_unrel((S.n_line_tiles + SL_QUAD - 1) / SL_QUAD, 0.0);
+        const double line_bytes = (double)(64ULL * db->wpf) * 128.0;
         uint32_t max_depth = 0;
         std::vector<uint32_t> tdepth(nt, 0);
         const double a1 = F.allowed + 1.0, n = F.n;
@@ -395,6 +438,10 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
                     best_s = s;
                 }
             }
+            if (const char *f = getenv("PF_SLICED_FORCE_PRE")) {  // tests: a given pre-test depth on every entry tile
+                const uint32_t v = (uint32_t)atoi(f);
+                if (tm.entry && v < K && v <= (uint32_t)SL_STEP_BATCH) best_s = v;
+            }
             tm.pre_steps = best_s;
             tm.filter_only = best_s != 0 && filt_ok;
             {   // rounds in flight before the first look at the columns: when 90 % of the terminals are expected to be settled
@@ -405,11 +452,18 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
                 }
                 tm.pre_rounds = (uint32_t)std::min(4.0, std::max(1.0, floor(j90 / 32.0 + 0.75)));
             }
-            const double bytes = (double)(64ULL * db->wpf) * tm.row_words * 4.0;
+            const double bytes = (double)(64ULL * db->wpf) * tm.row_stride * 4.0;
             // entry tiles are worked tile-major, one table hot at a time; deeper tiles are touched at random
             const double rate = tm.entry ? sector_rate(bytes) : sector_rate(1e12);
-            total_s += reach * best_unrel / rate;
-            total_sectors += reach * best_unrel;
+            const bool in_lines = S.tile_group[t] >= 0 && best_s >= 1 && best_s <= 2 && filt_ok;
+            if (in_lines) {
+                // tiles that share lines are worked together: one line load per k-mer and step answers all of them, the
+                // tile that holds out longest decides
+                group_unrel[S.tile_group[t]] = std::max(group_unrel[S.tile_group[t]], best_unrel);
+            } else {
+                total_s += reach * best_unrel / rate;
+                total_sectors += reach * best_unrel;
+            }
             if (entry_only) {
                 // what the tile cannot rule out goes to the node-at-a-time descent: two (read, child) pairs per surviving
                 // terminal column, each a cheap sampled test there (~32 probes at the L2 rate)
@@ -428,6 +482,10 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
                 }
             }
         }
+        for (double g : group_unrel) {
+            total_s += g / sector_rate(line_bytes);  // a line costs what a sector costs (scripts/mb/mb_coop.cu)
+            total_sectors += g;
+        }
         S.est_sectors_per_read = total_sectors;
         S.est_seconds_per_read = total_s;
         // a read that belongs to a genome of the database: the entry tile's pre-test (plus its exact pass unless the tile
@@ -436,8 +494,9 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
             double worst_entry = 0.0;
             for (uint32_t t : S.entry_tiles) {
                 const SlicedTileDev &tm = S.tiles[t];
-                const double bytes = (double)(64ULL * db->wpf) * tm.row_words * 4.0;
-                worst_entry += (n * (double)tm.pre_steps + (tm.filter_only ? 0.0 : n * (double)K)) / sector_rate(bytes);
+                const double bytes = (double)(64ULL * db->wpf) * tm.row_stride * 4.0;
+                const double share = S.tile_group[t] >= 0 && tm.filter_only && tm.pre_steps <= 2 ? 1.0 / SL_QUAD : 1.0;
+                worst_entry += (share * n * (double)tm.pre_steps + (tm.filter_only ? 0.0 : n * (double)K)) / sector_rate(bytes);
             }
             S.est_seconds_related = worst_entry + (entry_only ? pair_related_s : (double)max_depth * n * (double)K / sector_rate(1e12));
         }
@@ -466,9 +525,14 @@ void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, SlicedStat
     // node of the cut decides how many k-mers an unrelated read needs, and subtrees of equal size differ in fill
     const size_t n_by_leaves = cand.size();
     for (int i = 19; i >= 2; --i) cand.push_back((uint64_t)i);  // phi = i / 20
-    for (size_t ci = 0; ci < cand.size(); ++ci) {
+    size_t ci0 = 0, ci1 = cand.size();
+    if (const char *f = getenv("PF_SLICED_FORCE_G")) {  // tests: a given cut ("skip every verified node with more than G leaves")
+        cand.assign(1, (uint64_t)strtoull(f, nullptr, 10));
+        ci0 = 0, ci1 = 1;
+    }
+    for (size_t ci = ci0; ci < ci1; ++ci) {
         const uint64_t G = cand[ci];
-        const bool by_fill = ci >= n_by_leaves;
+        const bool by_fill = ci1 > 1 && ci >= n_by_leaves;
         const double phi = by_fill ? (double)G / 20.0 : 0.0;
         SlicedState T;
         T.skip.assign(nn, 0);
@@ -498,6 +562,8 @@ void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, SlicedStat
     S.entry_tiles = std::move(best.entry_tiles);
     S.tile_parent = std::move(best.tile_parent);
     S.tile_nodes = std::move(best.tile_nodes);
+    S.tile_group = std::move(best.tile_group);
+    S.n_line_tiles = best.n_line_tiles;
     S.table_words = best.table_words;
     S.entry_bytes = best.entry_bytes;
     S.est_sectors_per_read = best.est_sectors_per_read;
@@ -507,9 +573,9 @@ void plan_tiles(const pf_db *db, float threshold, uint64_t n_nominal, SlicedStat
         fprintf(stderr, "[sliced plan] chosen: %zu tiles, %zu entry, tables %.2f GB, est %.2f ns/read\n", S.tiles.size(),
                 S.entry_tiles.size(), S.table_words * 4.0 / 1e9, S.est_seconds_per_read * 1e9);
         for (uint32_t t : S.entry_tiles)
-            fprintf(stderr, "[sliced plan]   entry tile %u: %u columns, row %u B, %u children, pre-test %u steps, %u rounds first%s\n", t,
-                    S.tiles[t].n_cols, S.tiles[t].row_words * 4, S.tiles[t].n_children, S.tiles[t].pre_steps, S.tiles[t].pre_rounds,
-                    S.tiles[t].filter_only ? " (filter only)" : "");
+            fprintf(stderr, "[sliced plan]   entry tile %u: %u columns, row %u B, stride %u B, %u children, pre-test %u steps, %u rounds first%s\n", t,
+                    S.tiles[t].n_cols, S.tiles[t].row_words * 4, S.tiles[t].row_stride * 4, S.tiles[t].n_children, S.tiles[t].pre_steps,
+                    S.tiles[t].pre_rounds, S.tiles[t].filter_only ? " (filter only)" : "");
     }
 }
 
@@ -532,8 +598,8 @@ static int build_tables(pf_db *db, SlicedState &S) {
     PF_CUDA_OK(cudaMalloc(&S.d_tile_count, 2 * nt * 4));
     S.d_tile_cursor = S.d_tile_count + nt;
     PF_CUDA_OK(cudaMalloc(&S.d_tile_base, nt * 8));
-    PF_CUDA_OK(cudaMalloc(&S.d_counters, 4 * 8));
-    S.d_hit_cursor = S.d_counters + 3;
+    PF_CUDA_OK(cudaMalloc(&S.d_counters, 5 * 8));
+    S.d_hit_cursor = S.d_counters + 4;
     PF_CUDA_OK(cudaMalloc(&S.d_work, 8));
     {
         const size_t nn = db->n_nodes;
@@ -544,7 +610,7 @@ static int build_tables(pf_db *db, SlicedState &S) {
         PF_CUDA_OK(cudaMallocHost(&S.h_node_inj_base, (nn + 1) * 8));
     }
     PF_CUDA_OK(cudaMallocHost(&S.h_tile_count, nt * 4));
-    PF_CUDA_OK(cudaMallocHost(&S.h_counters, 4 * 8));
+    PF_CUDA_OK(cudaMallocHost(&S.h_counters, 5 * 8));
     PF_CUDA_OK(cudaMallocHost(&S.h_tile_base, nt * 8));
     cudaStream_t s = db->stream;
     uint32_t *d_col_slot = nullptr;
@@ -585,7 +651,7 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
     // already answered (hits per read, capped at 1) and starts at 1/2
     const double rho = db->related_share < 0 ? 0.5 : db->related_share;
     if (S.decided_mode && S.theta == threshold && S.n_nominal == n_nominal && S.decided_under == db->mode &&
-        S.decided_handover == db->handover &&
+        S.decided_handover == db->handover && S.tile_cols == db->tile_cols &&
         (db->mode != 0 || fabs(rho - S.decided_rho) <= 0.1)) {
         *use_sliced = S.decided_mode == 2;
         if (*use_sliced) {
@@ -618,6 +684,8 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
                     rho, t_pair * 1e9, p_unrel * 1e9, p_rel * 1e9, t_sliced * 1e9, P.est_seconds_per_read * 1e9,
                     P.est_seconds_related * 1e9, sliced ? "sliced" : "node-at-a-time");
     }
+    const bool cols_same = S.tile_cols == db->tile_cols;
+    S.tile_cols = db->tile_cols;
     S.theta = threshold;
     S.n_nominal = n_nominal;
     S.decided_mode = sliced ? 2 : 1;
@@ -625,7 +693,8 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
     S.decided_rho = rho;
     S.decided_handover = db->handover;
     if (!sliced) return PF_OK;
-    const bool same = S.tables_ready && S.skip == P.skip && S.tiles.size() == P.tiles.size() && S.hybrid == P.hybrid;
+    const bool same = S.tables_ready && S.skip == P.skip && S.tiles.size() == P.tiles.size() && S.hybrid == P.hybrid &&
+                      cols_same;
     if (same) {
         // same tiling, possibly other pre-test depths (they follow the threshold and the read length): refresh the tile records
         for (size_t t = 0; t < S.tiles.size(); ++t) {
@@ -648,6 +717,8 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
         S.entry_tiles = std::move(P.entry_tiles);
         S.tile_parent = std::move(P.tile_parent);
         S.tile_nodes = std::move(P.tile_nodes);
+        S.tile_group = std::move(P.tile_group);
+        S.n_line_tiles = P.n_line_tiles;
         S.hybrid = P.hybrid;
         S.table_words = P.table_words;
         S.entry_bytes = P.entry_bytes;
@@ -670,18 +741,24 @@ int sliced_prepare(pf_db *db, float threshold, uint64_t n_nominal, bool *use_sli
             return PF_OK;                  // auto: stay with the node-at-a-time path
         }
     }
-    // entry tiles that only filter with a 1- or 2-step pre-test come first: they can share one pass per read
+    // Under this threshold: the leading line groups whose tiles all filter with a 1- or 2-step pre-test are taken by the line
+    // kernel; the rest of the entry depth goes pair by pair (lean instantiation when every entry tile is of that kind).
     {
         auto groupable = [&](uint32_t t) {
             return S.tiles[t].filter_only && S.tiles[t].pre_steps >= 1 && S.tiles[t].pre_steps <= 2 &&
                    S.tiles[t].pre_steps < db->geom.num_hashes;
         };
-        std::stable_partition(S.entry_tiles.begin(), S.entry_tiles.end(), groupable);
-        S.n_groupable = 0;
-        for (uint32_t t : S.entry_tiles) S.n_groupable += groupable(t) ? 1u : 0u;
-        S.entry_lean = !S.entry_tiles.empty() && S.n_groupable == S.entry_tiles.size();
-        PF_CUDA_OK(cudaMemcpyAsync(S.d_entry, S.entry_tiles.data(), S.entry_tiles.size() * 4, cudaMemcpyHostToDevice, db->stream));
-        PF_CUDA_OK(cudaStreamSynchronize(db->stream));
+        S.n_quad_now = 0;
+        for (uint32_t e0 = 0; e0 < S.n_line_tiles; e0 += SL_QUAD) {
+            const uint32_t e1 = std::min<uint32_t>(e0 + SL_QUAD, S.n_line_tiles);
+            bool all = true;
+            for (uint32_t e = e0; e < e1; ++e) all = all && groupable(S.entry_tiles[e]);
+            if (!all) break;
+            S.n_quad_now = e1;
+        }
+        size_t n_groupable = 0;
+        for (uint32_t t : S.entry_tiles) n_groupable += groupable(t) ? 1u : 0u;
+        S.entry_lean = !S.entry_tiles.empty() && n_groupable == S.entry_tiles.size();
     }
     db->stats.sliced_tiles = S.tiles.size();
     db->stats.sliced_table_bytes = S.table_words * 4ULL;
@@ -707,6 +784,20 @@ static void launch_sliced(const SlicedArgs &a, int sm_count, bool lean, cudaStre
     }
 }
 
+static void launch_quad(const SlicedArgs &a, uint64_t max_kmers, uint32_t n_entry, uint32_t n_groups, int sm_count, cudaStream_t s) {
+    const int grid = sm_count * 3;
+    if (max_kmers < 256) {
+        if (a.hp.small_m) sliced_entry_quad_kernel<8, true><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        else sliced_entry_quad_kernel<8, false><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+    } else if (max_kmers < 65536) {
+        if (a.hp.small_m) sliced_entry_quad_kernel<16, true><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        else sliced_entry_quad_kernel<16, false><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+    } else {
+        if (a.hp.small_m) sliced_entry_quad_kernel<32, true><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        else sliced_entry_quad_kernel<32, false><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+    }
+}
+
 // The tile-level descent for reads [r0, r0 + n_chunk) of the batch whose hash values are cached in db->hb.
 int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint64_t kmer_base, uint32_t r0,
                uint32_t n_chunk, Descent &st) {
@@ -720,7 +811,7 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
     bool entry = true;
     while (n > 0) {
         if ((rc = S.reach[cur].ensure(n * 8)) || (rc = S.alive.ensure(n))) return rc;
-        PF_CUDA_OK(cudaMemsetAsync(S.d_counters, 0, 3 * 8, s));
+        PF_CUDA_OK(cudaMemsetAsync(S.d_counters, 0, 4 * 8, s));
         PF_CUDA_OK(cudaMemsetAsync(S.d_work, 0, 8, s));
         PF_CUDA_OK(cudaMemsetAsync(S.d_tile_count, 0, 2 * nt * 4, s));
         SlicedArgs a{};
@@ -758,18 +849,17 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
             db->ev_probe.push_back(e);
         }
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev], s));
-        // Entry depth.  Tiles that only filter with a 1- or 2-step pre-test (the usual plan) share one pass per read, up to
-        // SL_GROUP tiles at a time (sliced_entry_group_kernel; short reads, two or more such tiles); the rest of the depth --
+        // Entry depth.  Groups of tiles that only filter with a 1- or 2-step pre-test (the usual plan) and share 128-byte
+        // lines go through the line kernel, one pass per read and group (sliced_entry_quad_kernel); the rest of the depth --
         // or all of it -- goes pair by pair, with the lean instantiation when every tile is of that kind.
         const bool lean = entry && S.entry_lean && !getenv("PF_SLICED_NO_LEAN");
         uint32_t n_grouped = 0;
-        if (entry && bt->max_kmers < 256 && S.n_groupable >= 2 && !getenv("PF_SLICED_NO_GROUP")) {
-            n_grouped = S.n_groupable;
-            const uint32_t n_groups = (n_grouped + SL_GROUP - 1) / SL_GROUP;
+        if (entry && S.n_quad_now >= 2 && !getenv("PF_SLICED_NO_QUAD")) {
+            n_grouped = S.n_quad_now;
+            const uint32_t n_groups = (n_grouped + SL_QUAD - 1) / SL_QUAD;
             SlicedArgs g = a;
-            g.grab = 4u;
-            if (g.hp.small_m) sliced_entry_group_kernel<true><<<db->sm_count * 2, SL_THREADS, 0, s>>>(g, n_grouped, n_groups);
-            else sliced_entry_group_kernel<false><<<db->sm_count * 2, SL_THREADS, 0, s>>>(g, n_grouped, n_groups);
+            g.grab = bt->max_kmers <= 256 ? 4u : 1u;
+            launch_quad(g, bt->max_kmers, n_grouped, n_groups, db->sm_count, s);
             st.probe_launches++;
         }
         if (!entry || n_grouped < S.entry_tiles.size()) {
@@ -789,10 +879,11 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
         st.pairs += n;
         st.sliced_pairs += n;
         st.levels++;
-        PF_CUDA_OK(cudaMemcpyAsync(S.h_counters, S.d_counters, 3 * 8, cudaMemcpyDeviceToHost, s));
+        PF_CUDA_OK(cudaMemcpyAsync(S.h_counters, S.d_counters, 4 * 8, cudaMemcpyDeviceToHost, s));
         PF_CUDA_OK(cudaMemcpyAsync(S.h_tile_count, S.d_tile_count, nt * 4, cudaMemcpyDeviceToHost, s));
         PF_CUDA_OK(cudaStreamSynchronize(s));
         st.sectors += S.h_counters[0];
+        st.lines += S.h_counters[3];
         const uint64_t n_alive = S.h_counters[1], hits = S.h_counters[2];
         uint64_t next_n = 0;
         for (size_t t = 0; t < nt; ++t) {
@@ -881,8 +972,8 @@ int sliced_begin_block(pf_db *db) {
 }
 int sliced_set_hit_cursor(pf_db *db, uint64_t hits) {  // a chunk starts over (query_impl)
     SlicedState &S = *db->sliced;
-    S.h_counters[3] = hits;
-    PF_CUDA_OK(cudaMemcpyAsync(S.d_hit_cursor, S.h_counters + 3, 8, cudaMemcpyHostToDevice, db->stream));
+    S.h_counters[4] = hits;
+    PF_CUDA_OK(cudaMemcpyAsync(S.d_hit_cursor, S.h_counters + 4, 8, cudaMemcpyHostToDevice, db->stream));
     PF_CUDA_OK(cudaStreamSynchronize(db->stream));
     return PF_OK;
 }

@@ -32,7 +32,8 @@ struct SlicedTileDev {
     uint32_t pre_steps;   // probe steps of the sound pre-test pass (0 = none), chosen by the cost model
     uint32_t filter_only; // 1: the pre-test is all this tile does (its columns are implied by what passes below them)
     uint32_t pre_rounds;  // rounds of 32 k-mers the shallow pre-test keeps in flight between two looks at the columns
-    uint32_t pad_;
+    uint32_t row_stride;  // u32 words from one row of the table to the next: row_words, or 32 when the tile shares 128-byte
+                          // lines with up to three other entry tiles (its slot: 8 words at table_off)
     uint32_t valid[8];    // columns in use
     uint32_t terminal[8]; // columns that are tree leaves or have a child in another tile
     uint32_t leafmask[8]; // columns that are tree leaves
@@ -64,7 +65,7 @@ struct SlicedArgs {
     uint32_t *alive;             // indices of the pairs with a hit or a successor, any order
     uint32_t *tile_count;        // per tile: pairs the next depth will hold
     uint32_t *node_inj_count;    // hand-over to the node-at-a-time descent: per tree node, (read, node) pairs to inject; or null
-    unsigned long long *counters;  // [0] sectors loaded, [1] alive pairs, [2] leaf hits
+    unsigned long long *counters;  // [0] sectors loaded, [1] alive pairs, [2] leaf hits, [3] 128-byte lines loaded (entry groups)
     unsigned int *work_ctr;
     HashParams hp;
     float threshold;
@@ -177,8 +178,8 @@ PF_D uint32_t sl_ge(const uint32_t (&acc)[PW], uint32_t c) {
 // Out: the same, narrowed; acc = per-column counts of this lane's word.  Returns false as soon as no terminal column can
 // pass any more (read-level early exit; the rest of the read could not change that).
 template <int RW, int PW, bool SMALL_M>
-PF_D bool sl_scan(const HashParams &hp, const uint32_t *__restrict__ table, const uint64_t *__restrict__ hbp, uint32_t n_k,
-                  uint32_t need, uint32_t steps, uint32_t lane, const uint32_t (&term)[RW], uint32_t term_mine,
+PF_D bool sl_scan(const HashParams &hp, const uint32_t *__restrict__ table, uint32_t stride, const uint64_t *__restrict__ hbp,
+                  uint32_t n_k, uint32_t need, uint32_t steps, uint32_t lane, const uint32_t (&term)[RW], uint32_t term_mine,
                   uint32_t &alive_mine, uint32_t (&live)[RW], uint32_t (&acc)[PW], uint32_t &sectors) {
     const bool allowed0 = need == n_k;
     const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
@@ -204,7 +205,7 @@ PF_D bool sl_scan(const HashParams &hp, const uint32_t *__restrict__ table, cons
                         uint64_t idx;
                         if (SMALL_M) idx = mod_small(g, M0, M1, m32);
                         else idx = mod_any(g, hp.m, hp.M);
-                        sl_load_row<RW>(table + idx * RW, rows[b]);
+                        sl_load_row<RW>(table + idx * stride, rows[b]);
                         ++sectors;
                     }
                     const uint32_t i = s + b;
@@ -273,8 +274,9 @@ PF_D bool sl_scan(const HashParams &hp, const uint32_t *__restrict__ table, cons
 // The same pass for a shallow pre-test (ST = 1 or 2 probe steps): RB rounds of 32 k-mers are in flight together, so a
 // lane still has RB * ST independent row loads outstanding; the columns are re-examined every RB rounds.
 template <int RW, int PW, bool SMALL_M, int RB, int ST>
-PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ table, const uint64_t *__restrict__ hbp,
-                          uint32_t n_k, uint32_t need, uint32_t rounds, uint32_t lane, const uint32_t (&term)[RW],
+PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ table, uint32_t stride,
+                          const uint64_t *__restrict__ hbp, uint32_t n_k, uint32_t need, uint32_t rounds, uint32_t lane,
+                          const uint32_t (&term)[RW],
                           uint32_t term_mine, uint32_t &alive_mine, uint32_t (&live)[RW], uint32_t (&acc)[PW],
                           uint32_t &sectors) {
     // the plan expects a typical unrelated read to be settled after `rounds` rounds: that many are in flight first, then
@@ -307,7 +309,7 @@ PF_D bool sl_scan_shallow(const HashParams &hp, const uint32_t *__restrict__ tab
                     uint64_t idx;
                     if (SMALL_M) idx = mod_small(g, M0, M1, m32);
                     else idx = mod_any(g, hp.m, hp.M);
-                    sl_load_row<RW>(table + idx * RW, rows[j][st]);
+                    sl_load_row<RW>(table + idx * stride, rows[j][st]);
                     ++sectors;
                 }
             }
@@ -447,6 +449,7 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
     const uint32_t n_k = kmers_of(ldg32(a.lengths + r), hp.k);
     const uint32_t need = need_of(a.threshold, n_k);
     const uint32_t *__restrict__ table = a.tables + tm->table_off;
+    const uint32_t stride = tm->row_stride;
     const uint64_t *__restrict__ hbp = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
     const uint32_t my_word = sl_word_of_lane<RW>(lane);
     const uint32_t valid_mine = tm->valid[my_word], term_mine = tm->terminal[my_word];
@@ -469,13 +472,13 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
         if (pre != 0u && pre < hp.K) {
             bool ok;
             if (pre == 1u)
-                ok = sl_scan_shallow<RW, PW, SMALL_M, 4, 1>(hp, table, hbp, n_k, need, tm->pre_rounds, lane, term, term_mine, alive_mine, live,
+                ok = sl_scan_shallow<RW, PW, SMALL_M, 4, 1>(hp, table, stride, hbp, n_k, need, tm->pre_rounds, lane, term, term_mine, alive_mine, live,
                                                             acc, sectors);
             else if (pre == 2u)
-                ok = sl_scan_shallow<RW, PW, SMALL_M, 2, 2>(hp, table, hbp, n_k, need, tm->pre_rounds, lane, term, term_mine, alive_mine, live,
+                ok = sl_scan_shallow<RW, PW, SMALL_M, 2, 2>(hp, table, stride, hbp, n_k, need, tm->pre_rounds, lane, term, term_mine, alive_mine, live,
                                                             acc, sectors);
             else if constexpr (!LEAN)
-                ok = sl_scan<RW, PW, SMALL_M>(hp, table, hbp, n_k, need, pre, lane, term, term_mine, alive_mine, live, acc,
+                ok = sl_scan<RW, PW, SMALL_M>(hp, table, stride, hbp, n_k, need, pre, lane, term, term_mine, alive_mine, live, acc,
                                               sectors);
             else
                 ok = true;  // not reached: the host launches the lean kernel only where pre <= 2
@@ -486,7 +489,7 @@ PF_D bool sl_pair(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, uin
 #pragma unroll
             for (int pl = 0; pl < PW; ++pl) acc[pl] = 0xFFFFFFFFu;
         } else if constexpr (!LEAN) {
-            if (!sl_scan<RW, PW, SMALL_M>(hp, table, hbp, n_k, need, hp.K, lane, term, term_mine, alive_mine, live, acc, sectors))
+            if (!sl_scan<RW, PW, SMALL_M>(hp, table, stride, hbp, n_k, need, hp.K, lane, term, term_mine, alive_mine, live, acc, sectors))
                 return false;
         }
     }
@@ -589,54 +592,69 @@ static __global__ void __launch_bounds__(SL_THREADS, CTAS) sliced_probe_kernel(c
     if (lane == 0 && sectors_total) atomicAdd(a.counters, sectors_total);
 }
 
-// ---- entry depth, several tiles per pass -------------------------------------------------------------------------------
-// Every read meets every entry tile.  When those tiles only filter (filter_only, pre-test of 1 or 2 steps -- the usual plan)
-// a warp takes one read through up to SL_GROUP of them at once: the cached hash values are streamed and the row indices
-// derived ONCE per round (seeds and m are tree-global, so a k-mer's row index is the same in every table), and the rows of
-// all tables are in flight together.  Per tile the state is what sl_scan_shallow keeps: the bit-sliced count of possibly
-// present k-mers per column and the columns not yet ruled out; a tile drops out once none of its terminal columns is left,
-// the read once every tile has dropped out.  Outputs are those of the per-tile pairs (pair index = entry tile * n_chunk +
-// read), so everything downstream is unchanged.  Reads of up to 255 k-mers (8 count planes).
-constexpr int SL_GROUP = 4;
+// ---- entry depth on 128-byte lines ------------------------------------------------------------------------------------
+// Every read meets every entry tile, and a k-mer's row index is the same in every table (seeds and m are tree-global).  Past
+// the reach of the first-level TLB a random load costs the same per (instruction, 128-byte line) whether it brings 4 or 128
+// bytes (scripts/mb/mb_coop.cu: 36.7 G lines/s = 4.7 TB/s when four adjacent lanes take a line's four sectors in one
+// instruction, against 36.7 G sectors/s = 1.2 TB/s for a sector per lane).  So up to SL_QUAD entry tiles that only filter
+// (filter_only, pre-test of 1 or 2 steps -- the usual plan) have their tables interleaved row by row: row i of the shared
+// table is one line holding row i of each tile (32 bytes per tile, row_stride = 32 words), and a warp takes one read
+// through all of them at once.  Lane l serves tile l & 3; per round of 32 k-mers the warp issues four loads, load j
+// bringing the lines of k-mers 8 j + (l >> 2).  Each lane then holds four masks of ITS tile, adds them in place (3 planes)
+// and a reduce-scatter over the eight lanes of the tile (lane bits 2..4) leaves every lane with the 6-plane count of one
+// 32-column word: 32 lanes = 4 tiles x 8 words.  State per lane is what sl_scan_shallow keeps, for that one word: the
+// bit-sliced count of possibly present k-mers and the columns not yet ruled out; a tile drops out once none of its terminal
+// columns is left, the read once every tile has.  Outputs are those of the per-tile pairs (pair index = entry position *
+// n_chunk + read), so everything downstream is unchanged.
+constexpr int SL_QUAD = 4;
 
-template <int RW, bool SMALL_M>
-PF_D void sl_group_round(const HashParams &hp, const uint32_t *__restrict__ table, uint64_t i0, uint64_t i1, uint32_t steps,
-                         bool have, uint32_t lane, uint32_t (&acc)[8], uint32_t &sectors) {
-    uint32_t m[RW];
+// x: this lane's four masks (k-mers q, 8 + q, 16 + q, 24 + q of the round, q = lane >> 2) of the tile lane & 3.  Out: per
+// column of word sl_word_of_lane<8>(lane >> 2) of that tile, the number of the round's 32 k-mers whose mask has the bit set.
+PF_D void sl_quad_count(const uint32_t (&x)[4][8], uint32_t lane, uint32_t (&cnt)[6]) {
+    uint32_t a[6][8];
 #pragma unroll
-    for (int w = 0; w < RW; ++w) m[w] = 0u;
-    if (have) {
-        uint32_t r0[RW], r1[RW];
-        sl_load_row<RW>(table + i0 * RW, r0);
-#pragma unroll
-        for (int w = 0; w < RW; ++w) r1[w] = 0xFFFFFFFFu;
-        if (steps > 1u) sl_load_row<RW>(table + i1 * RW, r1);
-        sectors += steps;
-#pragma unroll
-        for (int w = 0; w < RW; ++w) m[w] = r0[w] & r1[w];
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t s1 = sl_xor3(x[0][w], x[1][w], x[2][w]), c1 = sl_maj(x[0][w], x[1][w], x[2][w]);
+        const uint32_t c2 = s1 & x[3][w];
+        a[0][w] = s1 ^ x[3][w];
+        a[1][w] = c1 ^ c2;
+        a[2][w] = c1 & c2;
     }
-    uint32_t cnt[6];
-    sl_count_columns<RW>(m, lane, cnt);
-    uint32_t carry = 0u;
 #pragma unroll
-    for (int pl = 0; pl < 8; ++pl) {
-        const uint32_t x = pl < 6 ? cnt[pl] : 0u;
-        const uint32_t sum = sl_xor3(acc[pl], x, carry);
-        carry = sl_maj(acc[pl], x, carry);
-        acc[pl] = sum;
+    for (int st = 0; st < 3; ++st) {
+        const int P = 3 + st, H = 8 >> (st + 1), bit = 2 + st;
+        const bool hi = (lane >> bit) & 1u;
+#pragma unroll
+        for (int w = 0; w < H; ++w) {
+            uint32_t carry = 0;
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl) {
+                const uint32_t lo_v = a[pl][w], hi_v = a[pl][w + H];
+                const uint32_t keep = hi ? hi_v : lo_v, send = hi ? lo_v : hi_v;
+                const uint32_t recv = __shfl_xor_sync(0xFFFFFFFFu, send, 1 << bit);
+                a[pl][w] = sl_xor3(keep, recv, carry);
+                carry = sl_maj(keep, recv, carry);
+            }
+            a[P][w] = carry;
+        }
     }
+#pragma unroll
+    for (int pl = 0; pl < 6; ++pl) cnt[pl] = a[pl][0];
 }
 
-template <bool SMALL_M>
-static __global__ void __launch_bounds__(SL_THREADS, 2) sliced_entry_group_kernel(const SlicedArgs a, uint32_t n_entry,
-                                                                                   uint32_t n_groups) {
+// n_entry: entry positions covered (the first n_entry entries of a.entry_tiles, SL_QUAD per group, the last group
+// possibly fewer); all tiles of a group share the table that starts at the first one's table_off.
+template <int PW, bool SMALL_M>
+static __global__ void __launch_bounds__(SL_THREADS, 3) sliced_entry_quad_kernel(const SlicedArgs a, uint32_t n_entry,
+                                                                                  uint32_t n_groups) {
     __shared__ uint32_t s_bits_all[SL_THREADS / 32][8];
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, q = lane >> 2;
+    const uint32_t my_word = sl_word_of_lane<8>(q);
+    const uint32_t sub_lanes = 0x11111111u << sub;  // the lanes serving my tile
     uint32_t *const s_bits = s_bits_all[threadIdx.x >> 5];
     const HashParams &hp = a.hp;
     const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
-    uint32_t sectors = 0u;
-    unsigned long long sectors_total = 0ULL;
+    unsigned long long lines_total = 0ULL;
     const uint32_t n_items = a.n_chunk * n_groups;  // item = group * n_chunk + read: group-major like the tile-major pairs
     for (;;) {
         uint32_t g0 = 0;
@@ -646,99 +664,91 @@ static __global__ void __launch_bounds__(SL_THREADS, 2) sliced_entry_group_kerne
         const uint32_t g1 = min(g0 + a.grab, n_items);
         for (uint32_t item = g0; item < g1; ++item) {
             const uint32_t grp = item / a.n_chunk, ri = item - grp * a.n_chunk, r = a.read0 + ri;
-            const uint32_t e0 = grp * SL_GROUP, ne = min((uint32_t)SL_GROUP, n_entry - e0);
+            const uint32_t e0 = grp * SL_QUAD, ne = min((uint32_t)SL_QUAD, n_entry - e0);
             const uint32_t n_k = kmers_of(ldg32(a.lengths + r), hp.k);
             const uint32_t need = need_of(a.threshold, n_k);
             if (need > n_k) continue;  // theta > 1: nothing can pass
             const uint64_t *__restrict__ hbp = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
-            const SlicedTileDev *tms[SL_GROUP];
-            uint32_t acc[SL_GROUP][8], alive[SL_GROUP], term_mine[SL_GROUP], rw[SL_GROUP], steps[SL_GROUP];
-            uint32_t live_tiles = 0u, any_two = 0u;
+            const bool tile_on = sub < ne;
+            const SlicedTileDev *tm_mine = a.tiles + ldg32(a.entry_tiles + e0 + (tile_on ? sub : 0u));
+            uint32_t alive = tile_on ? tm_mine->valid[my_word] : 0u;
+            const uint32_t term_mine = tile_on ? tm_mine->terminal[my_word] : 0u;
+            // a second probe step for every tile of the group as soon as one asks for it (more steps are never unsound)
+            const bool two = __any_sync(0xFFFFFFFFu, tile_on && tm_mine->pre_steps > 1u);
+            const uint32_t *__restrict__ slot = a.tables + (a.tiles + ldg32(a.entry_tiles + e0))->table_off + sub * 8u;
+            uint32_t acc[PW];
 #pragma unroll
-            for (int t = 0; t < SL_GROUP; ++t) {
-                tms[t] = a.tiles + ldg32(a.entry_tiles + min(e0 + (uint32_t)t, n_entry - 1u));
-                rw[t] = tms[t]->row_words;
-                steps[t] = tms[t]->pre_steps;
-                uint32_t w_mine = 0u;
-                switch (rw[t]) {
-                    case 8: w_mine = sl_word_of_lane<8>(lane); break;
-                    case 4: w_mine = sl_word_of_lane<4>(lane); break;
-                    case 2: w_mine = sl_word_of_lane<2>(lane); break;
-                    default: w_mine = 0u; break;
-                }
-                alive[t] = tms[t]->valid[w_mine];
-                term_mine[t] = tms[t]->terminal[w_mine];
-#pragma unroll
-                for (int pl = 0; pl < 8; ++pl) acc[t][pl] = 0u;
-                if ((uint32_t)t < ne) {
-                    live_tiles |= 1u << t;
-                    any_two |= steps[t] > 1u;
-                }
-            }
+            for (int pl = 0; pl < PW; ++pl) acc[pl] = 0u;
+            uint32_t live = __ballot_sync(0xFFFFFFFFu, (alive & term_mine) != 0u);  // lanes whose word still holds a terminal
             if (n_k != 0u && need != 0u) {  // need == 0: every column passes (query.rs:48)
-                for (uint32_t base = 0; base < n_k && live_tiles; base += 32u) {
+                for (uint32_t base = 0; base < n_k && live; base += 32u) {
                     const bool have = base + lane < n_k;
                     const uint64_t hbv = have ? sl_ld_stream(hbp + base + lane) : 0ULL;
                     const uint64_t h1 = fx_finish(hp.c1, hbv, hp.rot);
                     uint64_t i0, i1 = 0ULL;
                     if (SMALL_M) i0 = mod_small(h1, M0, M1, m32);
                     else i0 = mod_any(h1, hp.m, hp.M);
-                    if (any_two) {
+                    if (two) {
                         const uint64_t h2 = fx_finish(hp.c2, hbv, hp.rot);
                         if (SMALL_M) i1 = mod_small(h2, M0, M1, m32);
                         else i1 = mod_any(h2, hp.m, hp.M);
                     }
-                    const uint32_t done = min(base + 32u, n_k), rest = n_k - done;
+                    const bool mine_live = (live & sub_lanes) != 0u;
+                    uint32_t x[4][8];
 #pragma unroll
-                    for (int t = 0; t < SL_GROUP; ++t) {
-                        if (!((live_tiles >> t) & 1u)) continue;  // warp-uniform
-                        const uint32_t *__restrict__ table = a.tables + tms[t]->table_off;
-                        switch (rw[t]) {
-                            case 8: sl_group_round<8, SMALL_M>(hp, table, i0, i1, steps[t], have, lane, acc[t], sectors); break;
-                            case 4: sl_group_round<4, SMALL_M>(hp, table, i0, i1, steps[t], have, lane, acc[t], sectors); break;
-                            case 2: sl_group_round<2, SMALL_M>(hp, table, i0, i1, steps[t], have, lane, acc[t], sectors); break;
-                            default: sl_group_round<1, SMALL_M>(hp, table, i0, i1, steps[t], have, lane, acc[t], sectors); break;
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t kk = 8u * j + q;
+                        uint64_t r0i, r1i = 0ULL;
+                        if (SMALL_M) {
+                            r0i = __shfl_sync(0xFFFFFFFFu, (uint32_t)i0, kk);
+                            if (two) r1i = __shfl_sync(0xFFFFFFFFu, (uint32_t)i1, kk);
+                        } else {
+                            r0i = __shfl_sync(0xFFFFFFFFu, (unsigned long long)i0, kk);
+                            if (two) r1i = __shfl_sync(0xFFFFFFFFu, (unsigned long long)i1, kk);
                         }
-                        if (need > rest) {
-                            alive[t] &= sl_ge<8>(acc[t], need - rest);
-                            if (!__any_sync(0xFFFFFFFFu, (alive[t] & term_mine[t]) != 0u)) live_tiles &= ~(1u << t);
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) x[j][w] = 0u;
+                        if (mine_live && base + kk < n_k) {
+                            sl_load_row<8>(slot + r0i * 32u, x[j]);
+                            if (two) {
+                                uint32_t y[8];
+                                sl_load_row<8>(slot + r1i * 32u, y);
+#pragma unroll
+                                for (int w = 0; w < 8; ++w) x[j][w] &= y[w];
+                            }
                         }
+                    }
+                    const uint32_t done = min(base + 32u, n_k), rest = n_k - done;
+                    if (lane == 0u) lines_total += (unsigned long long)(done - base) * (two ? 2u : 1u);
+                    uint32_t cnt[6];
+                    sl_quad_count(x, lane, cnt);
+                    uint32_t carry = 0u;
+#pragma unroll
+                    for (int pl = 0; pl < PW; ++pl) {
+                        const uint32_t v = pl < 6 ? cnt[pl] : 0u;
+                        const uint32_t sum = sl_xor3(acc[pl], v, carry);
+                        carry = sl_maj(acc[pl], v, carry);
+                        acc[pl] = sum;
+                    }
+                    // a column cannot pass any more once its count plus all remaining k-mers stays below `need`
+                    if (need > rest) {
+                        alive &= sl_ge<PW>(acc, need - rest);
+                        live = __ballot_sync(0xFFFFFFFFu, (alive & term_mine) != 0u);
                     }
                 }
             }
             // columns the pre-test could not rule out count as passed (filter-only tiles: the exact tiles below decide)
-#pragma unroll
-            for (int t = 0; t < SL_GROUP; ++t) {
-                if (!((live_tiles >> t) & 1u)) continue;
-                const uint32_t pair = (e0 + (uint32_t)t) * a.n_chunk + ri;
-                switch (rw[t]) {
-                    case 8: {
-                        uint32_t reach[8];
-                        if (sl_reach<8>(a, tms[t], NONE32_D, lane, s_bits, alive[t], reach)) sl_record<8>(a, tms[t], pair, lane, reach);
-                        break;
-                    }
-                    case 4: {
-                        uint32_t reach[4];
-                        if (sl_reach<4>(a, tms[t], NONE32_D, lane, s_bits, alive[t], reach)) sl_record<4>(a, tms[t], pair, lane, reach);
-                        break;
-                    }
-                    case 2: {
-                        uint32_t reach[2];
-                        if (sl_reach<2>(a, tms[t], NONE32_D, lane, s_bits, alive[t], reach)) sl_record<2>(a, tms[t], pair, lane, reach);
-                        break;
-                    }
-                    default: {
-                        uint32_t reach[1];
-                        if (sl_reach<1>(a, tms[t], NONE32_D, lane, s_bits, alive[t], reach)) sl_record<1>(a, tms[t], pair, lane, reach);
-                        break;
-                    }
-                }
+            for (uint32_t t = 0; t < ne; ++t) {
+                // this tile's words to where sl_reach expects them: lane l holds word sl_word_of_lane<8>(l)
+                const uint32_t pass_t = __shfl_sync(0xFFFFFFFFu, alive, 4u * (lane & 7u) + t);
+                if (!(live & (0x11111111u << t))) continue;  // warp-uniform
+                const SlicedTileDev *tm = a.tiles + ldg32(a.entry_tiles + e0 + t);
+                uint32_t reach[8];
+                if (sl_reach<8>(a, tm, NONE32_D, lane, s_bits, pass_t, reach)) sl_record<8>(a, tm, (e0 + t) * a.n_chunk + ri, lane, reach);
             }
         }
-        sectors_total += __reduce_add_sync(0xFFFFFFFFu, sectors);
-        sectors = 0u;
     }
-    if (lane == 0 && sectors_total) atomicAdd(a.counters, sectors_total);
+    if (lane == 0 && lines_total) atomicAdd(a.counters + 3, lines_total);
 }
 
 // Second pass over the pairs that have an output: leaf hits go to the hit list and the per-leaf histogram
@@ -842,7 +852,8 @@ static __global__ void __launch_bounds__(256) slice_kernel(const uint64_t *__res
                                                            uint32_t *tables) {
     const uint32_t t = tile0 + blockIdx.y;
     const SlicedTileDev *tm = tiles + t;
-    const uint32_t rw = tm->row_words;
+    const uint32_t stride = tm->row_stride;
+    const uint32_t rw = stride == 32u ? 8u : tm->row_words;  // a slot in a shared line is written whole (unused columns: zero)
     const uint32_t wj = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     if (wj >= rw) return;
     const uint32_t slot = col_slot[(size_t)t * SL_MAX_COLS + 32u * wj + lane];
@@ -855,7 +866,7 @@ static __global__ void __launch_bounds__(256) slice_kernel(const uint64_t *__res
         const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
         x[0] = v0.x, x[1] = v0.y, x[2] = v0.z, x[3] = v0.w, x[4] = v1.x, x[5] = v1.y, x[6] = v1.z, x[7] = v1.w;
     }
-    uint32_t *out = tables + tm->table_off + (w0 * 32u) * rw + wj;
+    uint32_t *out = tables + tm->table_off + (w0 * 32u) * stride + wj;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         uint32_t mine = 0u;
@@ -864,7 +875,7 @@ static __global__ void __launch_bounds__(256) slice_kernel(const uint64_t *__res
             const uint32_t v = __ballot_sync(0xFFFFFFFFu, (x[i] >> b) & 1u);
             if (lane == (uint32_t)b) mine = v;
         }
-        out[((uint64_t)i * 32u + lane) * rw] = mine;  // row 32 (w0 + i) + lane, word wj
+        out[((uint64_t)i * 32u + lane) * stride] = mine;  // row 32 (w0 + i) + lane, word wj
     }
 }
 
