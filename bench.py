@@ -518,8 +518,16 @@ def run_ours(args, cfg):
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             tj = tj.get(args.config) or tj.get({"cfg3": "cfg3s", "cfg4": "cfg3s"}.get(args.config, ""), {})
-            key = "sliced_probe_kernel" if sliced else "probe_kernel"
-            traffic, traffic_src = tj.get(key + "_dram_bytes_per_launch"), tj.get("source")
+            if sliced:
+                # mean over the launches of both sliced kernels (entry line kernel + the depths below), as `achieved` is
+                tot = sum(tj.get(k + "_dram_bytes_per_launch", 0.0) * tj.get(k + "_launches", 0)
+                          for k in ("sliced_entry_quad_kernel", "sliced_probe_kernel"))
+                cnt = sum(tj.get(k + "_launches", 0) for k in ("sliced_entry_quad_kernel", "sliced_probe_kernel")
+                          if k + "_dram_bytes_per_launch" in tj)
+                traffic = tot / cnt if cnt else None
+            else:
+                traffic = tj.get("probe_kernel_dram_bytes_per_launch")
+            traffic_src = tj.get("source")
         rate = C.c_double(0)
         if sliced:
             # one 32 B sector per row load (each answers one probe step for every node of the tile) + the
@@ -527,27 +535,32 @@ def run_ours(args, cfg):
             alg_bytes = 32 * sectors + 128 * lines
             achieved = alg_bytes / (sliced_ms * 1e-3) / 1e9 if sliced_ms > 0 else 0.0
             peaks = {}
-            for name, nbytes in (("one_entry_table_460MB", int(info.words_per_filter) * 8 * 256),
+            for name, nbytes in (("one_256_column_table", int(info.words_per_filter) * 8 * 256),
                                  ("all_tables", min(max(int(st.sliced_table_bytes), 1 << 20), 48 << 30))):
                 _lib.check(L.pf_microbench_sectors(local_rank, max(nbytes, 1 << 20), 60, C.byref(rate)))
                 peaks[name] = rate.value
-            rs_peak = peaks["one_entry_table_460MB"]
+            rs_peak = peaks["all_tables"]
             sect_rate = (sectors + lines) / (sliced_ms * 1e-3) if sliced_ms > 0 else 0.0  # random accesses (sector or line)
             roofline = {
-                "bound": "hbm", "kernel": "sliced_probe_kernel (+ sliced_entry_group_kernel at the entry depth: same row gathers)",
+                "bound": "hbm",
+                "kernel": "sliced_entry_quad_kernel (entry depth: one 128 B line per k-mer and probe step answers up to 1024 "
+                          "nodes) + sliced_probe_kernel (depths below: one 32 B sector per k-mer and step, up to 256 nodes)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "note": "random 32 B row gathers over tables far larger than L2: the binding roof is the random-sector rate "
-                        "of HBM (micro-benchmark below, same footprint), about 1/5 of the streaming-copy peak in `peak`; ncu "
-                        "(profiles/r2r_cfg3s_*) shows the DRAM pipe 77 % busy on the HBM-bound launch, each missed 32 B sector "
-                        "costing ~105 B of DRAM traffic -- `traffic` is that capture's dram bytes per launch (stand-in config "
-                        "cfg3s for cfg3/cfg4: ncu cannot replay kernels over 72 GB of device memory)",
+                "note": "random gathers over tables far larger than L2 and than the 256 MB reach of the first-level TLB: "
+                        "what binds is the rate of random ACCESSES (about 37 G/s on this part whether an access brings 4, 32 "
+                        "or -- four adjacent lanes on one line -- 128 bytes: scripts/mb/mb_coop.cu, profiles/r2x_mb_*), not "
+                        "bytes; `random_access_peak_per_s` is that rate measured in this process over the same footprint, "
+                        "`frac_of_random_access_peak` the kernels' accesses (sector or line loads) against it, `frac` the "
+                        "useful bytes they bring against the streaming-copy peak.  `traffic`: dram bytes per launch from the "
+                        "ncu capture named in traffic_source (stand-in config for cfg3/cfg4: ncu's kernel replay has to save "
+                        "and restore 72 GB of device memory there)",
                 "algorithmic_bytes_per_launch": alg_bytes / n_sliced_launch, "launches_per_step": n_sliced_launch // steps,
                 "avg_launch_ms": sliced_ms / n_sliced_launch,
                 "kernel_share_of_step": sliced_ms / float(st.device_ms) if st.device_ms else None,
-                "sectors_per_s": sect_rate,
-                "random_sector_peak_per_s": peaks,
-                "frac_of_random_sector_peak": sect_rate / rs_peak if rs_peak else None,
+                "random_accesses_per_s": sect_rate, "sector_loads": sectors, "line_loads": lines,
+                "random_access_peak_per_s": peaks,
+                "frac_of_random_access_peak": sect_rate / rs_peak if rs_peak else None,
                 "tiles": int(st.sliced_tiles), "table_bytes": int(st.sliced_table_bytes),
                 "handed_over_to_probe_kernel": {
                     "note": "reads the tiles could not rule out continue node by node (probe_kernel, L2-resident filters)",

@@ -304,6 +304,9 @@ int sliced_begin_block(pf_db *db);
 int sliced_set_hit_cursor(pf_db *db, uint64_t hits);
 uint64_t sliced_entry_tiles(const pf_db *db);
 bool sliced_hybrid(const pf_db *db);
+// hf: null, or the chunk's hash-kernel arguments when the entry line kernel hashes on the fly (sliced_fused) -- the hash
+// values of the reads that survive the entry depth are then made here, between the entry depth and the next one
 int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint64_t kmer_base, uint32_t r0,
-               uint32_t n_chunk, Descent &st);
+               uint32_t n_chunk, Descent &st, const HashArgs *hf);
+bool sliced_fused(const pf_db *db, const pf_dev_batch *bt);
 }  // namespace pf

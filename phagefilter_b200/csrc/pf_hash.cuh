@@ -210,4 +210,25 @@ PF_D uint64_t canonical_hash_2bit(uint64_t x) {
     return mulmix(s0, s1) ^ (uint64_t)KM;
 }
 
+// The same with k (17..32) known only at run time: for kernels that hash on the fly next to other work and cannot afford
+// one instantiation per k (the entry line kernel of the sliced path).  A few selects and variable shifts more.
+PF_D uint64_t canonical_hash_2bit_rt(uint64_t x, uint32_t k) {
+    const uint64_t mask = k >= 32u ? ~0ULL : ((1ULL << (2u * k)) - 1ULL);
+    const uint64_t F = x & mask;
+    const uint64_t R = rev2(~x) >> (64u - 2u * k);
+    const uint64_t C = F < R ? F : R;
+    const uint32_t c0 = (uint32_t)C, c1 = (uint32_t)(C >> 32);
+    const uint64_t W0 = expand8(c0), W1 = expand8(c0 >> 16), W2 = expand8(c1), W3 = expand8(c1 >> 16);
+    auto bytes_at = [&](uint32_t o) -> uint64_t {  // le64 of bytes [o, o + 8), 1 <= o <= 24; o + 8 <= k, so W3 is only read for k > 24
+        const uint32_t q = o >> 3, sh = 8u * (o & 7u);
+        const uint64_t a = q == 0u ? W0 : (q == 1u ? W1 : (q == 2u ? W2 : W3));
+        const uint64_t b = q == 0u ? W1 : (q == 1u ? W2 : W3);
+        return sh ? (a >> sh) | (b << (64u - sh)) : a;
+    };
+    const uint64_t t = mulmix(FX_SEED1 ^ W0, FX_PREVENT ^ W1);
+    const uint64_t s0 = FX_SEED2 ^ bytes_at(k - 16u);
+    const uint64_t s1 = t ^ bytes_at(k - 8u);
+    return mulmix(s0, s1) ^ (uint64_t)k;
+}
+
 }  // namespace pf

@@ -908,6 +908,12 @@ static __global__ void flag_reads_kernel(const uint32_t *__restrict__ reads, uns
         flag[reads[i]] = 1;
 }
 
+// flag[r] = 1 for the exception reads (bytes other than upper-case ACGT) among reads [r0, r0 + n), 0 for the others
+static __global__ void flag_exc_kernel(const uint32_t *__restrict__ exc_index, uint32_t r0, uint32_t n, uint8_t *flag) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        flag[r0 + i] = exc_index[r0 + i] != NONE32_D;
+}
+
 static __global__ void zero_kernel(uint4 *p, size_t n16) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
         p[i] = make_uint4(0u, 0u, 0u, 0u);

@@ -949,17 +949,17 @@ int pf::finish_csr(pf_db *db, uint32_t n_reads, uint64_t hits_total, int want_hi
 // Between the tiles and the node-at-a-time descent (hybrid evaluation): flag the reads that own a handed-over pair, give
 // them step-0 indices (hash kernel restricted to flagged reads), and make the running hit total the level scan continues
 // from equal to what the tiles have already emitted.
-static int hand_over(pf_db *db, const pf_dev_batch *bt, HashArgs h, uint64_t chunk_kmers, Descent &st) {
+static int hand_over(pf_db *db, const pf_dev_batch *bt, HashArgs h, uint64_t chunk_kmers, bool fused, Descent &st) {
     cudaStream_t s = db->stream;
     int rc;
     const uint64_t n_inj = db->inj_level_off.back();
-    if (db->hp.small_m) {
-        if ((rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
+    if (db->hp.small_m || fused) {  // fused: the entry depth hashed on the fly, the survivors' values are cached only now
+        if (db->hp.small_m && (rc = db->idx0.ensure(std::max<uint64_t>(chunk_kmers, 1)))) return rc;
         if ((rc = db->read_flag.ensure(bt->n_reads))) return rc;
         PF_CUDA_OK(cudaMemsetAsync(db->read_flag.p, 0, bt->n_reads, s));
         flag_reads_kernel<<<(uint32_t)std::min<uint64_t>((n_inj + 255) / 256, 65535), 256, 0, s>>>(db->inj_read, n_inj, db->read_flag.p);
         PF_CUDA_OK(cudaMemsetAsync(h.work_ctr, 0, 4, s));
-        h.idx0 = db->idx0.p;
+        h.idx0 = db->hp.small_m ? db->idx0.p : nullptr;
         h.flags = db->read_flag.p;
         launch_hash(h, db->sm_count * 8, s);
         st.other_launches += 2;
@@ -1058,7 +1058,20 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
         h.k = db->hp.k;
         h.work_ctr = db->d_work + n_levels;
         h.grab = hash_grab(bt->max_kmers);
-        if (chunk_kmers) {
+        // Sliced path with every entry tile on shared lines: the entry kernel hashes on the fly and only the reads that
+        // survive it get their values cached (run_sliced); reads with bytes other than ACGT are hashed here, byte-exact.
+        const bool fused = sliced && sliced_fused(db, bt);
+        if (fused) {
+            if (bt->n_exc && chunk_kmers) {
+                if ((rc = db->read_flag.ensure(bt->n_reads))) return rc;
+                flag_exc_kernel<<<(uint32_t)std::min<uint32_t>((n_chunk + 255) / 256, 4096), 256, 0, s>>>(bt->exc_index.p, r0, n_chunk,
+                                                                                                           db->read_flag.p);
+                HashArgs he = h;
+                he.flags = db->read_flag.p;
+                launch_hash(he, db->sm_count * 8, s);
+                st.other_launches += 2;
+            }
+        } else if (chunk_kmers) {
             launch_hash(h, db->sm_count * 8, s);
             st.other_launches++;
         }
@@ -1069,11 +1082,11 @@ static int query_impl(pf_db *db, const pf_dev_batch *bt, float threshold, int wa
             // the tiles append hits through their own cursor: it continues where the block's hit list stands (earlier
             // chunks may have added hits through the node-at-a-time descent after a hand-over)
             if (r0 != 0 && (rc = sliced_set_hit_cursor(db, st.hits_total))) return rc;
-            rc = run_sliced(db, bt, threshold, want_hits, kmer_base, r0, n_chunk, st);
+            rc = run_sliced(db, bt, threshold, want_hits, kmer_base, r0, n_chunk, st, fused ? &h : nullptr);
             if (rc == PF_OK && sliced_hybrid(db) && !db->inj_level_off.empty() && db->inj_level_off.back() > 0) {
                 // the reads that survived the tiles go down the tree node by node.  That descent uses the step-0 bit indices
                 // next to the hash values; they are made now, for the surviving reads only.
-                rc = hand_over(db, bt, h, chunk_kmers, st);
+                rc = hand_over(db, bt, h, chunk_kmers, fused, st);
                 if (rc == PF_OK) rc = run_levels(db, bt, threshold, want_hits, G, kmer_base, 0, n_levels, r0, 0, st);
                 db->inj_level_off.clear();
             }

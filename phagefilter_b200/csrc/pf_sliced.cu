@@ -236,6 +236,9 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
     const size_t nn = db->n_nodes;
     const uint32_t K = db->geom.num_hashes;
     const size_t MAXC = std::min<size_t>(std::max<uint32_t>(db->tile_cols, 32u), SL_MAX_COLS);  // columns per tile
+    // tiles below the cut: a narrower tile is a smaller table (PF_SLICED_SUB_COLS, experiment)
+    static const size_t sub_env = getenv("PF_SLICED_SUB_COLS") ? (size_t)atoi(getenv("PF_SLICED_SUB_COLS")) : 0;
+    const size_t MAXS = sub_env >= 32 ? std::min(MAXC, sub_env) : MAXC;
     S.tiles.clear();
     S.col_slot.clear();
     S.child_tile.clear();
@@ -271,29 +274,35 @@ static void tile_tree(const pf_db *db, const TreeFacts &F, SlicedState &S, bool 
         // entry tiles see every read: roots side by side, as few tiles as possible.  Below them come the reads that
         // (mostly) belong there: whole subtrees, several per tile, so that such a read needs one more tile only.
         for (uint32_t r : job.roots) (job.parent_tile < 0 ? RA : RB).push_back(r);
+        // nodes that can serve as pure filters (interior, verified subtree) first: the entry tiles made of them alone can
+        // share 128-byte lines (layout_tables); leaves and unverified nodes of the cut gather in the last tiles
+        auto filt_node = [&](uint32_t u) { return db->h_leaf[u] < 0 && F.vb[u]; };
+        std::stable_partition(RA.begin(), RA.end(), filt_node);
         for (size_t c0 = 0; c0 < RA.size(); c0 += MAXC) {
             std::vector<uint32_t> cols(RA.begin() + c0, RA.begin() + std::min(RA.size(), c0 + MAXC));
             const size_t cap = std::min<size_t>(width_for(cols.size()), MAXC);
+            bool pure = true;
+            for (uint32_t u : cols) pure = pure && filt_node(u);
             for (size_t i = 0; i < cols.size() && cols.size() < cap; ++i)
                 for (uint32_t c : {db->h_left[cols[i]], db->h_right[cols[i]]})
-                    if (c != NONE32 && cols.size() < cap) cols.push_back(c);
+                    if (c != NONE32 && cols.size() < cap && (!pure || filt_node(c))) cols.push_back(c);
             made.push_back(std::move(cols));
         }
         std::vector<uint32_t> cur;
         for (uint32_t r : RB) {
-            if (F.sz[r] <= (uint32_t)MAXC) {
-                if (cur.size() + F.sz[r] > MAXC) {
+            if (F.sz[r] <= (uint32_t)MAXS) {
+                if (cur.size() + F.sz[r] > MAXS) {
                     made.push_back(std::move(cur));
                     cur.clear();
                 }
-                bfs_subtree(r, MAXC, cur);
+                bfs_subtree(r, MAXS, cur);
             } else {
                 if (!cur.empty()) {
                     made.push_back(std::move(cur));
                     cur.clear();
                 }
                 std::vector<uint32_t> cols;
-                bfs_subtree(r, MAXC, cols);
+                bfs_subtree(r, MAXS, cols);
                 made.push_back(std::move(cols));
             }
         }
@@ -784,23 +793,36 @@ static void launch_sliced(const SlicedArgs &a, int sm_count, bool lean, cudaStre
     }
 }
 
+template <bool FUSE>
 static void launch_quad(const SlicedArgs &a, uint64_t max_kmers, uint32_t n_entry, uint32_t n_groups, int sm_count, cudaStream_t s) {
     const int grid = sm_count * 3;
     if (max_kmers < 256) {
-        if (a.hp.small_m) sliced_entry_quad_kernel<8, true><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
-        else sliced_entry_quad_kernel<8, false><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        if (a.hp.small_m) sliced_entry_quad_kernel<8, true, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        else sliced_entry_quad_kernel<8, false, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
     } else if (max_kmers < 65536) {
-        if (a.hp.small_m) sliced_entry_quad_kernel<16, true><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
-        else sliced_entry_quad_kernel<16, false><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        if (a.hp.small_m) sliced_entry_quad_kernel<16, true, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        else sliced_entry_quad_kernel<16, false, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
     } else {
-        if (a.hp.small_m) sliced_entry_quad_kernel<32, true><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
-        else sliced_entry_quad_kernel<32, false><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        if (a.hp.small_m) sliced_entry_quad_kernel<32, true, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        else sliced_entry_quad_kernel<32, false, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
     }
+}
+
+// The entry depth can make its hash values itself when every entry tile goes through the line kernel and k fits the 2-bit
+// register path: nothing downstream needs the values of the reads that do not survive (with tiles below the cut,
+// run_sliced has the survivors hashed before the next depth; with a hand-over to the node-at-a-time descent, hand_over
+// does, together with their step-0 indices).
+bool sliced_fused(const pf_db *db, const pf_dev_batch *bt) {
+    static const bool off = getenv("PF_SLICED_NO_FUSE") != nullptr || getenv("PF_SLICED_NO_QUAD") != nullptr;
+    if (off || !db->sliced) return false;
+    const SlicedState &S = *db->sliced;
+    (void)bt;
+    return S.n_quad_now >= 2 && S.n_quad_now == S.entry_tiles.size() && db->hp.k >= 17 && db->hp.k <= 32;
 }
 
 // The tile-level descent for reads [r0, r0 + n_chunk) of the batch whose hash values are cached in db->hb.
 int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits, uint64_t kmer_base, uint32_t r0,
-               uint32_t n_chunk, Descent &st) {
+               uint32_t n_chunk, Descent &st, const HashArgs *hf) {
     SlicedState &S = *db->sliced;
     cudaStream_t s = db->stream;
     const size_t nt = S.tiles.size();
@@ -859,7 +881,17 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
             const uint32_t n_groups = (n_grouped + SL_QUAD - 1) / SL_QUAD;
             SlicedArgs g = a;
             g.grab = bt->max_kmers <= 256 ? 4u : 1u;
-            launch_quad(g, bt->max_kmers, n_grouped, n_groups, db->sm_count, s);
+            if (hf) {
+                if ((rc = db->read_flag.ensure(bt->n_reads))) return rc;
+                PF_CUDA_OK(cudaMemsetAsync(db->read_flag.p + r0, 0, n_chunk, s));
+                g.packed = hf->packed;
+                g.word_off = hf->word_off;
+                g.exc_index = hf->exc_index;
+                g.surv_flags = db->read_flag.p;
+                launch_quad<true>(g, bt->max_kmers, n_grouped, n_groups, db->sm_count, s);
+            } else {
+                launch_quad<false>(g, bt->max_kmers, n_grouped, n_groups, db->sm_count, s);
+            }
             st.probe_launches++;
         }
         if (!entry || n_grouped < S.entry_tiles.size()) {
@@ -953,6 +985,14 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
             }
             const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_alive + 7) / 8, (uint64_t)db->sm_count * 8);
             sliced_emit_kernel<<<blocks, 256, 0, s>>>(e);
+            st.other_launches++;
+        }
+        if (entry && hf && next_n) {
+            // the entry depth made its hash values on the fly: the reads that go on get theirs cached now
+            HashArgs h = *hf;
+            h.flags = db->read_flag.p;
+            PF_CUDA_OK(cudaMemsetAsync(h.work_ctr, 0, 4, s));
+            launch_hash(h, db->sm_count * 8, s);
             st.other_launches++;
         }
         st.hits_total += hits;

@@ -70,6 +70,12 @@ struct SlicedArgs {
     HashParams hp;
     float threshold;
     uint32_t grab;
+    // entry line kernel hashing on the fly (FUSE): the 2-bit reads themselves; hash values are then cached only for the
+    // reads that survive the entry depth (flagged here, hashed by hash_kernel restricted to the flags)
+    const uint32_t *packed;
+    const uint64_t *word_off;
+    const uint32_t *exc_index;   // reads with bytes other than ACGT keep the cached path (hashed beforehand); may be null
+    uint8_t *surv_flags;         // [batch reads] set for every read with a recorded pair; null when not fused
 };
 
 template <int RW>
@@ -529,6 +535,7 @@ PF_D void sl_record(const SlicedArgs &a, const SlicedTileDev *__restrict__ tm, u
     if (lane == 0u) {
         const unsigned long long slot = atomicAdd(a.counters + 1, 1ULL);
         a.alive[slot] = pair;
+        if (a.surv_flags) a.surv_flags[a.fr_read ? ldg32(a.fr_read + pair) : a.read0 + pair % a.n_chunk] = 1;
         if (hits) atomicAdd(a.counters + 2, (unsigned long long)hits);
     }
     for (uint32_t c = lane; c < tm->n_children; c += 32u) {
@@ -644,7 +651,10 @@ PF_D void sl_quad_count(const uint32_t (&x)[4][8], uint32_t lane, uint32_t (&cnt
 
 // n_entry: entry positions covered (the first n_entry entries of a.entry_tiles, SL_QUAD per group, the last group
 // possibly fewer); all tiles of a group share the table that starts at the first one's table_off.
-template <int PW, bool SMALL_M>
+// FUSE: the hash values are not read from the cache but made on the spot from the 2-bit read (17 <= k <= 32; reads with
+// other bytes than ACGT were hashed beforehand and keep the cached path) -- nine reads in ten leave after two or three
+// rounds, so most of the batch is never hashed completely nor written to and read back from HBM.
+template <int PW, bool SMALL_M, bool FUSE>
 static __global__ void __launch_bounds__(SL_THREADS, 3) sliced_entry_quad_kernel(const SlicedArgs a, uint32_t n_entry,
                                                                                   uint32_t n_groups) {
     __shared__ uint32_t s_bits_all[SL_THREADS / 32][8];
@@ -669,6 +679,16 @@ static __global__ void __launch_bounds__(SL_THREADS, 3) sliced_entry_quad_kernel
             const uint32_t need = need_of(a.threshold, n_k);
             if (need > n_k) continue;  // theta > 1: nothing can pass
             const uint64_t *__restrict__ hbp = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
+            bool on_the_fly = false;
+            const uint64_t *w64 = nullptr;
+            uint64_t lo = 0ULL;
+            if (FUSE) {
+                on_the_fly = !a.exc_index || ldg32(a.exc_index + r) == NONE32_D;
+                if (on_the_fly && n_k != 0u) {
+                    w64 = reinterpret_cast<const uint64_t *>(a.packed + __ldg(a.word_off + r));
+                    lo = __ldg(w64);
+                }
+            }
             const bool tile_on = sub < ne;
             const SlicedTileDev *tm_mine = a.tiles + ldg32(a.entry_tiles + e0 + (tile_on ? sub : 0u));
             uint32_t alive = tile_on ? tm_mine->valid[my_word] : 0u;
@@ -683,7 +703,15 @@ static __global__ void __launch_bounds__(SL_THREADS, 3) sliced_entry_quad_kernel
             if (n_k != 0u && need != 0u) {  // need == 0: every column passes (query.rs:48)
                 for (uint32_t base = 0; base < n_k && live; base += 32u) {
                     const bool have = base + lane < n_k;
-                    const uint64_t hbv = have ? sl_ld_stream(hbp + base + lane) : 0ULL;
+                    uint64_t hbv;
+                    if (FUSE && on_the_fly) {  // as hash_kernel: the 32 bases from position base + lane on, canonical, hashed
+                        const uint64_t hi = __ldg(w64 + (base >> 5) + 1);
+                        const uint32_t sh = 2u * lane;
+                        hbv = canonical_hash_2bit_rt((lo >> sh) | ((hi << 1) << (63u - sh)), hp.k);
+                        lo = hi;
+                    } else {
+                        hbv = have ? sl_ld_stream(hbp + base + lane) : 0ULL;
+                    }
                     const uint64_t h1 = fx_finish(hp.c1, hbv, hp.rot);
                     uint64_t i0, i1 = 0ULL;
                     if (SMALL_M) i0 = mod_small(h1, M0, M1, m32);

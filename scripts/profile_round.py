@@ -29,6 +29,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CMD = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--profile"]
 CONFIG = "cfg2"
+HOT = ("hash_kernel", "probe_kernel", "sliced_entry_quad_kernel")  # the kernels the full-set pass captures
 TIMED_STEP = 4  # 1-based index of the timed step among the hash_kernel launches
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
@@ -54,13 +55,20 @@ def read_launch_list(path):
     return rows
 
 
+def step_marker(rows):
+    """The kernel a step starts with: the entry line kernel when it hashes on the fly (hash_kernel then runs in the middle
+    of the step, for the surviving reads only), else hash_kernel."""
+    return "sliced_entry_quad_kernel" if any("sliced_entry_quad_kernel" in r[1] for r in rows) else "hash_kernel"
+
+
 def timed_step(rows):
-    hashes = [i for i, r in enumerate(rows) if "hash_kernel" in r[1]]
+    marker = step_marker(rows)
+    hashes = [i for i, r in enumerate(rows) if marker in r[1]]
     if len(hashes) < TIMED_STEP:
-        raise SystemExit(f"expected at least {TIMED_STEP} hash_kernel launches, found {len(hashes)}")
+        raise SystemExit(f"expected at least {TIMED_STEP} {marker} launches, found {len(hashes)}")
     lo = hashes[TIMED_STEP - 1]
     hi = hashes[TIMED_STEP] if len(hashes) > TIMED_STEP else len(rows)
-    return [r for r in rows[lo:hi] if "pf::" in r[1] or "hash_kernel" in r[1] or "probe_kernel" in r[1]]
+    return [r for r in rows[lo:hi] if "pf::" in r[1] or any(k in r[1] for k in HOT)]
 
 
 def cmd_run(tag, no_bench=False, launches_only=False):
@@ -78,11 +86,11 @@ def cmd_run(tag, no_bench=False, launches_only=False):
     if launches_only:
         print("launch list only:", len(rows), "launches")
         return
-    sel = [r for r in rows if "hash_kernel" in r[1] or "probe_kernel" in r[1]]
-    step = [r for r in timed_step(rows) if "hash_kernel" in r[1] or "probe_kernel" in r[1]]
+    sel = [r for r in rows if any(k in r[1] for k in HOT)]
+    step = [r for r in timed_step(rows) if any(k in r[1] for k in HOT)]
     skip = sel.index(step[0])
     rep = os.path.join(out, "full")
-    subprocess.run(["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", "regex:hash_kernel|probe_kernel",
+    subprocess.run(["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", "regex:" + "|".join(HOT),
                     "-s", str(skip), "-c", str(len(step)), "-f", "-o", rep, *CMD], check=True, stdout=subprocess.DEVNULL)
     with open(os.path.join(out, "full_raw.csv"), "w") as f:
         subprocess.run(["ncu", "-i", rep + ".ncu-rep", "--page", "raw", "--csv"], check=True, stdout=f)
@@ -142,7 +150,7 @@ def cmd_summarise(tag):
     if "probe_kernel_dram_bytes_per_launch" in tj:  # round-1 layout: one flat entry for cfg2
         tj = {"cfg2": tj}
     entry = {}
-    for key in ("sliced_probe_kernel", "probe_kernel"):
+    for key in ("sliced_entry_quad_kernel", "sliced_probe_kernel", "probe_kernel"):
         pl = [r for r in launches if key in r[col["Kernel Name"]] and (key != "probe_kernel" or "sliced" not in r[col["Kernel Name"]])]
         if pl and "dram__bytes_read.sum" in col:
             mean = sum(as_bytes(r, "dram__bytes_read.sum") + as_bytes(r, "dram__bytes_write.sum") for r in pl) / len(pl)
@@ -150,7 +158,9 @@ def cmd_summarise(tag):
             entry[key + "_launches"] = len(pl)
             print(f"  DRAM traffic per {key} launch: {mean / 1e9:.2f} GB over {len(pl)} launches")
     if entry:
-        entry["source"] = (f"profiles/{tag}_ncu_full_summary.csv (ncu --set full on bench.py --config {CONFIG}, dram__bytes_read.sum + "
+        forced = os.environ.get("PF_SLICED_FORCE_G")
+        entry["source"] = (f"profiles/{tag}_ncu_full_summary.csv (ncu --set full on bench.py --config {CONFIG}"
+                           + (f" with PF_SLICED_FORCE_G={forced}" if forced else "") + ", dram__bytes_read.sum + "
                            "dram__bytes_write.sum, mean over that kernel's launches of one step)")
         tj[CONFIG] = entry
         json.dump(tj, open(tpath, "w"), indent=1)

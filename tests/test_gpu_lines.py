@@ -123,6 +123,26 @@ def test_threshold_edges(db):
     gt.set_mode(0)
 
 
+@pytest.mark.parametrize("k", [17, 24, 25, 32, 16, 33])
+def test_line_groups_other_kmer_sizes(oracle, tmp_path, k):
+    """The entry kernel hashes on the fly for 17 <= k <= 32 (every byte offset of the hash's suffix words) and reads
+    cached values otherwise."""
+    from phagefilter_b200 import BloomTree
+    from phagefilter_b200.synth import make_genomes
+    genomes = make_genomes(40, 10, seed=4242, len_lo=2000, len_hi=3000)
+    d = str(tmp_path / "db")
+    ot = oracle_build_db(oracle, genomes, k, d, largest=4000)
+    gt = BloomTree.load(d)
+    gt.set_tile_cols(32)
+    os.environ["PF_SLICED_FORCE_G"] = "4"
+    os.environ["PF_SLICED_FORCE_PRE"] = "1"
+    reads = _reads(genomes, 3000, 120, seed=k) + [genomes[0][1][:k], genomes[1][1][5:5 + k + 1], b"ACGTN" * 30,
+                                                 genomes[2][1][:33], genomes[2][1][:63], genomes[2][1][:64], genomes[2][1][:65]]
+    for theta in (0.9, 0.6):
+        _check(ot, gt, reads, theta, case=f"k={k}")
+    gt.close()
+
+
 def test_line_kernel_was_exercised():
     """The cases above are only worth something if the line kernel took part in most of them."""
     import json
@@ -130,4 +150,5 @@ def test_line_kernel_was_exercised():
     with open("gpurun_out/lines_cases.json", "w") as f:
         json.dump(USED, f, indent=1)
     used = [k for k, v in USED.items() if v > 0]
-    assert len(used) >= len(USED) // 2 and len(used) >= 8, USED
+    assert len(used) >= 30, USED
+    assert sum(1 for k in used if k.startswith("k=")) >= 12, USED
