@@ -793,19 +793,29 @@ static void launch_sliced(const SlicedArgs &a, int sm_count, bool lean, cudaStre
     }
 }
 
+template <bool FUSE, int CTAS>
+static void launch_quad_c(const SlicedArgs &a, uint64_t max_kmers, uint32_t n_entry, uint32_t n_groups, int sm_count, cudaStream_t s) {
+    const int grid = sm_count * CTAS;
+    if (max_kmers < 256) {
+        if (a.hp.small_m) sliced_entry_quad_kernel<8, true, FUSE, CTAS><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        else sliced_entry_quad_kernel<8, false, FUSE, CTAS><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+    } else if (max_kmers < 65536) {
+        if (a.hp.small_m) sliced_entry_quad_kernel<16, true, FUSE, 3><<<sm_count * 3, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        else sliced_entry_quad_kernel<16, false, FUSE, 3><<<sm_count * 3, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+    } else {
+        if (a.hp.small_m) sliced_entry_quad_kernel<32, true, FUSE, 3><<<sm_count * 3, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+        else sliced_entry_quad_kernel<32, false, FUSE, 3><<<sm_count * 3, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
+    }
+}
+// Short reads (8 count planes): 4 CTAs per SM.  The kernel is latency-bound (ncu on cfg3: 24 warps per SM at 3 CTAs, 7 of
+// them waiting on the gathers per issue, DRAM pipe a third busy), so resident warps win over registers: 28.2 ms per cfg3
+// step at 4 CTAs (64 registers, ~100 B spilled), 30.0 at 3, 35.6 at 2 (PF_QUAD_CTAS=3 for the A/B).  Working out the next
+// round's row indices while the lines are on their way was tried and is slower (30.4 ms: more live registers).
 template <bool FUSE>
 static void launch_quad(const SlicedArgs &a, uint64_t max_kmers, uint32_t n_entry, uint32_t n_groups, int sm_count, cudaStream_t s) {
-    const int grid = sm_count * 3;
-    if (max_kmers < 256) {
-        if (a.hp.small_m) sliced_entry_quad_kernel<8, true, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
-        else sliced_entry_quad_kernel<8, false, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
-    } else if (max_kmers < 65536) {
-        if (a.hp.small_m) sliced_entry_quad_kernel<16, true, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
-        else sliced_entry_quad_kernel<16, false, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
-    } else {
-        if (a.hp.small_m) sliced_entry_quad_kernel<32, true, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
-        else sliced_entry_quad_kernel<32, false, FUSE><<<grid, SL_THREADS, 0, s>>>(a, n_entry, n_groups);
-    }
+    static const int ctas = getenv("PF_QUAD_CTAS") ? atoi(getenv("PF_QUAD_CTAS")) : 4;
+    if (ctas == 3) launch_quad_c<FUSE, 3>(a, max_kmers, n_entry, n_groups, sm_count, s);
+    else launch_quad_c<FUSE, 4>(a, max_kmers, n_entry, n_groups, sm_count, s);
 }
 
 // The entry depth can make its hash values itself when every entry tile goes through the line kernel and k fits the 2-bit

@@ -654,8 +654,8 @@ PF_D void sl_quad_count(const uint32_t (&x)[4][8], uint32_t lane, uint32_t (&cnt
 // FUSE: the hash values are not read from the cache but made on the spot from the 2-bit read (17 <= k <= 32; reads with
 // other bytes than ACGT were hashed beforehand and keep the cached path) -- nine reads in ten leave after two or three
 // rounds, so most of the batch is never hashed completely nor written to and read back from HBM.
-template <int PW, bool SMALL_M, bool FUSE>
-static __global__ void __launch_bounds__(SL_THREADS, 3) sliced_entry_quad_kernel(const SlicedArgs a, uint32_t n_entry,
+template <int PW, bool SMALL_M, bool FUSE, int CTAS>
+static __global__ void __launch_bounds__(SL_THREADS, CTAS) sliced_entry_quad_kernel(const SlicedArgs a, uint32_t n_entry,
                                                                                   uint32_t n_groups) {
     __shared__ uint32_t s_bits_all[SL_THREADS / 32][8];
     const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, q = lane >> 2;
@@ -666,6 +666,10 @@ static __global__ void __launch_bounds__(SL_THREADS, 3) sliced_entry_quad_kernel
     const uint32_t M0 = (uint32_t)hp.M, M1 = (uint32_t)(hp.M >> 32), m32 = (uint32_t)hp.m;
     unsigned long long lines_total = 0ULL;
     const uint32_t n_items = a.n_chunk * n_groups;  // item = group * n_chunk + read: group-major like the tile-major pairs
+    // what this lane keeps of its group's tile records (items are group-major: reloaded only when the group changes)
+    uint32_t cur_grp = NONE32_D, valid_mine = 0u, term_mine = 0u;
+    bool two = false;
+    const uint32_t *__restrict__ slot = nullptr;
     for (;;) {
         uint32_t g0 = 0;
         if (lane == 0) g0 = atomicAdd(a.work_ctr, a.grab);
@@ -678,49 +682,62 @@ static __global__ void __launch_bounds__(SL_THREADS, 3) sliced_entry_quad_kernel
             const uint32_t n_k = kmers_of(ldg32(a.lengths + r), hp.k);
             const uint32_t need = need_of(a.threshold, n_k);
             if (need > n_k) continue;  // theta > 1: nothing can pass
-            const uint64_t *__restrict__ hbp = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
             bool on_the_fly = false;
+            if (FUSE) on_the_fly = !a.exc_index || ldg32(a.exc_index + r) == NONE32_D;
+            // cached hash values (not FUSE, or a read with bytes other than ACGT) ...
+            const uint64_t *__restrict__ hbp = nullptr;
+            if (!on_the_fly) hbp = a.hb + (__ldg(a.kmer_off + r) - a.kmer_base);
+            // ... or the 2-bit read itself: lane l keeps 64-bit word wb + l of it, rounds take their two words by shuffle
             const uint64_t *w64 = nullptr;
-            uint64_t lo = 0ULL;
-            if (FUSE) {
-                on_the_fly = !a.exc_index || ldg32(a.exc_index + r) == NONE32_D;
-                if (on_the_fly && n_k != 0u) {
-                    w64 = reinterpret_cast<const uint64_t *>(a.packed + __ldg(a.word_off + r));
-                    lo = __ldg(w64);
-                }
+            uint64_t wv = 0ULL;
+            uint32_t n_w = 0u;  // words the rounds will ask for: 0 .. ((n_k - 1) >> 5) + 1
+            if (FUSE && on_the_fly && n_k != 0u) {
+                w64 = reinterpret_cast<const uint64_t *>(a.packed + __ldg(a.word_off + r));
+                n_w = ((n_k - 1u) >> 5) + 2u;
+                if (lane < n_w) wv = __ldg(w64 + lane);
             }
-            const bool tile_on = sub < ne;
-            const SlicedTileDev *tm_mine = a.tiles + ldg32(a.entry_tiles + e0 + (tile_on ? sub : 0u));
-            uint32_t alive = tile_on ? tm_mine->valid[my_word] : 0u;
-            const uint32_t term_mine = tile_on ? tm_mine->terminal[my_word] : 0u;
-            // a second probe step for every tile of the group as soon as one asks for it (more steps are never unsound)
-            const bool two = __any_sync(0xFFFFFFFFu, tile_on && tm_mine->pre_steps > 1u);
-            const uint32_t *__restrict__ slot = a.tables + (a.tiles + ldg32(a.entry_tiles + e0))->table_off + sub * 8u;
+            if (grp != cur_grp) {
+                cur_grp = grp;
+                const bool tile_on = sub < ne;
+                const SlicedTileDev *tm_mine = a.tiles + ldg32(a.entry_tiles + e0 + (tile_on ? sub : 0u));
+                valid_mine = tile_on ? tm_mine->valid[my_word] : 0u;
+                term_mine = tile_on ? tm_mine->terminal[my_word] : 0u;
+                // a second probe step for every tile of the group as soon as one asks for it (more steps are never unsound)
+                two = __any_sync(0xFFFFFFFFu, tile_on && tm_mine->pre_steps > 1u);
+                slot = a.tables + (a.tiles + ldg32(a.entry_tiles + e0))->table_off + sub * 8u;
+            }
+            uint32_t alive = valid_mine;
             uint32_t acc[PW];
 #pragma unroll
             for (int pl = 0; pl < PW; ++pl) acc[pl] = 0u;
             uint32_t live = __ballot_sync(0xFFFFFFFFu, (alive & term_mine) != 0u);  // lanes whose word still holds a terminal
             if (n_k != 0u && need != 0u) {  // need == 0: every column passes (query.rs:48)
-                for (uint32_t base = 0; base < n_k && live; base += 32u) {
-                    const bool have = base + lane < n_k;
+                // row indices of the k-mer this lane owns in the round that starts at k-mer `base` (warp-uniform call)
+                auto round_indices = [&](uint32_t base, uint64_t &i0, uint64_t &i1) {
                     uint64_t hbv;
                     if (FUSE && on_the_fly) {  // as hash_kernel: the 32 bases from position base + lane on, canonical, hashed
-                        const uint64_t hi = __ldg(w64 + (base >> 5) + 1);
+                        const uint32_t wi = base >> 5, wb = (wi / 31u) * 31u;  // lanes hold words wb .. wb + 31; a round needs wi, wi + 1
+                        if (wi == wb && wi != 0u) wv = wb + lane < n_w ? __ldg(w64 + wb + lane) : 0ULL;
+                        const uint64_t lo = __shfl_sync(0xFFFFFFFFu, (unsigned long long)wv, wi - wb);
+                        const uint64_t hi = __shfl_sync(0xFFFFFFFFu, (unsigned long long)wv, wi - wb + 1u);
                         const uint32_t sh = 2u * lane;
                         hbv = canonical_hash_2bit_rt((lo >> sh) | ((hi << 1) << (63u - sh)), hp.k);
-                        lo = hi;
                     } else {
-                        hbv = have ? sl_ld_stream(hbp + base + lane) : 0ULL;
+                        hbv = base + lane < n_k ? sl_ld_stream(hbp + base + lane) : 0ULL;
                     }
                     const uint64_t h1 = fx_finish(hp.c1, hbv, hp.rot);
-                    uint64_t i0, i1 = 0ULL;
                     if (SMALL_M) i0 = mod_small(h1, M0, M1, m32);
                     else i0 = mod_any(h1, hp.m, hp.M);
+                    i1 = 0ULL;
                     if (two) {
                         const uint64_t h2 = fx_finish(hp.c2, hbv, hp.rot);
                         if (SMALL_M) i1 = mod_small(h2, M0, M1, m32);
                         else i1 = mod_any(h2, hp.m, hp.M);
                     }
+                };
+                uint64_t i0 = 0ULL, i1 = 0ULL;
+                for (uint32_t base = 0; base < n_k && live; base += 32u) {
+                    round_indices(base, i0, i1);
                     const bool mine_live = (live & sub_lanes) != 0u;
                     uint32_t x[4][8];
 #pragma unroll
