@@ -511,6 +511,7 @@ def run_ours(args, cfg):
         n_launch = max(int(st.probe_launches), 1)
         sectors, sliced_ms, sliced_pairs = int(st.sector_loads), float(st.sliced_kernel_ms), int(st.sliced_pairs)
         lines = int(st.line_loads)  # 128-byte line loads of the entry line kernel (a row of up to four entry tiles each)
+        entry_ms = float(st.entry_kernel_ms)
         n_sliced_launch = max(int(st.sliced_launches), 1)  # one timed launch per tile-tree depth
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
         traffic, traffic_src = None, None
@@ -558,7 +559,16 @@ def run_ours(args, cfg):
                 "algorithmic_bytes_per_launch": alg_bytes / n_sliced_launch, "launches_per_step": n_sliced_launch // steps,
                 "avg_launch_ms": sliced_ms / n_sliced_launch,
                 "kernel_share_of_step": sliced_ms / float(st.device_ms) if st.device_ms else None,
-                "random_accesses_per_s": sect_rate, "sector_loads": sectors, "line_loads": lines,
+                "random_accesses_per_s": sect_rate,
+                "per_kernel": {
+                    "entry_depth (sliced_entry_quad_kernel when the entry tiles share lines)": {
+                        "ms_per_step": entry_ms / steps, "line_loads_per_step": lines // steps,
+                        "lines_per_s": lines / (entry_ms * 1e-3) if entry_ms > 0 and lines else None,
+                        "gbytes_per_s": 128 * lines / (entry_ms * 1e-3) / 1e9 if entry_ms > 0 and lines else None},
+                    "depths_below (sliced_probe_kernel)": {
+                        "ms_per_step": (sliced_ms - entry_ms) / steps,
+                        "sector_loads_per_step": (sectors // steps) if lines else None,
+                        "sectors_per_s": sectors / ((sliced_ms - entry_ms) * 1e-3) if lines and sliced_ms > entry_ms else None}},
                 "random_access_peak_per_s": peaks,
                 "frac_of_random_access_peak": sect_rate / rs_peak if rs_peak else None,
                 "tiles": int(st.sliced_tiles), "table_bytes": int(st.sliced_table_bytes),

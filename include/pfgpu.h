@@ -180,6 +180,7 @@ typedef struct pf_stats_t {
     double sliced_kernel_ms;  /* CUDA-event time of the sliced kernel's launches (`probe_kernel_ms`: the node-at-a-time kernel's) */
     uint64_t sliced_launches; /* timed launches of the sliced kernels (one per tile-tree depth; the entry depth may be two kernels timed as one) */
     uint64_t line_loads;      /* 128-byte line loads of the entry line kernel (one line = one row of up to four entry tiles); not in sector_loads */
+    double entry_kernel_ms;   /* the share of sliced_kernel_ms spent at the entry depth (every read against every entry tile) */
 } pf_stats_t;
 int pf_get_stats(pf_db *db, pf_stats_t *out);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can

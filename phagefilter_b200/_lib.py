@@ -58,7 +58,7 @@ class Stats(C.Structure):
         ("memo_hits", C.c_uint64), ("memo_lookups", C.c_uint64),
         ("sliced_blocks", C.c_uint64), ("sliced_tiles", C.c_uint64), ("sliced_table_bytes", C.c_uint64),
         ("chunk_splits", C.c_uint64), ("sector_loads", C.c_uint64), ("sliced_pairs", C.c_uint64),
-        ("sliced_kernel_ms", C.c_double), ("sliced_launches", C.c_uint64), ("line_loads", C.c_uint64),
+        ("sliced_kernel_ms", C.c_double), ("sliced_launches", C.c_uint64), ("line_loads", C.c_uint64), ("entry_kernel_ms", C.c_double),
     ]
 
 

@@ -742,6 +742,7 @@ void pf::account_stats(pf_db *db, const Descent &st, uint64_t n_reads, uint64_t 
         if (e / 2 < st.ev_sliced.size() && st.ev_sliced[e / 2]) {
             db->stats.sliced_kernel_ms += pm;
             db->stats.sliced_launches++;
+            if (st.ev_sliced[e / 2] == 2) db->stats.entry_kernel_ms += pm;
         }
         else {
             db->stats.probe_kernel_ms += pm;

@@ -917,7 +917,7 @@ int run_sliced(pf_db *db, const pf_dev_batch *bt, float threshold, int want_hits
         }
         PF_CUDA_OK(cudaEventRecord(db->ev_probe[st.n_ev + 1], s));
         st.n_ev += 2;
-        st.ev_sliced.push_back(1);
+        st.ev_sliced.push_back(entry ? 2 : 1);  // 2: the entry depth (line kernel and / or entry pairs)
         st.pairs += n;
         st.sliced_pairs += n;
         st.levels++;
