@@ -314,6 +314,17 @@ int pf_plan_tiles(uint64_t n_nodes, const uint32_t *left, const uint32_t *right,
                   const uint8_t *mono, uint64_t num_bits, uint32_t num_hashes, float threshold, uint64_t nominal_kmers,
                   int handover, uint8_t *skip_out, int32_t *node_tile_out, uint32_t *node_col_out, int32_t *tile_parent_out,
                   uint32_t *tile_width_out, uint64_t tile_cap, uint64_t *n_tiles_out, uint64_t *n_entry_out);
+/* The same plan -- with tiles of at most tile_cols columns (pf_db_set_tile_cols) -- and where its tables lie: per tile the
+ * first u32 word of its table, the words from one row to the next (32 when the tile shares 128-byte lines with up to three
+ * other entry tiles, else the words of a row), the words of a row, the line group (-1: a table of its own), the pre-test
+ * depth and whether the pre-test is all the tile does; the entry tiles in the order the kernels walk them (the first
+ * n_line_tiles share lines, four per group); the u32 words all tables take and the rows of one table. */
+int pf_plan_tile_layout(uint64_t n_nodes, const uint32_t *left, const uint32_t *right, const int32_t *leaf, const uint64_t *pop,
+                        const uint8_t *mono, uint64_t num_bits, uint32_t num_hashes, float threshold, uint64_t nominal_kmers,
+                        int handover, int tile_cols, uint64_t tile_cap, uint64_t *table_off_out, uint32_t *row_stride_out,
+                        uint32_t *row_words_out, int32_t *tile_group_out, uint32_t *pre_steps_out, uint8_t *filter_only_out,
+                        uint32_t *entry_order_out, uint64_t *n_tiles_out, uint64_t *n_entry_out, uint64_t *n_line_tiles_out,
+                        uint64_t *table_words_out, uint64_t *rows_out);
 
 /* ------------------------------------------------------------------------------------------
  * Roofline micro-benchmark: all SMs issue independent random 32-byte-sector loads over a

@@ -138,6 +138,12 @@ SYMBOLS = {
                                 C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_uint32),
                                 C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(C.c_uint64),
                                 C.POINTER(C.c_uint64)]),
+    "pf_plan_tile_layout": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.c_uint64, C.c_uint32, C.c_float, C.c_uint64,
+                                      C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                      C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8),
+                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

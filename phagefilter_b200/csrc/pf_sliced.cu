@@ -1031,16 +1031,8 @@ int sliced_set_hit_cursor(pf_db *db, uint64_t hits) {  // a chunk starts over (q
 }  // namespace pf
 
 // Host-only view of the tiling for tests (no device needed): the tree is given as level-ordered arrays.
-extern "C" int pf_plan_tiles(uint64_t n_nodes, const uint32_t *left, const uint32_t *right, const int32_t *leaf,
-                             const uint64_t *pop, const uint8_t *mono, uint64_t num_bits, uint32_t num_hashes,
-                             float threshold, uint64_t nominal_kmers, int handover, uint8_t *skip_out, int32_t *node_tile_out,
-                             uint32_t *node_col_out, int32_t *tile_parent_out, uint32_t *tile_width_out, uint64_t tile_cap,
-                             uint64_t *n_tiles_out, uint64_t *n_entry_out) {
-    if (!left || !right || !leaf || !pop || !mono || !n_tiles_out || n_nodes == 0 || num_bits == 0) {
-        pf::set_error("pf_plan_tiles: bad argument");
-        return PF_ERR_ARG;
-    }
-    pf_db db;
+static void host_db_from_arrays(pf_db &db, uint64_t n_nodes, const uint32_t *left, const uint32_t *right, const int32_t *leaf,
+                                const uint64_t *pop, const uint8_t *mono, uint64_t num_bits, uint32_t num_hashes) {
     db.n_nodes = n_nodes;
     db.h_left.assign(left, left + n_nodes);
     db.h_right.assign(right, right + n_nodes);
@@ -1065,6 +1057,19 @@ extern "C" int pf_plan_tiles(uint64_t n_nodes, const uint32_t *left, const uint3
         lo = hi;
         hi = nh;
     }
+}
+
+extern "C" int pf_plan_tiles(uint64_t n_nodes, const uint32_t *left, const uint32_t *right, const int32_t *leaf,
+                             const uint64_t *pop, const uint8_t *mono, uint64_t num_bits, uint32_t num_hashes,
+                             float threshold, uint64_t nominal_kmers, int handover, uint8_t *skip_out, int32_t *node_tile_out,
+                             uint32_t *node_col_out, int32_t *tile_parent_out, uint32_t *tile_width_out, uint64_t tile_cap,
+                             uint64_t *n_tiles_out, uint64_t *n_entry_out) {
+    if (!left || !right || !leaf || !pop || !mono || !n_tiles_out || n_nodes == 0 || num_bits == 0) {
+        pf::set_error("pf_plan_tiles: bad argument");
+        return PF_ERR_ARG;
+    }
+    pf_db db;
+    host_db_from_arrays(db, n_nodes, left, right, leaf, pop, mono, num_bits, num_hashes);
     pf::SlicedState S;
     S.hybrid = handover == 1;
     pf::plan_tiles(&db, threshold, nominal_kmers ? nominal_kmers : 1, S);
@@ -1083,5 +1088,45 @@ extern "C" int pf_plan_tiles(uint64_t n_nodes, const uint32_t *left, const uint3
     }
     *n_tiles_out = S.tiles.size();
     if (n_entry_out) *n_entry_out = S.entry_tiles.size();
+    return PF_OK;
+}
+
+// The same plan with narrower tiles if asked, and where its tables lie: per tile the first u32 word of its table, the
+// words from one row to the next, the words of a row, the group of entry tiles it shares 128-byte lines with (-1: a table
+// of its own), its pre-test depth and whether the pre-test is all it does; the entry tiles in the order the kernels walk
+// them (the first n_line_tiles share lines, SL_QUAD per group); the words all tables take.
+extern "C" int pf_plan_tile_layout(uint64_t n_nodes, const uint32_t *left, const uint32_t *right, const int32_t *leaf,
+                                   const uint64_t *pop, const uint8_t *mono, uint64_t num_bits, uint32_t num_hashes,
+                                   float threshold, uint64_t nominal_kmers, int handover, int tile_cols, uint64_t tile_cap,
+                                   uint64_t *table_off_out, uint32_t *row_stride_out, uint32_t *row_words_out,
+                                   int32_t *tile_group_out, uint32_t *pre_steps_out, uint8_t *filter_only_out,
+                                   uint32_t *entry_order_out, uint64_t *n_tiles_out, uint64_t *n_entry_out,
+                                   uint64_t *n_line_tiles_out, uint64_t *table_words_out, uint64_t *rows_out) {
+    if (!left || !right || !leaf || !pop || !mono || !n_tiles_out || n_nodes == 0 || num_bits == 0 ||
+        (tile_cols != 32 && tile_cols != 64 && tile_cols != 128 && tile_cols != 256)) {
+        pf::set_error("pf_plan_tile_layout: bad argument");
+        return PF_ERR_ARG;
+    }
+    pf_db db;
+    host_db_from_arrays(db, n_nodes, left, right, leaf, pop, mono, num_bits, num_hashes);
+    db.tile_cols = (uint32_t)tile_cols;
+    pf::SlicedState S;
+    S.hybrid = handover == 1;
+    pf::plan_tiles(&db, threshold, nominal_kmers ? nominal_kmers : 1, S);
+    for (size_t t = 0; t < S.tiles.size() && t < tile_cap; ++t) {
+        if (table_off_out) table_off_out[t] = S.tiles[t].table_off;
+        if (row_stride_out) row_stride_out[t] = S.tiles[t].row_stride;
+        if (row_words_out) row_words_out[t] = S.tiles[t].row_words;
+        if (tile_group_out) tile_group_out[t] = S.tile_group[t];
+        if (pre_steps_out) pre_steps_out[t] = S.tiles[t].pre_steps;
+        if (filter_only_out) filter_only_out[t] = (uint8_t)S.tiles[t].filter_only;
+    }
+    for (size_t e = 0; e < S.entry_tiles.size() && e < tile_cap; ++e)
+        if (entry_order_out) entry_order_out[e] = S.entry_tiles[e];
+    *n_tiles_out = S.tiles.size();
+    if (n_entry_out) *n_entry_out = S.entry_tiles.size();
+    if (n_line_tiles_out) *n_line_tiles_out = S.n_line_tiles;
+    if (table_words_out) *table_words_out = S.table_words;
+    if (rows_out) *rows_out = 64ULL * db.wpf;
     return PF_OK;
 }
