@@ -109,6 +109,27 @@ def test_line_groups_long_and_mixed_reads(db):
     gt.set_mode(0)
 
 
+def test_line_groups_chunked_batch(db):
+    """The batch in several hash-cache chunks, and chunks cut again because the (read, entry tile) pairs outgrow a tiny pair
+    index: the entry kernel hashes on the fly chunk by chunk and only each chunk's survivors get cached values."""
+    genomes, ot, gt = db
+    gt.set_tile_cols(32)
+    os.environ["PF_SLICED_FORCE_G"] = "4"
+    os.environ["PF_SLICED_FORCE_PRE"] = "1"
+    reads = _reads(genomes, 5000, 150, seed=21) + [b"ACGTN" * 40, genomes[9][1][:200].lower(), b"", b"ACGT"]
+    gt.set_hash_cache_bytes(12 * 131 * 700)  # ~700 reads per chunk
+    try:
+        _check(ot, gt, reads, 0.8, case="chunked")
+        gt.set_frontier_cap(3000)            # fewer pairs than a chunk's reads x entry tiles
+        _check(ot, gt, reads, 0.8, case="chunked, tiny pair index")
+        _check(ot, gt, reads, 1.0, case="chunked, tiny pair index")
+    finally:
+        gt.set_frontier_cap(0xFF000000)
+        gt.set_hash_cache_bytes(16 << 30)
+    gt.set_tile_cols(256)
+    gt.set_mode(0)
+
+
 def test_threshold_edges(db):
     """theta = 0 (every node passes), theta > 1 (nothing passes), with the line layout in place."""
     genomes, ot, gt = db
