@@ -13,6 +13,10 @@
 // produce).  Two shortcuts leave nodes out, both only where the load-time analysis VERIFIED that every (node, child)
 // pair below is a bitwise superset, i.e. "a leaf below passes => this node passes" (pf_sliced.cu: the skipped top of the
 // tree, and filter-only tiles whose sound pre-test is all they do).
+//
+// Rows that are lines: the tiles every read has to meet (the entry depth) lie four to a 128-byte line, because past the
+// TLB reach a random access costs this part the same whether it brings a sector or a line (scripts/mb/mb_coop.cu); the
+// kernel for that depth (sliced_entry_quad_kernel) also makes the k-mer hashes on the fly.  See DESIGN.md 4.2 and 5.
 #pragma once
 #include "pf_kernels.cuh"
 
