@@ -662,6 +662,9 @@ def run_ours(args, cfg):
                      "hits_last_step": n_hits,
                      "reference_semantics_probes_per_step": int(p_ref * args.reads),
                      "reference_semantics_pairs_per_step": int(pairs_ref * args.reads),
+                     # bloom probes per second under the REFERENCE's semantics -- the probes its descent would
+                     # have issued for these reads, divided by the time this path takes to give the same answers (all ranks)
+                     "reference_semantics_probes_per_s": p_ref * args.reads * world / (ms_all / steps * 1e-3) if ms_all > 0 else None,
                      "reference_semantics_sample": f"oracle on the first {n_sample} reads, scaled to the step",
                      "parity_check": {"reads": n_sample, "hits": int(len(cpu_hits)), "identical_to_oracle": parity_ok},
                      "db_build_s": round(build_s, 2), "db_open_s": round(open_s, 2), "warmup_s": round(warm_s, 2)},
